@@ -1,0 +1,33 @@
+"""The oracle (oracle/tls_oracle.c + the numpy restatement) against golden vectors
+produced by the reference's own numba path (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import assert_search_parity, load_search_golden, search_goldens
+from oracle import oracle
+
+
+@pytest.mark.parametrize("name", search_goldens())
+def test_c_oracle_matches_reference(name):
+    g = load_search_golden(name)
+    got = oracle.search_periods_c(g["t"], g["y"], g["dy"], g["periods"], g["templates"], g["params"])
+    # the oracle is held to a much tighter bar than the product: 1e-9 relative
+    assert_search_parity(got, g, rtol=1e-9, label=name)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "ties_unsorted", "ragged_L", "no_admissible"])
+def test_numpy_oracle_matches_reference(name):
+    g = load_search_golden(name)
+    idx = np.linspace(0, len(g["periods"]) - 1, 12).astype(int)
+    out = [oracle.search_period_numpy(g["periods"][k], g["t"], g["y"], g["dy"], g["templates"], g["params"]) for k in idx]
+    got = (np.array([o[0] for o in out]), np.array([o[1] for o in out]), np.array([o[2] for o in out]))
+    sub = dict(g, chi2=g["chi2"][idx], row=g["row"][idx], depth=g["depth"][idx])
+    assert_search_parity(got, sub, rtol=1e-9, label=name)
+
+
+def test_single_thread_equals_all_threads():
+    g = load_search_golden("small")
+    a = oracle.search_periods_c(g["t"], g["y"], g["dy"], g["periods"], g["templates"], g["params"], threads=1)
+    b = oracle.search_periods_c(g["t"], g["y"], g["dy"], g["periods"], g["templates"], g["params"], threads=0)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
