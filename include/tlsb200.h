@@ -1,0 +1,128 @@
+/*
+ * tlsb200.h — C ABI of the B200 (sm_100a) TLS period-search library (libtlsb200.so).
+ *
+ * The reference (hippke/tls 1.0.31) has no FFI/plugin interface; its seam for this
+ * path is the Python call
+ *     core.search_period(period, t, y, dy, transit_depth_min, R_star_min, R_star_max,
+ *                        M_star_min, M_star_max, lc_arr, lc_cache_overview, T0_fit_margin)
+ * (/root/reference/transitleastsquares/core.py:96-188) made once per trial period from
+ * main.py:142-160 (pool) and main.py:165-183 (serial).  Every argument except `period`
+ * is loop-invariant, so the replacement is ONE batched call per search.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer; the library
+ *     copies host->device and never keeps a host pointer after return;
+ *   - every function returns 0 on success or a negative tlsb_status; the message of
+ *     the last failure on the calling thread is tlsb_last_error();
+ *   - there is NO CPU fallback: without a CUDA device the calls fail with
+ *     TLSB_ERR_CUDA.
+ */
+#ifndef TLSB200_H
+#define TLSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    TLSB_OK = 0,
+    TLSB_ERR_ARG = -1,    /* bad argument (null pointer, n < 3, no templates, ...) */
+    TLSB_ERR_CUDA = -2,   /* CUDA runtime error or no device                       */
+    TLSB_ERR_ALLOC = -3,  /* host or device allocation failed                      */
+    TLSB_ERR_STATE = -4   /* handle used before its inputs were set                */
+} tlsb_status;
+
+/* The light curve after validate_inputs (validate.py:9-46): t, y, dy are f64[n], dy > 0.
+ * Replaces the t=, y=, dy= arguments of search_period (core.py:98-100). */
+typedef struct {
+    const double *t;
+    const double *y;
+    const double *dy;
+    int64_t n;
+} tlsb_lightcurve;
+
+/* The template bank, flattened.  Replaces lc_arr (ragged object array, transit.py:159)
+ * and lc_cache_overview (struct array {duration, width_in_samples, overshoot},
+ * transit.py:108-111) of search_period (core.py:106-107).  Row r owns
+ * signal[offset[r] .. offset[r]+length[r]) with length[r] <= width[r]. */
+typedef struct {
+    const double *signal;
+    const int64_t *offset;
+    const int64_t *length;
+    const int64_t *width;
+    const double *overshoot;
+    int64_t rows;
+} tlsb_templates;
+
+/* The scalar arguments of search_period (core.py:101-105,108). */
+typedef struct {
+    double transit_depth_min;
+    double R_star_min;
+    double R_star_max;
+    double M_star_min;
+    double M_star_max;
+    double T0_fit_margin;
+} tlsb_params;
+
+/* Where to run.  devices == NULL or n_devices <= 0 means "current device".  With
+ * several ordinals the periods are dealt round-robin to the GPUs by host threads of
+ * this one process (the one-process-per-GPU + NCCL path lives above the ABI, in
+ * tls_b200/distributed.py, and uses the handle API below). */
+typedef struct {
+    const int32_t *devices;
+    int32_t n_devices;
+} tlsb_exec;
+
+/*
+ * One search: replaces the whole period loop of main.py:140-185.
+ * Outputs are in the order of periods[] (main.py:190-196 sorts afterwards):
+ *   chi2_out[p]   = search_period(...)[1]   minimum chi^2, N if nothing was fitted,
+ *                                           +inf if no duration was admissible
+ *   row_out[p]    = search_period(...)[2]   row of the template bank
+ *   depth_out[p]  = search_period(...)[3]   1 - depth of the best model (0 if none)
+ *   t0_index_out  = optional (may be NULL): index into the phase-sorted samples of the
+ *                   window start of the best model, -1 if none.  The reference discards
+ *                   this (stats.py:136-138).
+ */
+int tlsb_search_periods(const tlsb_lightcurve *lc, const double *periods, int64_t n_periods,
+                        const tlsb_templates *tp, const tlsb_params *prm, const tlsb_exec *ex,
+                        double *chi2_out, int64_t *row_out, double *depth_out,
+                        int64_t *t0_index_out);
+
+/* ---- handle API: inputs stay resident in HBM across searches (multi-planet reruns,
+ * batches, benchmarking the kernels without the copies). ---- */
+typedef struct tlsb_handle tlsb_handle;
+
+int tlsb_create(tlsb_handle **out, int32_t device);
+int tlsb_destroy(tlsb_handle *h);
+/* host -> device; each may be called again to replace that input */
+int tlsb_set_lightcurve(tlsb_handle *h, const tlsb_lightcurve *lc);
+int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_params *prm);
+int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods);
+/* Launch the search kernels on `cuda_stream` (a cudaStream_t, NULL = default stream);
+ * asynchronous.  Results go to the handle's device buffer, or, when `records_dev` is not
+ * NULL, to that device buffer of 3*n_periods 8-byte words laid out as three planes:
+ * chi2 (f64), depth (f64), packed (int64: row in the low 32 bits, t0 index in the high). */
+int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev);
+/* Wait for the stream and copy the handle's own result buffer to the host. */
+int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_t *row_out,
+                     double *depth_out, int64_t *t0_index_out);
+/* Number of kernels this library launched for the most recent tlsb_search_async. */
+int64_t tlsb_last_launch_count(const tlsb_handle *h);
+/* Average device time [ms] per launch of the main search kernel between the CUDA events the
+ * library records around it on its launching stream (0 if nothing ran). Synchronises. */
+double tlsb_last_search_kernel_ms(tlsb_handle *h);
+/* 1 if the most recent search ran with the folded light curve resident in shared memory,
+ * 0 if it streamed it through global scratch. */
+int32_t tlsb_last_path_resident(const tlsb_handle *h);
+
+const char *tlsb_last_error(void);
+const char *tlsb_version(void);
+int32_t tlsb_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TLSB200_H */

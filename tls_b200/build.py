@@ -1,0 +1,52 @@
+"""Builds libtlsb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", "tlsb_search.cu")]
+HEADERS = [os.path.join(os.path.dirname(HERE), "include", "tlsb200.h")]
+LIB = os.path.join(HERE, "libtlsb200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+def nvcc_path():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libtlsb200.so cannot be built")
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    built = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > built for p in SRC + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force=False, verbose=False):
+    """Compile if the library is missing or older than its sources; returns the path."""
+    if not force and not is_stale():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRC
+    env = dict(os.environ)
+    env.pop("CC", None)   # the image exports a gcc wrapper that nvcc must not pick up
+    env.pop("CXX", None)
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,218 @@
+"""ctypes binding of libtlsb200.so (``include/tlsb200.h``) — the only way the
+package reaches the GPU.  There is deliberately no CPU fallback: every entry
+point raises ``RuntimeError`` if the library is missing or CUDA is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+EXPORTS = (
+    "tlsb_search_periods", "tlsb_create", "tlsb_destroy", "tlsb_set_lightcurve",
+    "tlsb_set_templates", "tlsb_set_periods", "tlsb_search_async", "tlsb_get_results",
+    "tlsb_last_launch_count", "tlsb_last_search_kernel_ms", "tlsb_last_path_resident",
+    "tlsb_last_error", "tlsb_version", "tlsb_device_count",
+)
+
+_c_i64 = ctypes.c_int64
+_c_vp = ctypes.c_void_p
+
+
+class LightCurve(ctypes.Structure):
+    _fields_ = [("t", _c_vp), ("y", _c_vp), ("dy", _c_vp), ("n", _c_i64)]
+
+
+class Templates(ctypes.Structure):
+    _fields_ = [("signal", _c_vp), ("offset", _c_vp), ("length", _c_vp), ("width", _c_vp),
+                ("overshoot", _c_vp), ("rows", _c_i64)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in (
+        "transit_depth_min", "R_star_min", "R_star_max", "M_star_min", "M_star_max", "T0_fit_margin")]
+
+
+class Exec(ctypes.Structure):
+    _fields_ = [("devices", _c_vp), ("n_devices", ctypes.c_int32)]
+
+
+def library_path():
+    return _build.LIB
+
+
+def lib():
+    """Load (building first if the sources are newer and nvcc is present)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this machine: use the shipped .so if there is one
+            if not os.path.exists(path):
+                raise RuntimeError("libtlsb200.so is missing and could not be built: %s" % exc)
+    L = ctypes.CDLL(path)
+    L.tlsb_last_error.restype = ctypes.c_char_p
+    L.tlsb_version.restype = ctypes.c_char_p
+    L.tlsb_device_count.restype = ctypes.c_int32
+    L.tlsb_last_launch_count.restype = _c_i64
+    L.tlsb_last_launch_count.argtypes = [_c_vp]
+    L.tlsb_last_search_kernel_ms.restype = ctypes.c_double
+    L.tlsb_last_search_kernel_ms.argtypes = [_c_vp]
+    L.tlsb_last_path_resident.restype = ctypes.c_int32
+    L.tlsb_last_path_resident.argtypes = [_c_vp]
+    L.tlsb_create.argtypes = [ctypes.POINTER(_c_vp), ctypes.c_int32]
+    L.tlsb_destroy.argtypes = [_c_vp]
+    L.tlsb_set_lightcurve.argtypes = [_c_vp, ctypes.POINTER(LightCurve)]
+    L.tlsb_set_templates.argtypes = [_c_vp, ctypes.POINTER(Templates), ctypes.POINTER(Params)]
+    L.tlsb_set_periods.argtypes = [_c_vp, _c_vp, _c_i64]
+    L.tlsb_search_async.argtypes = [_c_vp, _c_vp, _c_vp]
+    L.tlsb_get_results.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
+    L.tlsb_search_periods.argtypes = [
+        ctypes.POINTER(LightCurve), _c_vp, _c_i64, ctypes.POINTER(Templates), ctypes.POINTER(Params),
+        ctypes.POINTER(Exec), _c_vp, _c_vp, _c_vp, _c_vp]
+    _LIB = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().tlsb_last_error()
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_c_vp)
+
+
+class _Packed(object):
+    """Keeps the numpy buffers alive next to the ctypes structs that point into them."""
+
+    def __init__(self, t, y, dy, templates, params):
+        self.t, self.y, self.dy = _f64(t), _f64(y), _f64(dy)
+        if not (len(self.t) == len(self.y) == len(self.dy)):
+            raise ValueError("Arrays (t, y, dy) must be of the same dimensions")
+        self.signal = _f64(templates["signal"])
+        self.offset, self.length = _i64(templates["offset"]), _i64(templates["length"])
+        self.width, self.overshoot = _i64(templates["width"]), _f64(templates["overshoot"])
+        self.lc = LightCurve(_ptr(self.t), _ptr(self.y), _ptr(self.dy), len(self.t))
+        self.tp = Templates(_ptr(self.signal), _ptr(self.offset), _ptr(self.length),
+                            _ptr(self.width), _ptr(self.overshoot), len(self.width))
+        self.prm = Params(*[float(params[n]) for n, _ in Params._fields_])
+
+
+def device_count():
+    return int(lib().tlsb_device_count())
+
+
+def search_periods(t, y, dy, periods, templates, params, devices=None, return_t0_index=False):
+    """One batched search through ``tlsb_search_periods`` with HOST buffers.
+
+    Replaces the period loop of main.py:140-185.  Returns ``(chi2, row, depth)`` (and the
+    window-start index of the best model when asked) in the order of ``periods``."""
+    L = lib()
+    pk = _Packed(t, y, dy, templates, params)
+    periods = _f64(periods)
+    P = len(periods)
+    chi2 = np.empty(P, np.float64)
+    row = np.empty(P, np.int64)
+    depth = np.empty(P, np.float64)
+    t0 = np.empty(P, np.int64)
+    if devices is None:
+        ex = None
+    else:
+        devs = np.ascontiguousarray(np.atleast_1d(devices), dtype=np.int32)
+        ex = Exec(_ptr(devs), len(devs))
+    rc = L.tlsb_search_periods(ctypes.byref(pk.lc), _ptr(periods), P, ctypes.byref(pk.tp),
+                               ctypes.byref(pk.prm), ctypes.byref(ex) if ex is not None else None,
+                               _ptr(chi2), _ptr(row), _ptr(depth), _ptr(t0))
+    _check(rc, "tlsb_search_periods")
+    return (chi2, row, depth, t0) if return_t0_index else (chi2, row, depth)
+
+
+class Searcher(object):
+    """Handle API: inputs stay resident in HBM between searches."""
+
+    def __init__(self, device=-1):
+        self._h = _c_vp()
+        _check(lib().tlsb_create(ctypes.byref(self._h), int(device)), "tlsb_create")
+        self._keep = None
+        self.n_periods = 0
+
+    def close(self):
+        if self._h:
+            lib().tlsb_destroy(self._h)
+            self._h = _c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_inputs(self, t, y, dy, templates, params):
+        pk = _Packed(t, y, dy, templates, params)
+        _check(lib().tlsb_set_lightcurve(self._h, ctypes.byref(pk.lc)), "tlsb_set_lightcurve")
+        _check(lib().tlsb_set_templates(self._h, ctypes.byref(pk.tp), ctypes.byref(pk.prm)), "tlsb_set_templates")
+        self._keep = pk
+
+    def set_lightcurve(self, t, y, dy):
+        t, y, dy = _f64(t), _f64(y), _f64(dy)
+        lc = LightCurve(_ptr(t), _ptr(y), _ptr(dy), len(t))
+        _check(lib().tlsb_set_lightcurve(self._h, ctypes.byref(lc)), "tlsb_set_lightcurve")
+
+    def set_periods(self, periods):
+        periods = _f64(periods)
+        _check(lib().tlsb_set_periods(self._h, _ptr(periods), len(periods)), "tlsb_set_periods")
+        self.n_periods = len(periods)
+
+    def search_async(self, stream=None, records_ptr=None):
+        _check(lib().tlsb_search_async(self._h, _c_vp(stream or 0), _c_vp(records_ptr or 0)), "tlsb_search_async")
+
+    def results(self, stream=None):
+        P = self.n_periods
+        chi2 = np.empty(P, np.float64)
+        row = np.empty(P, np.int64)
+        depth = np.empty(P, np.float64)
+        t0 = np.empty(P, np.int64)
+        _check(lib().tlsb_get_results(self._h, _c_vp(stream or 0), _ptr(chi2), _ptr(row), _ptr(depth), _ptr(t0)),
+               "tlsb_get_results")
+        return chi2, row, depth, t0
+
+    @property
+    def launch_count(self):
+        return int(lib().tlsb_last_launch_count(self._h))
+
+    @property
+    def kernel_ms(self):
+        return float(lib().tlsb_last_search_kernel_ms(self._h))
+
+    @property
+    def resident(self):
+        return bool(lib().tlsb_last_path_resident(self._h))
+
+
+def unpack_records(records, n_periods):
+    """Split the 3-plane device record layout (chi2 | depth | row+t0<<32) copied to host."""
+    rec = np.asarray(records).reshape(3, n_periods)
+    chi2 = rec[0].view(np.float64)
+    depth = rec[1].view(np.float64)
+    packed = rec[2].view(np.int64)
+    row = (packed & 0xFFFFFFFF).astype(np.int64)
+    t0 = (packed >> 32).astype(np.int64)
+    return chi2, row, depth, t0
