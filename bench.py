@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py — trial-periods/sec of the TLS period x duration x T0 grid search on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1] [--impl reference]
+
+A "step" is one pass of the hot path (everything `core.search_period` does, for every
+trial period of the grid) over one synthetic light curve:
+
+* ``value``  — inputs resident in HBM, timed on the device with CUDA events around each
+  step (plan kernel + search kernel [+ the NCCL all-gather of the per-period records when
+  N > 1]); L2 is flushed between steps, outside the event brackets.
+* ``e2e``    — the same search through the reference-facing C-ABI call
+  ``tlsb_search_periods`` with HOST buffers (pinned), host<->device copies inside the
+  timed region, wall clock bracketed by device synchronisation.
+* multi-GPU  — weak scaling: every rank searches ``P`` periods of the same light curve; the
+  job's grid is the reference's period grid oversampled N x (``oversampling_factor = 3 N``),
+  dealt to the ranks round-robin (period k -> rank k mod N), one all-gather at the end of
+  each step.  value = all ranks' periods / max-over-ranks time.
+* ``--impl reference`` — the CPU implementation of the same path (the C restatement of the
+  reference under ``oracle/``, all host threads) on a bounded sample of the same workload.
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+METRIC = "trial-periods/sec (full duration x T0 scan)"
+UNIT = "periods/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg1", help="cfg1 (default, the config the metric is quoted on), "
+                    "tutorial01, cfg1_500ppm, cfg3, cfg2")
+    ap.add_argument("--max-periods", type=int, default=0, help="cap the periods per rank (0 = whole grid)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- workload
+def build_inputs(workload, oversampling):
+    from tls_b200 import transitleastsquares, workloads
+
+    t, y, dy, kw = workloads.lightcurve(workload)
+    kw = dict(kw)
+    kw["oversampling_factor"] = oversampling
+    return transitleastsquares(t, y, dy, verbose=False).prepare(verbose=False, **kw)
+
+
+def admissible_ranges(inp):
+    """Unique widths and, per period, how many are admissible (core.py:143-156) — used only to
+    count the algorithmic bytes of the roofline; the search itself plans on the device."""
+    from tls_b200.grid import T14
+
+    widths = np.asarray(inp.templates["width"])
+    uniq = np.unique(widths)
+    first_row = np.array([int(np.argmax(widths == w)) for w in uniq])
+    L = np.asarray(inp.templates["length"])[first_row]
+    N = len(inp.y)
+    span = float(np.max(inp.t) - np.min(inp.t))
+    prm = inp.params
+    return uniq, L, N, span, prm, T14
+
+
+def algorithmic_bytes(inp, periods):
+    """B(P) = 24 N + 8 (N+M) + sum_{W admissible} [8 (N+M) + 4 L_W] + 24 per period."""
+    uniq, L, N, span, prm, T14 = admissible_ranges(inp)
+    M = int(uniq.max())
+    M += M % 2
+    tile = 8.0 * (N + M) + 4.0 * L  # per unique width
+    ctile = np.concatenate([[0.0], np.cumsum(tile)])
+    total = 0.0
+    widths_total = 0
+    for p in periods:
+        dmax = T14(prm["R_star_max"], prm["M_star_max"], p, small=False)
+        dmin = T14(prm["R_star_min"], prm["M_star_min"], p, small=True)
+        naive = span / p
+        corr = (naive + 1) / naive
+        lo = np.searchsorted(uniq, np.floor(dmin * N), side="left")
+        hi = np.searchsorted(uniq, np.ceil(dmax * N * corr), side="right")
+        hi = max(hi, lo)
+        total += 24.0 * N + 8.0 * (N + M) + (ctile[hi] - ctile[lo]) + 24.0
+        widths_total += hi - lo
+    return total, widths_total / max(1, len(periods)), M
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    REASONS = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+        0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown",
+    }
+
+    def __init__(self, index, period_s=0.005):
+        super().__init__(daemon=True)
+        self.index, self.period_s = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period_s)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample(inp, periods, seconds, threads=0):
+    """Time the CPU oracle (all host threads) on an evenly spread sample of `periods` sized
+    for about `seconds` of wall time.  Returns (periods/s, sample size, threads)."""
+    from oracle import oracle
+
+    cores = oracle.host_threads() if threads == 0 else threads
+    probe = periods[np.linspace(0, len(periods) - 1, min(len(periods), 8 * cores)).astype(int)]
+    oracle.search_periods_c(inp.t, inp.y, inp.dy, probe[:cores], inp.templates, inp.params, threads=threads)  # warm
+    t0 = time.perf_counter()
+    oracle.search_periods_c(inp.t, inp.y, inp.dy, probe, inp.templates, inp.params, threads=threads)
+    rate = len(probe) / (time.perf_counter() - t0)
+    n = int(min(len(periods), max(len(probe), rate * seconds)))
+    sample = periods[np.linspace(0, len(periods) - 1, n).astype(int)]
+    t0 = time.perf_counter()
+    oracle.search_periods_c(inp.t, inp.y, inp.dy, sample, inp.templates, inp.params, threads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, cores
+
+
+def workload_config(args, inp, n_gpus, P_rank, P_total, oversampling):
+    return {
+        "workload": "%s: %s" % (args.workload, WORKLOAD_NOTES.get(args.workload, "")),
+        "n_points": int(len(inp.y)),
+        "periods_per_gpu": int(P_rank),
+        "periods_total": int(P_total),
+        "oversampling_factor": int(oversampling),
+        "template_rows": int(len(inp.templates["width"])),
+        "unique_widths": int(len(np.unique(inp.templates["width"]))),
+        "partition": "period k -> rank k mod %d" % n_gpus,
+        "l2": "flushed between steps (256 MiB write outside the timed events)",
+    }
+
+
+WORKLOAD_NOTES = {
+    "cfg1": "90 d @ 30 min synthetic (tutorial-01 planet), 50 ppm white noise, dy=None, default grids",
+    "tutorial01": "100 d @ 30 min synthetic of tutorial 01, 50 ppm, default grids",
+    "cfg1_500ppm": "cfg1 shape at 500 ppm",
+    "cfg3": "TESS 27 d @ 2 min, 500 ppm, duration_grid_step=1.02",
+    "cfg2": "Kepler-long 4 yr @ 30 min, 50 ppm, default grid",
+}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    oversampling = 3 * args.gpus
+    inp = build_inputs(args.workload, oversampling)
+    periods = inp.periods
+    if args.max_periods:
+        periods = periods[: args.max_periods * args.gpus]
+    from oracle import oracle
+
+    cores = oracle.host_threads()
+    # size one step for a few seconds of CPU work
+    rate, n0, _ = cpu_sample(inp, periods, 2.0)
+    per_step = int(min(len(periods), max(cores * 8, rate * 3.0)))
+    sample = periods[np.linspace(0, len(periods) - 1, per_step).astype(int)]
+    for _ in range(max(1, min(args.warmup, 3))):
+        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample[: max(cores * 4, per_step // 8)], inp.templates, inp.params)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample, inp.templates, inp.params)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    what = "%d of %d periods per step (evenly spread), C restatement of core.search_period, OpenMP" % (per_step, len(periods))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args, inp, args.gpus, len(periods) // args.gpus, len(periods), oversampling),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the search has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    if args.gpus != world and rank == 0 and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+    n_gpus = world
+
+    from tls_b200 import native
+    from tls_b200.distributed import ShardedSearch
+
+    oversampling = 3 * n_gpus
+    inp = build_inputs(args.workload, oversampling)
+    all_periods = inp.periods
+    if args.max_periods:
+        all_periods = all_periods[: args.max_periods * n_gpus]
+    job = ShardedSearch(inp.t, inp.y, inp.dy, inp.templates, inp.params, all_periods,
+                        rank=rank, world=world, device=local, dist=dist)
+    P_rank, P_total = job.n_local, len(all_periods)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs, CUDA events per step -------------------------------
+    for _ in range(max(3, args.warmup)):
+        flush.zero_()
+        job.step(stream)
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms, launches = [], 0
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        job.step(stream)
+        ev[k][1].record(stream)
+        launches += job.launch_count
+        kernel_ms.append(job.kernel_ms)  # the library's own events around the search kernel (synchronises)
+    barrier()
+    sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    value = P_total * args.steps / (total_ms * 1e-3)
+
+    # ---- parity spot check of what was just timed (rank 0, against the CPU oracle) ----------
+    chi2, row, depth, _t0 = job.local_results()
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle
+
+        sel = np.linspace(0, P_rank - 1, min(P_rank, 64)).astype(int)
+        w = oracle.search_periods_c(inp.t, inp.y, inp.dy, job.local_periods[sel], inp.templates, inp.params)
+        fin = np.isfinite(w[0])
+        parity = {
+            "periods_checked": int(len(sel)),
+            "rows_equal": bool(np.array_equal(row[sel], w[1])),
+            "chi2_max_rel_err": float(np.max(np.abs(chi2[sel][fin] - w[0][fin]) / np.abs(w[0][fin]))) if fin.any() else 0.0,
+        }
+
+    # ---- e2e: the C-ABI one-shot call with pinned host buffers ------------------------------
+    pin = {}
+    for name, arr in (("t", inp.t), ("y", inp.y), ("dy", inp.dy), ("periods", job.local_periods)):
+        tt = torch.from_numpy(np.ascontiguousarray(arr, np.float64).copy()).pin_memory()
+        pin[name] = (tt, tt.numpy())
+    h2d = 8 * (3 * len(inp.y) + P_rank) + sum(int(np.asarray(v).nbytes) for v in inp.templates.values())
+    d2h = 24 * P_rank
+
+    def e2e_step():
+        out = native.search_periods(pin["t"][1], pin["y"][1], pin["dy"][1], pin["periods"][1], inp.templates,
+                                    inp.params, devices=[local])
+        if dist is not None:
+            job.gather_host(out)
+        return out
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = P_total * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    peaks, peak_src = None, "fallback"
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+        peak_gbs, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        peak_gbs = 6650.0
+    roofline = cpu = None
+    if rank == 0:
+        alg_bytes, mean_widths, M = algorithmic_bytes(inp, job.local_periods)
+        k_ms = float(np.mean(kernel_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "traffic": None, "peak_source": peak_src, "kernel": "tlsb_search_kernel",
+            "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+            "algorithmic_bytes_per_period": alg_bytes / P_rank, "mean_admissible_widths": mean_widths,
+            "kernel_share_of_step": k_ms * args.steps / float(sum(step_ms)),
+            "path": "resident (folded curve in shared memory)" if job.resident else "streaming (per-CTA L2 scratch)",
+        }
+        traffic_file = os.path.join(REPO, "profiles", "traffic_%s.json" % args.workload)
+        if os.path.exists(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if not args.no_cpu_baseline:
+            rate, n, cores = cpu_sample(inp, job.local_periods, args.cpu_seconds)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d of %d periods (evenly spread) of the same workload, C restatement of "
+                             "core.search_period under oracle/, OpenMP over periods" % (n, P_rank)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, inp, n_gpus, P_rank, P_total, oversampling),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "call": "tlsb_search_periods (C ABI, host buffers)"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+            "cpu_baseline": cpu, "parity": parity,
+        }
+        print(json.dumps(line))
+    job.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

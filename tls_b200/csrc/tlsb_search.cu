@@ -825,19 +825,51 @@ double tlsb_last_search_kernel_ms(tlsb_handle *h)
     return (double)ms;
 }
 
+// The one-shot entry point keeps one handle per device alive between calls (device buffers,
+// events), so that a second search of similar size pays no cudaMalloc/cudaFree.
+static std::mutex g_pool_mutex;
+static std::vector<std::pair<int, tlsb_handle *>> g_pool;  // (device, idle handle)
+
+static tlsb_handle *pool_take(int device)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (size_t k = 0; k < g_pool.size(); ++k)
+        if (g_pool[k].first == device) {
+            tlsb_handle *h = g_pool[k].second;
+            g_pool.erase(g_pool.begin() + (long)k);
+            return h;
+        }
+    return nullptr;
+}
+
+static void pool_give(tlsb_handle *h)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pool.emplace_back(h->device, h);
+}
+
 static int search_on_device(int device, const tlsb_lightcurve *lc, const double *periods, int64_t nP,
                             const tlsb_templates *tp, const tlsb_params *prm, double *chi2, int64_t *row,
                             double *depth, int64_t *t0, std::string *err)
 {
-    tlsb_handle *h = nullptr;
-    int rc = tlsb_create(&h, device);
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        if (err) *err = "no CUDA device available (this library has no CPU fallback)";
+        g_error = *err;
+        return TLSB_ERR_CUDA;
+    }
+    tlsb_handle *h = pool_take(device);
+    int rc = h ? 0 : tlsb_create(&h, device);
     if (!rc) rc = tlsb_set_lightcurve(h, lc);
     if (!rc) rc = tlsb_set_templates(h, tp, prm);
     if (!rc) rc = tlsb_set_periods(h, periods, nP);
     if (!rc) rc = tlsb_search_async(h, nullptr, nullptr);
     if (!rc) rc = tlsb_get_results(h, nullptr, chi2, row, depth, t0);
     if (rc && err) *err = g_error;
-    tlsb_destroy(h);
+    if (rc)
+        tlsb_destroy(h);  // do not recycle a handle that failed
+    else
+        pool_give(h);
     return rc;
 }
 

@@ -1,0 +1,155 @@
+"""One process per GPU: shard the trial periods, search locally, all-gather the records.
+
+The reference parallelises the period loop with a process pool (main.py:140-163); periods
+are independent, so here period ``k`` goes to rank ``k mod world`` (interleaved: the cost per
+period drifts along the grid) and the only exchange is ONE all-gather of the
+per-period records ``{chi2 f64, depth f64, row i32 | t0_index i32}`` (24 bytes) at the end —
+NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests of this host logic.  There is no
+reduction: the SDE needs the whole chi2 array (stats.py:105-107).
+
+``torch`` is plumbing here (device buffers, streams, ``torch.distributed``); the search
+itself is the CUDA library behind ``include/tlsb200.h``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+WORDS_PER_PERIOD = 3  # chi2 | depth | packed(row, t0 index): three planes of 8-byte words
+
+
+def shard_indices(n_periods, rank, world):
+    """Indices of the periods rank ``rank`` searches (interleaved partition)."""
+    return np.arange(rank, n_periods, world)
+
+
+def shard_capacity(n_periods, world):
+    """Record slots per rank in the gathered buffer (the largest shard)."""
+    return (n_periods + world - 1) // world
+
+
+def pack_records(chi2, row, depth, t0_index, capacity):
+    """Host-side mirror of the kernel's record layout: int64[3 * capacity], three planes with
+    the plane stride equal to the shard's own period count (as the kernel writes them)."""
+    n = len(chi2)
+    out = np.zeros(WORDS_PER_PERIOD * capacity, dtype=np.int64)
+    out[0:n] = np.ascontiguousarray(chi2, np.float64).view(np.int64)
+    out[n:2 * n] = np.ascontiguousarray(depth, np.float64).view(np.int64)
+    packed = (np.asarray(row, np.int64) & 0xFFFFFFFF) | (np.asarray(t0_index, np.int64) << 32)
+    out[2 * n:3 * n] = packed
+    return out
+
+
+def unpack_gathered(gathered, n_periods, world):
+    """Undo the interleaved partition: ``gathered`` is int64[world * 3 * capacity] (rank-major).
+    Returns (chi2, row, depth, t0_index) in the order of the job's period list."""
+    cap = shard_capacity(n_periods, world)
+    g = np.asarray(gathered, dtype=np.int64).reshape(world, WORDS_PER_PERIOD * cap)
+    chi2 = np.empty(n_periods, np.float64)
+    depth = np.empty(n_periods, np.float64)
+    row = np.empty(n_periods, np.int64)
+    t0 = np.empty(n_periods, np.int64)
+    for r in range(world):
+        idx = shard_indices(n_periods, r, world)
+        n = len(idx)
+        chi2[idx] = g[r, 0:n].view(np.float64)
+        depth[idx] = g[r, n:2 * n].view(np.float64)
+        packed = g[r, 2 * n:3 * n]
+        row[idx] = packed & 0xFFFFFFFF
+        t0[idx] = packed >> 32
+    return chi2, row, depth, t0
+
+
+def all_gather_records(local_records, dist, world):
+    """One collective: every rank ends with all ranks' record buffers (rank-major)."""
+    import torch
+
+    out = torch.empty(world * local_records.numel(), dtype=local_records.dtype, device=local_records.device)
+    dist.all_gather_into_tensor(out, local_records)
+    return out
+
+
+class ShardedSearch(object):
+    """The period search of one light curve on ``world`` GPUs, one process per GPU.
+
+    ``step(stream)`` launches this rank's share (plan + search kernels) on ``stream`` and, when
+    ``world > 1``, the all-gather of the records behind it; everything is asynchronous."""
+
+    def __init__(self, t, y, dy, templates, params, periods, rank=0, world=1, device=0, dist=None):
+        import torch
+
+        from . import native
+
+        self.rank, self.world, self.dist = rank, world, dist
+        self.all_periods = np.ascontiguousarray(periods, np.float64)
+        self.index = shard_indices(len(self.all_periods), rank, world)
+        self.local_periods = np.ascontiguousarray(self.all_periods[self.index])
+        self.n_local = len(self.local_periods)
+        self.capacity = shard_capacity(len(self.all_periods), world)
+        self.searcher = native.Searcher(device=device)
+        self.searcher.set_inputs(t, y, dy, templates, params)
+        self.searcher.set_periods(self.local_periods)
+        self.records = torch.zeros(WORDS_PER_PERIOD * self.capacity, dtype=torch.int64, device="cuda:%d" % device)
+        self.gathered = None
+        if world > 1:
+            self.gathered = torch.empty(world * self.records.numel(), dtype=torch.int64, device=self.records.device)
+
+    def step(self, stream=None):
+        ptr = stream.cuda_stream if stream is not None else 0
+        self.searcher.search_async(stream=ptr, records_ptr=self.records.data_ptr())
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered, self.records)
+
+    @property
+    def launch_count(self):
+        return self.searcher.launch_count
+
+    @property
+    def kernel_ms(self):
+        return self.searcher.kernel_ms
+
+    @property
+    def resident(self):
+        return self.searcher.resident
+
+    def local_results(self):
+        """This rank's (chi2, row, depth, t0_index), in the order of ``local_periods``."""
+        from . import native
+
+        rec = self.records.cpu().numpy()
+        return native.unpack_records(rec[: WORDS_PER_PERIOD * self.n_local], self.n_local)
+
+    def results(self):
+        """All periods' (chi2, row, depth, t0_index) in the job's period order (every rank)."""
+        if self.world == 1:
+            return self.local_results()
+        return unpack_gathered(self.gathered.cpu().numpy(), len(self.all_periods), self.world)
+
+    def gather_host(self, local_out):
+        """All-gather host-side results (the e2e path: results already copied back)."""
+        import torch
+
+        chi2, row, depth = local_out[:3]
+        t0 = local_out[3] if len(local_out) > 3 else np.full(len(chi2), -1, np.int64)
+        rec = torch.from_numpy(pack_records(chi2, row, depth, t0, self.capacity)).to(self.records.device, non_blocking=False)
+        out = all_gather_records(rec, self.dist, self.world)
+        return unpack_gathered(out.cpu().numpy(), len(self.all_periods), self.world)
+
+    def close(self):
+        self.searcher.close()
+
+
+def search_periods_distributed(t, y, dy, periods, templates, params, dist, device=None):
+    """Drop-in for the period loop when ``torch.distributed`` is initialised with one process
+    per GPU: returns the full (chi2, row, depth) on every rank."""
+    import torch
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = torch.cuda.current_device()
+    job = ShardedSearch(t, y, dy, templates, params, periods, rank=rank, world=world, device=device, dist=dist)
+    try:
+        job.step(torch.cuda.current_stream(device))
+        chi2, row, depth, _ = job.results()
+    finally:
+        job.close()
+    return chi2, row, depth
