@@ -43,9 +43,12 @@
 
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kQueue = 64;            // per-warp survivor queue (offsets)
+constexpr int kBlock = 5;             // R: consecutive T0 candidates one lane carries through the tap loop
+                                      // (odd: neighbouring lanes sit R*stride doubles apart in shared memory)
+constexpr int kTile = 32 * kBlock;    // candidates one warp gates per scheduler grab
+constexpr int kQueue = 64;            // per-warp survivor queue (blocks)
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kSignalDepth = 0.5;  // tls_constants.py:71
@@ -68,23 +71,32 @@ int fail(int code, const std::string &msg)
 // ------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------
+// Per unique width (ascending), core.py:113 / :163-165.  One record so that a lane can fetch
+// everything about "its" width with a few shared-memory loads.
+struct WidthRec {
+    int W;        // width in samples
+    int L;        // template length L <= W
+    int X;        // T0 stride (core.py:50-55)
+    int row;      // first row of the bank with that width
+    int q;        // offset of the (zero padded) template in tq
+    int ncand;    // candidates: offsets i = c*X, c in [0, ncand)
+    int tiles;    // ceil(ncand / kTile)
+    int cum;      // tiles of all wider widths (the sweep runs wide -> narrow)
+    double os;    // overshoot
+    double invW;  // 1 / W
+};
+
 struct SearchArgs {
     // light curve, prepared once per curve by prepare_kernel
     const double *t;      // [N]
     const double *dval;   // [N] 1 - y
     const double *wval;   // [N] 1 / dy^2
     int N;
-    // template bank reduced to unique widths (ascending), core.py:113 / :163-165
-    const double *tq;     // flat q_j = (1 - signal_j) / SIGNAL_DEPTH
-    const int *uW;        // width in samples
-    const int *uL;        // template length L <= W
-    const int *uX;        // T0 stride (core.py:50-55)
-    const int *uRow;      // first row of the bank with that width
-    const int *uQ;        // offset of the template in tq
-    const double *uOS;    // overshoot
-    const double *uInvW;  // 1 / W
+    const double *tq;     // flat q_j = (1 - signal_j) / SIGNAL_DEPTH, each template zero padded
+    const WidthRec *rec;  // [nU]
     int nU;
     int M;                // patch length (max width, made even) core.py:114-116
+    int pad;              // readable slack behind the patched arrays (kBlock * max stride)
     // periods
     const double *periods;
     const int *ulo;       // [P] admissible unique-width index range [ulo, uhi)
@@ -178,6 +190,59 @@ __device__ __forceinline__ bool better(double c, int u, int i, const Best &b)
     return (c < b.chi2) || (c == b.chi2 && (u < b.u || (u == b.u && i < b.i)));
 }
 
+// The tap loop for one block of kBlock candidates of width record `wr`, window starts
+// i0 + r*X (r < kBlock).  With the stride X the taps split into X residue classes
+// j = X*a + b; inside one class candidate r at step m = a + r reads sample i0 + b + X*m, so
+// every staged sample (w, w*d) feeds all kBlock candidates and the template value loaded at
+// step m is reused from registers for the next kBlock-1 steps.  Templates are zero padded
+// in tq, so the ramp-in/ramp-out steps need no predicates.
+__device__ __forceinline__ void tap_block(const WidthRec &wr, const double *__restrict__ tq,
+                                          const double *__restrict__ w, const double *__restrict__ wd,
+                                          int i0, double (&A)[kBlock], double (&B)[kBlock])
+{
+    const int L = wr.L, X = wr.X;
+#pragma unroll
+    for (int r = 0; r < kBlock; ++r) { A[r] = 0.0; B[r] = 0.0; }
+    const int nb = X < L ? X : L;
+    for (int b = 0; b < nb; ++b) {
+        const int steps = (L - b + X - 1) / X + kBlock - 1;
+        const double *__restrict__ qp = tq + wr.q + b;
+        const double *__restrict__ wp = w + i0 + b;
+        const double *__restrict__ wdp = wd + i0 + b;
+        double qw[kBlock], pw[kBlock];  // circular: the value loaded at step m lives in slot m % kBlock
+#pragma unroll
+        for (int r = 0; r < kBlock; ++r) { qw[r] = 0.0; pw[r] = 0.0; }
+        for (int m0 = 0; m0 < steps; m0 += kBlock) {
+#pragma unroll
+            for (int mm = 0; mm < kBlock; ++mm) {
+                const int m = m0 + mm;
+                if (m < steps) {
+                    const double qk = __ldg(qp + (size_t)m * X);
+                    const double wv = wp[(size_t)m * X], wdv = wdp[(size_t)m * X];
+                    qw[mm] = qk;
+                    pw[mm] = qk * qk;
+#pragma unroll
+                    for (int r = 0; r < kBlock; ++r) {
+                        const int slot = (mm - r + kBlock) % kBlock;  // loaded r steps ago
+                        B[r] = fma(qw[slot], wdv, B[r]);
+                        A[r] = fma(pw[slot], wv, A[r]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Samples L..W-1 of a window are in neither the in-transit nor the out-of-transit sum when a
+// template was trimmed to L < W (rare: L == W for the limb-darkened templates).
+__device__ __noinline__ double untouched_tail(const double *w, const double *wd, int from, int to)
+{
+    double rest = 0.0;
+#pragma unroll 1
+    for (int k = from; k < to; ++k) rest += wd[k] * wd[k] / w[k];  // w d^2
+    return rest;
+}
+
 template <bool kResident>
 __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
 {
@@ -185,12 +250,13 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int N = a.N, M = a.M, NM = N + M, NB = a.NB;
+    const int N = a.N, M = a.M, NM = N + M, NB = a.NB, nU = a.nU;
+    const int NMP = NM + a.pad;
 
     // ---- carve memory ------------------------------------------------------------------
     // cs  : (NM+1) doubles  cumulative sums of d (cs[0] = 0)
-    // w   : NM doubles
-    // U   : union { wd : NM doubles } / { skey : N doubles, sid : N idx, slot : N idx [, hist] }
+    // w   : NMP doubles
+    // U   : union { wd : NMP doubles } / { skey : N doubles, sid : N idx, slot : N idx [, hist] }
     // hist: NB+1 ints  (inside U on the resident path, in shared memory on the streaming path)
     const size_t cs_elems = (size_t)(NM + 2) & ~(size_t)1;
     double *cs, *w, *wd, *skey;
@@ -200,20 +266,20 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
     if (kResident) {
         cs = reinterpret_cast<double *>(smem_raw);
         w = cs + cs_elems;
-        unsigned char *U = reinterpret_cast<unsigned char *>(w + NM);
+        unsigned char *U = reinterpret_cast<unsigned char *>(w + NMP);
         wd = reinterpret_cast<double *>(U);
         skey = reinterpret_cast<double *>(U);
         hist = reinterpret_cast<int *>(skey + N);
         sid = reinterpret_cast<idx_t *>(hist + NB + 1);
         slot = sid + N;
         size_t sort_bytes = (size_t)N * 8 + (size_t)(NB + 1) * 4 + (size_t)N * 2 * sizeof(idx_t);
-        size_t u_bytes = sort_bytes > (size_t)NM * 8 ? sort_bytes : (size_t)NM * 8;
+        size_t u_bytes = sort_bytes > (size_t)NMP * 8 ? sort_bytes : (size_t)NMP * 8;
         tail = U + ((u_bytes + 15) & ~(size_t)15);
     } else {
         unsigned char *g = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
         cs = reinterpret_cast<double *>(g);
         w = cs + cs_elems;
-        unsigned char *U = reinterpret_cast<unsigned char *>(w + NM);
+        unsigned char *U = reinterpret_cast<unsigned char *>(w + NMP);
         wd = reinterpret_cast<double *>(U);
         skey = reinterpret_cast<double *>(U);
         sid = reinterpret_cast<idx_t *>(skey + N);
@@ -221,17 +287,26 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
         hist = reinterpret_cast<int *>(smem_raw);
         tail = smem_raw + (((size_t)(NB + 1) * 4 + 15) & ~(size_t)15);
     }
-    double *red_d = reinterpret_cast<double *>(tail);          // [2*kWarps + 2]
-    int *red_i = reinterpret_cast<int *>(red_d + 2 * kWarps + 2);  // [2*kWarps]
-    int *queue = red_i + 2 * kWarps;                           // [kWarps*kQueue]
-    int *s_next = queue + kWarps * kQueue;                     // [1]
+    WidthRec *rec = reinterpret_cast<WidthRec *>(tail);                       // [nU]
+    double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kWarps + 2]
+    int *red_i = reinterpret_cast<int *>(red_d + 2 * kWarps + 2);             // [2*kWarps]
+    int2 *queue = reinterpret_cast<int2 *>(red_i + 2 * kWarps);               // [kWarps*kQueue]
+    int *s_next = reinterpret_cast<int *>(queue + kWarps * kQueue);           // [2] period slot, tile counter
+
+    for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kThreads)
+        reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
 
     const unsigned lt_mask = (1u << lane) - 1u;
+    const double depth_min = a.depth_min;
+    int2 *myq = queue + wid * kQueue;
 
     for (;;) {
-        if (tid == 0) *s_next = atomicAdd(a.counter, 1);
+        if (tid == 0) {
+            s_next[0] = atomicAdd(a.counter, 1);
+            s_next[1] = 0;
+        }
         __syncthreads();
-        const int slot_p = *s_next;
+        const int slot_p = s_next[0];
         if (slot_p >= a.P) break;
         const int p = a.order[slot_p];
         const double period = a.periods[p];
@@ -284,13 +359,18 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
         __syncthreads();  // sort scratch is dead from here; wd may overwrite it
         // wrap the first M samples to the end (core.py:126-132), build w*d, reduce T = sum w d^2
         double tpart = 0.0;
-        for (int k = tid; k < NM; k += kThreads) {
-            const int src = k < N ? k : k - N;
-            const double d = cs[src + 1], wv = w[src];
-            const double x = wv * d;
-            if (k >= N) { cs[k + 1] = d; w[k] = wv; }
-            wd[k] = x;
-            if (k < N) tpart = fma(x, d, tpart);
+        for (int k = tid; k < NMP; k += kThreads) {
+            if (k < NM) {
+                const int src = k < N ? k : k - N;
+                const double d = cs[src + 1], wv = w[src];
+                const double x = wv * d;
+                if (k >= N) { cs[k + 1] = d; w[k] = wv; }
+                wd[k] = x;
+                if (k < N) tpart = fma(x, d, tpart);
+            } else {  // slack read (never used) by partially valid candidate blocks
+                w[k] = 0.0;
+                wd[k] = 0.0;
+            }
         }
         if (tid == 0) cs[0] = 0.0;
 #pragma unroll
@@ -301,68 +381,81 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
         double T = 0.0;
         for (int k = 0; k < kWarps; ++k) T += red_d[kWarps + 1 + k];  // fixed order: deterministic
 
-        // ---- B. gate + survivor compaction + tap loop, one warp at a time ----------------
+        // ---- B. gate + survivor compaction + tap loop ----------------------------------------
+        // Warps grab tiles of kTile candidates of one width from a CTA-wide counter (wide
+        // widths first: the expensive tiles go out early), gate them from two cumulative-sum
+        // reads per candidate, ballot-compact the surviving blocks into a per-warp queue and
+        // run the tap loop only on full warps of survivors (the queue mixes widths freely).
         Best best;
         best.chi2 = (double)N;  // core.py:46: a model must beat N to count
         best.D = 0.0;
         best.u = -1;  // "no model yet": loses every tie, so a candidate must be strictly below N
         best.i = -1;
-        int *myq = queue + wid * kQueue;
-        const double depth_min = a.depth_min;
+        int qn = 0;
 
-        for (int u = ulo; u < uhi; ++u) {
-            const int W = a.uW[u], L = a.uL[u], xth = a.uX[u];
-            const double os = a.uOS[u], invW = a.uInvW[u];
-            const double *__restrict__ q = a.tq + a.uQ[u];
-            const int ncand = (NM - W) / xth + 1;  // offsets i = c*xth, i in [0, NM-W]
-            int qn = 0;
-
-            auto run_taps = [&](int i, bool active) {
-                if (!active) return;
-                const double mean = (cs[i + W] - cs[i]) * invW;
-                const double D = mean * os;
-                double A = 0.0, B = 0.0;
-                const double *wp = w + i, *wdp = wd + i;
-#pragma unroll 4
-                for (int j = 0; j < L; ++j) {
-                    const double qj = __ldg(q + j);
-                    B = fma(qj, wdp[j], B);
-                    A = fma(qj * qj, wp[j], A);
-                }
-                double chi = T + D * (D * A - 2.0 * B);
-                if (L < W) {  // samples L..W-1 of the window are in neither sum
-                    double rest = 0.0;
-                    for (int k = L; k < W; ++k) rest += wdp[k] * wdp[k] / wp[k];
-                    chi -= rest;
-                }
-                if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
-            };
-
-            for (int g = wid; g * 32 < ncand; g += kWarps) {
-                const int c = g * 32 + lane;
-                const int i = c * xth;
-                bool pass = false;
-                if (c < ncand) {
-                    const double mean = (cs[i + W] - cs[i]) * invW;
-                    pass = mean > depth_min;  // core.py:58 (the stride is built into c)
-                }
-                const unsigned m = __ballot_sync(kFull, pass);
-                if (pass) myq[qn + __popc(m & lt_mask)] = i;
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    run_taps(myq[lane], true);
-                    const int rem = qn - 32;
-                    int v = 0;
-                    if (lane < rem) v = myq[32 + lane];
-                    __syncwarp();
-                    if (lane < rem) myq[lane] = v;
-                    __syncwarp();
-                    qn = rem;
+        auto run_taps = [&](int2 e, bool active) {
+            if (!active) return;
+            const int u = e.y & 0xffff, mask = e.y >> 16;
+            const WidthRec wr = rec[u];
+            const int i0 = e.x * wr.X;
+            double A[kBlock], B[kBlock];
+            tap_block(wr, a.tq, w, wd, i0, A, B);
+#pragma unroll
+            for (int rr = 0; rr < kBlock; ++rr) {
+                if (mask & (1 << rr)) {
+                    const int i = i0 + rr * wr.X;
+                    const double mean = (cs[i + wr.W] - cs[i]) * wr.invW;
+                    const double D = mean * wr.os;
+                    double chi = T + D * (D * A[rr] - 2.0 * B[rr]);
+                    if (wr.L < wr.W) chi -= untouched_tail(w, wd, i + wr.L, i + wr.W);
+                    if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
                 }
             }
-            if (qn > 0) run_taps(lane < qn ? myq[lane] : 0, lane < qn);
-            __syncwarp();
+        };
+
+        const int tile_base = rec[uhi - 1].cum;
+        const int tile_end = rec[ulo].cum + rec[ulo].tiles;
+        int cur_u = uhi - 1;
+        bool more = true;
+        while (more || qn > 0) {
+            if (more) {
+                int g = 0;
+                if (lane == 0) g = atomicAdd(&s_next[1], 1);
+                g = __shfl_sync(kFull, g, 0) + tile_base;
+                more = g < tile_end;
+                if (more) {
+                    while (g >= rec[cur_u].cum + rec[cur_u].tiles) --cur_u;
+                    const int u = cur_u;
+                    const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
+                    const double invW = rec[u].invW;
+                    const int c0 = (g - rec[u].cum) * kTile + lane * kBlock;
+                    int mask = 0;
+#pragma unroll
+                    for (int rr = 0; rr < kBlock; ++rr) {
+                        const int c = c0 + rr;
+                        if (c < ncand) {
+                            const int i = c * X;
+                            const double mean = (cs[i + W] - cs[i]) * invW;
+                            if (mean > depth_min) mask |= 1 << rr;  // core.py:58 (the stride is built into c)
+                        }
+                    }
+                    const unsigned m = __ballot_sync(kFull, mask != 0);
+                    if (mask) myq[qn + __popc(m & lt_mask)] = make_int2(c0, u | (mask << 16));
+                    qn += __popc(m);
+                    __syncwarp();
+                }
+            }
+            if (qn >= 32 || (!more && qn > 0)) {  // a full warp of survivors, or the last partial one
+                const int take = qn < 32 ? qn : 32;
+                run_taps(lane < take ? myq[lane] : make_int2(0, 0), lane < take);
+                const int rem = qn - take;
+                int2 v = make_int2(0, 0);
+                if (lane < rem) v = myq[32 + lane];
+                __syncwarp();
+                if (lane < rem) myq[lane] = v;
+                __syncwarp();
+                qn = rem;
+            }
         }
 
         // ---- C. block arg-min with the reference's tie order ---------------------------
@@ -385,10 +478,13 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
         __syncthreads();
         if (wid == 0) {
             Best b2;
-            b2.chi2 = red_d[lane];
-            b2.D = red_d[kWarps + lane];
-            b2.u = red_i[lane];
-            b2.i = red_i[kWarps + lane];
+            b2.chi2 = (double)N; b2.D = 0.0; b2.u = -1; b2.i = -1;
+            if (lane < kWarps) {
+                b2.chi2 = red_d[lane];
+                b2.D = red_d[kWarps + lane];
+                b2.u = red_i[lane];
+                b2.i = red_i[kWarps + lane];
+            }
 #pragma unroll
             for (int off = 16; off; off >>= 1) {
                 Best o;
@@ -402,11 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
                 if (b2.u >= 0) {
                     a.out_chi2[p] = b2.chi2;
                     a.out_depth[p] = 1.0 - b2.D;  // core.py:74
-                    a.out_packed[p] = (long long)(unsigned)a.uRow[b2.u] | ((long long)b2.i << 32);
+                    a.out_packed[p] = (long long)(unsigned)rec[b2.u].row | ((long long)b2.i << 32);
                 } else {  // every duration returned the sentinel: first admissible row, depth 0
                     a.out_chi2[p] = (double)N;
                     a.out_depth[p] = 0.0;
-                    a.out_packed[p] = (long long)(unsigned)a.uRow[ulo] | ((long long)(unsigned)-1 << 32);
+                    a.out_packed[p] = (long long)(unsigned)rec[ulo].row | ((long long)(unsigned)-1 << 32);
                 }
             }
         }
@@ -490,10 +586,9 @@ struct tlsb_handle {
     bool have_lc = false;
     // templates
     tlsb_params prm{};
-    int nU = 0, M = 0;
-    std::vector<int> uW, uL, uX, uRow, uQ;
-    std::vector<double> uOS, uInvW;
-    DevBuf tq, d_uW, d_uL, d_uX, d_uRow, d_uQ, d_uOS, d_uInvW;
+    int nU = 0, M = 0, pad = 0;
+    std::vector<WidthRec> recs;   // unique widths, ascending
+    DevBuf tq, d_rec;
     bool have_tp = false;
     // periods
     int P = 0;
@@ -523,6 +618,19 @@ int upload(DevBuf &buf, const void *src, size_t bytes, cudaStream_t s = nullptr)
 int refresh_periods(tlsb_handle *h)
 {
     const int P = h->P, N = h->N;
+    // candidates and scheduler tiles per width (depend on N + M), wide -> narrow prefix
+    int cum = 0;
+    for (int u = h->nU - 1; u >= 0; --u) {
+        WidthRec &wr = h->recs[u];
+        wr.ncand = (N + h->M - wr.W) / wr.X + 1;  // offsets i = c*X, i in [0, N+M-W]
+        wr.tiles = (wr.ncand + kTile - 1) / kTile;
+        wr.cum = cum;
+        cum += wr.tiles;
+    }
+    {
+        int rc0;
+        if ((rc0 = upload(h->d_rec, h->recs.data(), sizeof(WidthRec) * (size_t)h->nU))) return rc0;
+    }
     std::vector<int> lo(P), hi(P), order(P);
     for (int p = 0; p < P; ++p) {
         const double period = h->h_periods[p];
@@ -533,16 +641,19 @@ int refresh_periods(tlsb_handle *h)
         const double wmin_f = std::floor(dmin * (double)N);
         const double wmax_f = std::ceil(dmax * (double)N * corr);
         int a = 0;
-        while (a < h->nU && (double)h->uW[a] < wmin_f) ++a;
+        while (a < h->nU && (double)h->recs[a].W < wmin_f) ++a;
         int b = h->nU;
-        while (b > a && (double)h->uW[b - 1] > wmax_f) --b;
+        while (b > a && (double)h->recs[b - 1].W > wmax_f) --b;
         if (!(wmax_f >= wmin_f)) b = a;  // NaN / empty
         lo[p] = a;
         hi[p] = b;
     }
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int x, int y) { return (hi[x] - lo[x]) > (hi[y] - lo[y]); });
+    // most expensive first: cost ~ number of candidate tiles in the admissible range
+    auto cost = [&](int p) {
+        return hi[p] > lo[p] ? h->recs[lo[p]].cum + h->recs[lo[p]].tiles - h->recs[hi[p] - 1].cum : 0;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost(x) > cost(y); });
     int rc;
     if ((rc = upload(h->ulo, lo.data(), sizeof(int) * P))) return rc;
     if ((rc = upload(h->uhi, hi.data(), sizeof(int) * P))) return rc;
@@ -554,23 +665,26 @@ int refresh_periods(tlsb_handle *h)
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-size_t tail_bytes() { return (2 * kWarps + 2) * 8 + 2 * kWarps * 4 + kWarps * kQueue * 4 + 16; }
-
-size_t resident_smem_bytes(int N, int M, int NB)
+size_t tail_bytes(int nU)
 {
-    const size_t NM = (size_t)N + M;
-    const size_t cs = ((NM + 2) & ~(size_t)1) * 8, w = NM * 8;
-    const size_t sort_bytes = (size_t)N * 8 + (size_t)(NB + 1) * 4 + (size_t)N * 2 * 2;
-    const size_t u = std::max(sort_bytes, NM * 8);
-    return cs + w + align16(u) + tail_bytes();
+    return (size_t)nU * sizeof(WidthRec) + (2 * kWarps + 2) * 8 + 2 * kWarps * 4 + kWarps * kQueue * 8 + 16;
 }
 
-size_t streaming_scratch_bytes(int N, int M)
+size_t resident_smem_bytes(int N, int M, int pad, int NB, int nU)
 {
-    const size_t NM = (size_t)N + M;
-    const size_t cs = ((NM + 2) & ~(size_t)1) * 8, w = NM * 8;
+    const size_t NM = (size_t)N + M, NMP = NM + pad;
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8, w = NMP * 8;
+    const size_t sort_bytes = (size_t)N * 8 + (size_t)(NB + 1) * 4 + (size_t)N * 2 * 2;
+    const size_t u = std::max(sort_bytes, NMP * 8);
+    return cs + w + align16(u) + tail_bytes(nU);
+}
+
+size_t streaming_scratch_bytes(int N, int M, int pad)
+{
+    const size_t NM = (size_t)N + M, NMP = NM + pad;
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8, w = NMP * 8;
     const size_t sort_bytes = (size_t)N * 8 + (size_t)N * 2 * 4;
-    const size_t u = std::max(sort_bytes, NM * 8);
+    const size_t u = std::max(sort_bytes, NMP * 8);
     return (cs + w + align16(u) + 255) & ~(size_t)255;
 }
 
@@ -622,8 +736,7 @@ int tlsb_destroy(tlsb_handle *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_uW, &h->d_uL, &h->d_uX,
-                      &h->d_uRow, &h->d_uQ, &h->d_uOS, &h->d_uInvW, &h->periods, &h->ulo, &h->uhi,
+    for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo, &h->uhi,
                       &h->order, &h->out, &h->counter, &h->scratch})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -672,20 +785,23 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     std::sort(uniq.begin(), uniq.end());
     uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
     const int nU = (int)uniq.size();
-    h->uW.assign(nU, 0); h->uL.assign(nU, 0); h->uX.assign(nU, 1); h->uRow.assign(nU, 0);
-    h->uQ.assign(nU, 0); h->uOS.assign(nU, 0.0); h->uInvW.assign(nU, 0.0);
+    if (nU > 65535) return fail(TLSB_ERR_ARG, "tlsb_set_templates: more than 65535 distinct widths");
+    std::vector<WidthRec> recs(nU);
     std::vector<double> tq;
+    int xmax = 1;
     for (int u = 0; u < nU; ++u) {
         int r = 0;
         while (tp->width[r] != uniq[u]) ++r;
         const int64_t W = uniq[u], L = tp->length[r];
-        if (W < 1 || L < 1 || L > W) return fail(TLSB_ERR_ARG, "tlsb_set_templates: need 1 <= length <= width");
-        h->uW[u] = (int)W;
-        h->uL[u] = (int)L;
-        h->uRow[u] = r;
-        h->uQ[u] = (int)tq.size();
-        h->uOS[u] = tp->overshoot[r];
-        h->uInvW[u] = 1.0 / (double)W;
+        if (W < 1 || L < 1 || L > W || W > (int64_t)1 << 28)
+            return fail(TLSB_ERR_ARG, "tlsb_set_templates: need 1 <= length <= width");
+        WidthRec &wr = recs[u];
+        wr.W = (int)W;
+        wr.L = (int)L;
+        wr.row = r;
+        wr.q = (int)tq.size();
+        wr.os = tp->overshoot[r];
+        wr.invW = 1.0 / (double)W;
         // core.py:50-55 stride of the T0 scan
         int xth = 1;
         const double margin = prm->T0_fit_margin;
@@ -694,22 +810,22 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
             xth = (int)((double)W / inv_margin);
             if (xth < 1) xth = 1;
         }
-        h->uX[u] = xth;
+        wr.X = xth;
+        xmax = std::max(xmax, xth);
+        wr.ncand = 0;  // needs N: filled by refresh_periods
+        wr.tiles = 0;
+        wr.cum = 0;
         const double *s = tp->signal + tp->offset[r];
         for (int64_t j = 0; j < L; ++j) tq.push_back((1 - s[j]) / kSignalDepth);  // core.py:61-68
+        for (int j = 0; j < xth * (kBlock - 1); ++j) tq.push_back(0.0);           // ramp-out of tap_block
     }
-    int M = h->uW[nU - 1];  // core.py:114-116
+    int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
     int rc;
     if ((rc = upload(h->tq, tq.data(), tq.size() * 8))) return rc;
-    if ((rc = upload(h->d_uW, h->uW.data(), nU * 4))) return rc;
-    if ((rc = upload(h->d_uL, h->uL.data(), nU * 4))) return rc;
-    if ((rc = upload(h->d_uX, h->uX.data(), nU * 4))) return rc;
-    if ((rc = upload(h->d_uRow, h->uRow.data(), nU * 4))) return rc;
-    if ((rc = upload(h->d_uQ, h->uQ.data(), nU * 4))) return rc;
-    if ((rc = upload(h->d_uOS, h->uOS.data(), nU * 8))) return rc;
-    if ((rc = upload(h->d_uInvW, h->uInvW.data(), nU * 8))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->recs.swap(recs);
+    h->pad = (kBlock * xmax + 1) & ~1;
     h->nU = nU;
     h->M = M;
     h->prm = *prm;
@@ -753,9 +869,7 @@ int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
 
     SearchArgs a{};
     a.t = h->t.as<double>(); a.dval = h->dval.as<double>(); a.wval = h->wval.as<double>(); a.N = h->N;
-    a.tq = h->tq.as<double>(); a.uW = h->d_uW.as<int>(); a.uL = h->d_uL.as<int>(); a.uX = h->d_uX.as<int>();
-    a.uRow = h->d_uRow.as<int>(); a.uQ = h->d_uQ.as<int>(); a.uOS = h->d_uOS.as<double>();
-    a.uInvW = h->d_uInvW.as<double>(); a.nU = h->nU; a.M = h->M;
+    a.tq = h->tq.as<double>(); a.rec = h->d_rec.as<WidthRec>(); a.nU = h->nU; a.M = h->M; a.pad = h->pad;
     a.periods = h->periods.as<double>(); a.ulo = h->ulo.as<int>(); a.uhi = h->uhi.as<int>();
     a.order = h->order.as<int>(); a.P = h->P; a.depth_min = h->prm.transit_depth_min;
     a.out_chi2 = reinterpret_cast<double *>(records_dev);
@@ -764,7 +878,7 @@ int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
     a.counter = h->counter.as<int>();
 
     const int grid = std::min(h->P, h->num_sms);
-    const size_t need = resident_smem_bytes(h->N, h->M, h->N);
+    const size_t need = resident_smem_bytes(h->N, h->M, h->pad, h->N, h->nU);
     const bool resident = h->N < 65536 && need <= h->max_smem;
     h->resident = resident;
     CUDA_TRY(cudaEventRecord(h->ev0, s));
@@ -773,12 +887,13 @@ int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
         CUDA_TRY(cudaFuncSetAttribute(tlsb_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         tlsb_search_kernel<true><<<grid, kThreads, need, s>>>(a);
     } else {
-        const size_t budget = h->max_smem - tail_bytes() - 64;
+        if (tail_bytes(h->nU) + 4096 > h->max_smem) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
+        const size_t budget = h->max_smem - tail_bytes(h->nU) - 64;
         a.NB = (int)std::min<size_t>((size_t)h->N, budget / 4 - 2);
-        a.scratch_per_cta = streaming_scratch_bytes(h->N, h->M);
+        a.scratch_per_cta = streaming_scratch_bytes(h->N, h->M, h->pad);
         if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
         a.scratch = h->scratch.as<unsigned char>();
-        const size_t smem = align16((size_t)(a.NB + 1) * 4) + tail_bytes();
+        const size_t smem = align16((size_t)(a.NB + 1) * 4) + tail_bytes(h->nU);
         CUDA_TRY(cudaFuncSetAttribute(tlsb_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tlsb_search_kernel<false><<<grid, kThreads, smem, s>>>(a);
     }
