@@ -48,7 +48,8 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kBlock = 5;             // R: consecutive T0 candidates one lane carries through the tap loop
                                       // (odd: neighbouring lanes sit R*stride doubles apart in shared memory)
 constexpr int kTile = 32 * kBlock;    // candidates one warp gates per scheduler grab
-constexpr int kQueue = 64;            // per-warp survivor queue (blocks)
+constexpr int kQueue = 4096;          // CTA-wide survivor queue (blocks of kBlock candidates)
+constexpr int kQueueStop = kQueue - kWarps * 32;  // gating pauses here: every warp can still add a tile
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kSignalDepth = 0.5;  // tls_constants.py:71
@@ -84,6 +85,7 @@ struct WidthRec {
     int cum;      // tiles of all wider widths (the sweep runs wide -> narrow)
     double os;    // overshoot
     double invW;  // 1 / W
+    double sq2;   // sum_j q_j^2 (the quadratic term when all weights are equal)
 };
 
 struct SearchArgs {
@@ -109,6 +111,7 @@ struct SearchArgs {
     double *out_depth;
     long long *out_packed;
     // scheduling
+    double w0;            // the common weight 1/dy^2 when every dy is the same (dy=None), else unused
     int *counter;         // [2] next period, finished CTAs
     // streaming path scratch
     unsigned char *scratch;
@@ -194,41 +197,50 @@ __device__ __forceinline__ bool better(double c, int u, int i, const Best &b)
 // i0 + r*X (r < kBlock).  With the stride X the taps split into X residue classes
 // j = X*a + b; inside one class candidate r at step m = a + r reads sample i0 + b + X*m, so
 // every staged sample (w, w*d) feeds all kBlock candidates and the template value loaded at
-// step m is reused from registers for the next kBlock-1 steps.  Templates are zero padded
-// in tq, so the ramp-in/ramp-out steps need no predicates.
+// step m is reused from registers for the next kBlock-1 steps.  Steps go in unguarded groups
+// of kBlock (loads of a whole group can be in flight together): templates are zero padded in
+// tq and the patched arrays have slack behind them, so ramp-in/ramp-out need no predicates.
+// kUniformW: all weights equal (dy=None) -> only B = sum q_j (w d)_{i+j} is accumulated.
+template <bool kUnit, bool kUniformW>
 __device__ __forceinline__ void tap_block(const WidthRec &wr, const double *__restrict__ tq,
                                           const double *__restrict__ w, const double *__restrict__ wd,
                                           int i0, double (&A)[kBlock], double (&B)[kBlock])
 {
-    const int L = wr.L, X = wr.X;
+    const int L = wr.L, X = kUnit ? 1 : wr.X;
 #pragma unroll
     for (int r = 0; r < kBlock; ++r) { A[r] = 0.0; B[r] = 0.0; }
     const int nb = X < L ? X : L;
     for (int b = 0; b < nb; ++b) {
-        const int steps = (L - b + X - 1) / X + kBlock - 1;
+        const int groups = ((L - b + X - 1) / X + 2 * kBlock - 2) / kBlock;  // ceil((taps + kBlock-1) / kBlock)
         const double *__restrict__ qp = tq + wr.q + b;
         const double *__restrict__ wp = w + i0 + b;
         const double *__restrict__ wdp = wd + i0 + b;
         double qw[kBlock], pw[kBlock];  // circular: the value loaded at step m lives in slot m % kBlock
 #pragma unroll
         for (int r = 0; r < kBlock; ++r) { qw[r] = 0.0; pw[r] = 0.0; }
-        for (int m0 = 0; m0 < steps; m0 += kBlock) {
+#pragma unroll 1
+        for (int g = 0; g < groups; ++g) {
+            double qk[kBlock], wv[kBlock], wdv[kBlock];
 #pragma unroll
             for (int mm = 0; mm < kBlock; ++mm) {
-                const int m = m0 + mm;
-                if (m < steps) {
-                    const double qk = __ldg(qp + (size_t)m * X);
-                    const double wv = wp[(size_t)m * X], wdv = wdp[(size_t)m * X];
-                    qw[mm] = qk;
-                    pw[mm] = qk * qk;
+                qk[mm] = __ldg(qp + mm * X);
+                wdv[mm] = wdp[mm * X];
+                if (!kUniformW) wv[mm] = wp[mm * X];
+            }
 #pragma unroll
-                    for (int r = 0; r < kBlock; ++r) {
-                        const int slot = (mm - r + kBlock) % kBlock;  // loaded r steps ago
-                        B[r] = fma(qw[slot], wdv, B[r]);
-                        A[r] = fma(pw[slot], wv, A[r]);
-                    }
+            for (int mm = 0; mm < kBlock; ++mm) {
+                qw[mm] = qk[mm];
+                if (!kUniformW) pw[mm] = qk[mm] * qk[mm];
+#pragma unroll
+                for (int r = 0; r < kBlock; ++r) {
+                    const int slot = (mm - r + kBlock) % kBlock;  // loaded r steps ago
+                    B[r] = fma(qw[slot], wdv[mm], B[r]);
+                    if (!kUniformW) A[r] = fma(pw[slot], wv[mm], A[r]);
                 }
             }
+            qp += kBlock * X;
+            wp += kBlock * X;
+            wdp += kBlock * X;
         }
     }
 }
@@ -243,7 +255,7 @@ __device__ __noinline__ double untouched_tail(const double *w, const double *wd,
     return rest;
 }
 
-template <bool kResident>
+template <bool kResident, bool kUniformW>
 __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
 {
     using idx_t = typename std::conditional<kResident, unsigned short, unsigned int>::type;
@@ -290,20 +302,21 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
     WidthRec *rec = reinterpret_cast<WidthRec *>(tail);                       // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kWarps + 2]
     int *red_i = reinterpret_cast<int *>(red_d + 2 * kWarps + 2);             // [2*kWarps]
-    int2 *queue = reinterpret_cast<int2 *>(red_i + 2 * kWarps);               // [kWarps*kQueue]
-    int *s_next = reinterpret_cast<int *>(queue + kWarps * kQueue);           // [2] period slot, tile counter
+    int2 *queue = reinterpret_cast<int2 *>(red_i + 2 * kWarps);               // [kQueue]
+    int *s_next = reinterpret_cast<int *>(queue + kQueue);  // [4] period slot, tile counter, queue fill, queue head
 
     for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kThreads)
         reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
 
     const unsigned lt_mask = (1u << lane) - 1u;
     const double depth_min = a.depth_min;
-    int2 *myq = queue + wid * kQueue;
 
     for (;;) {
         if (tid == 0) {
             s_next[0] = atomicAdd(a.counter, 1);
             s_next[1] = 0;
+            s_next[2] = 0;
+            s_next[3] = 0;
         }
         __syncthreads();
         const int slot_p = s_next[0];
@@ -382,80 +395,89 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
         for (int k = 0; k < kWarps; ++k) T += red_d[kWarps + 1 + k];  // fixed order: deterministic
 
         // ---- B. gate + survivor compaction + tap loop ----------------------------------------
-        // Warps grab tiles of kTile candidates of one width from a CTA-wide counter (wide
-        // widths first: the expensive tiles go out early), gate them from two cumulative-sum
-        // reads per candidate, ballot-compact the surviving blocks into a per-warp queue and
-        // run the tap loop only on full warps of survivors (the queue mixes widths freely).
+        // B1: warps grab tiles of kTile candidates of one width from a CTA-wide counter (wide
+        //     widths first), gate them from two cumulative-sum reads per candidate and append
+        //     the surviving blocks to a CTA-wide queue (one reservation per tile, so a tile's
+        //     survivors stay together and the queue is nearly sorted by width).
+        // B2: warps grab 32 consecutive queue entries - almost always one width, so template
+        //     loads broadcast and the lanes run in lockstep - and run the tap loop.
+        // The queue is bounded; B1/B2 alternate until all tiles are gated.
         Best best;
         best.chi2 = (double)N;  // core.py:46: a model must beat N to count
         best.D = 0.0;
         best.u = -1;  // "no model yet": loses every tie, so a candidate must be strictly below N
         best.i = -1;
-        int qn = 0;
-
-        auto run_taps = [&](int2 e, bool active) {
-            if (!active) return;
-            const int u = e.y & 0xffff, mask = e.y >> 16;
-            const WidthRec wr = rec[u];
-            const int i0 = e.x * wr.X;
-            double A[kBlock], B[kBlock];
-            tap_block(wr, a.tq, w, wd, i0, A, B);
-#pragma unroll
-            for (int rr = 0; rr < kBlock; ++rr) {
-                if (mask & (1 << rr)) {
-                    const int i = i0 + rr * wr.X;
-                    const double mean = (cs[i + wr.W] - cs[i]) * wr.invW;
-                    const double D = mean * wr.os;
-                    double chi = T + D * (D * A[rr] - 2.0 * B[rr]);
-                    if (wr.L < wr.W) chi -= untouched_tail(w, wd, i + wr.L, i + wr.W);
-                    if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
-                }
-            }
-        };
 
         const int tile_base = rec[uhi - 1].cum;
         const int tile_end = rec[ulo].cum + rec[ulo].tiles;
         int cur_u = uhi - 1;
-        bool more = true;
-        while (more || qn > 0) {
-            if (more) {
-                int g = 0;
-                if (lane == 0) g = atomicAdd(&s_next[1], 1);
-                g = __shfl_sync(kFull, g, 0) + tile_base;
-                more = g < tile_end;
-                if (more) {
-                    while (g >= rec[cur_u].cum + rec[cur_u].tiles) --cur_u;
-                    const int u = cur_u;
-                    const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
-                    const double invW = rec[u].invW;
-                    const int c0 = (g - rec[u].cum) * kTile + lane * kBlock;
-                    int mask = 0;
+        for (;;) {
+            // B1
+            for (;;) {
+                int g = tile_end;
+                if (lane == 0 && *(volatile int *)&s_next[2] < kQueueStop) g = atomicAdd(&s_next[1], 1) + tile_base;
+                g = __shfl_sync(kFull, g, 0);
+                if (g >= tile_end) break;
+                while (g >= rec[cur_u].cum + rec[cur_u].tiles) --cur_u;
+                const int u = cur_u;
+                const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
+                const double invW = rec[u].invW;
+                const int c0 = (g - rec[u].cum) * kTile + lane * kBlock;
+                int mask = 0;
 #pragma unroll
-                    for (int rr = 0; rr < kBlock; ++rr) {
-                        const int c = c0 + rr;
-                        if (c < ncand) {
-                            const int i = c * X;
-                            const double mean = (cs[i + W] - cs[i]) * invW;
-                            if (mean > depth_min) mask |= 1 << rr;  // core.py:58 (the stride is built into c)
-                        }
+                for (int rr = 0; rr < kBlock; ++rr) {
+                    const int c = c0 + rr;
+                    if (c < ncand) {
+                        const int i = c * X;
+                        const double mean = (cs[i + W] - cs[i]) * invW;
+                        if (mean > depth_min) mask |= 1 << rr;  // core.py:58 (the stride is built into c)
                     }
-                    const unsigned m = __ballot_sync(kFull, mask != 0);
-                    if (mask) myq[qn + __popc(m & lt_mask)] = make_int2(c0, u | (mask << 16));
-                    qn += __popc(m);
-                    __syncwarp();
+                }
+                const unsigned m = __ballot_sync(kFull, mask != 0);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_next[2], __popc(m));
+                    base = __shfl_sync(kFull, base, 0);
+                    if (mask) queue[base + __popc(m & lt_mask)] = make_int2(c0, u | (mask << 16));
                 }
             }
-            if (qn >= 32 || (!more && qn > 0)) {  // a full warp of survivors, or the last partial one
-                const int take = qn < 32 ? qn : 32;
-                run_taps(lane < take ? myq[lane] : make_int2(0, 0), lane < take);
-                const int rem = qn - take;
-                int2 v = make_int2(0, 0);
-                if (lane < rem) v = myq[32 + lane];
-                __syncwarp();
-                if (lane < rem) myq[lane] = v;
-                __syncwarp();
-                qn = rem;
+            __syncthreads();
+            const int qfill = s_next[2];
+            const bool done = s_next[1] + tile_base >= tile_end;  // every tile has been handed out
+            // B2
+            for (;;) {
+                int h = 0;
+                if (lane == 0) h = atomicAdd(&s_next[3], 32);
+                h = __shfl_sync(kFull, h, 0);
+                if (h >= qfill) break;
+                if (h + lane < qfill) {
+                    const int2 e = queue[h + lane];
+                    const int u = e.y & 0xffff, mask = e.y >> 16;
+                    const WidthRec wr = rec[u];
+                    const int i0 = e.x * wr.X;
+                    double A[kBlock], B[kBlock];
+                    if (wr.X == 1)
+                        tap_block<true, kUniformW>(wr, a.tq, w, wd, i0, A, B);
+                    else
+                        tap_block<false, kUniformW>(wr, a.tq, w, wd, i0, A, B);
+#pragma unroll
+                    for (int rr = 0; rr < kBlock; ++rr) {
+                        if (mask & (1 << rr)) {
+                            const int i = i0 + rr * wr.X;
+                            const double mean = (cs[i + wr.W] - cs[i]) * wr.invW;
+                            const double D = mean * wr.os;
+                            const double Aq = kUniformW ? a.w0 * wr.sq2 : A[rr];
+                            double chi = T + D * (D * Aq - 2.0 * B[rr]);
+                            if (wr.L < wr.W) chi -= untouched_tail(w, wd, i + wr.L, i + wr.W);
+                            if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
+                        }
+                    }
+                }
             }
+            if (done) break;
+            __syncthreads();  // everyone has left B2 before the queue is reused
+            if (tid == 0) { s_next[2] = 0; s_next[3] = 0; }
+            __syncthreads();
         }
 
         // ---- C. block arg-min with the reference's tie order ---------------------------
@@ -582,6 +604,8 @@ struct tlsb_handle {
     // light curve
     int N = 0;
     double span = 0.0;
+    bool uniform_w = false;  // every dy identical (dy=None -> std(y) everywhere, validate.py:39-40)
+    double w0 = 0.0;         // 1/dy^2 in that case
     DevBuf t, y, dy, dval, wval;
     bool have_lc = false;
     // templates
@@ -667,7 +691,7 @@ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 size_t tail_bytes(int nU)
 {
-    return (size_t)nU * sizeof(WidthRec) + (2 * kWarps + 2) * 8 + 2 * kWarps * 4 + kWarps * kQueue * 8 + 16;
+    return (size_t)nU * sizeof(WidthRec) + (2 * kWarps + 2) * 8 + 2 * kWarps * 4 + (size_t)kQueue * 8 + 32;
 }
 
 size_t resident_smem_bytes(int N, int M, int pad, int NB, int nU)
@@ -761,10 +785,14 @@ int tlsb_set_lightcurve(tlsb_handle *h, const tlsb_lightcurve *lc)
                                                   h->dval.as<double>(), h->wval.as<double>(), n);
     CUDA_TRY(cudaGetLastError());
     double tmin = lc->t[0], tmax = lc->t[0];  // core.py:148: max(t) - min(t)
+    bool uniform = true;
     for (int k = 1; k < n; ++k) {
         tmin = std::min(tmin, lc->t[k]);
         tmax = std::max(tmax, lc->t[k]);
+        uniform = uniform && lc->dy[k] == lc->dy[0];
     }
+    h->uniform_w = uniform;
+    h->w0 = 1.0 / (lc->dy[0] * lc->dy[0]);
     CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->N = n;
     h->span = tmax - tmin;
@@ -816,8 +844,14 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
         wr.tiles = 0;
         wr.cum = 0;
         const double *s = tp->signal + tp->offset[r];
-        for (int64_t j = 0; j < L; ++j) tq.push_back((1 - s[j]) / kSignalDepth);  // core.py:61-68
-        for (int j = 0; j < xth * (kBlock - 1); ++j) tq.push_back(0.0);           // ramp-out of tap_block
+        double sq2 = 0.0;
+        for (int64_t j = 0; j < L; ++j) {
+            const double q = (1 - s[j]) / kSignalDepth;  // core.py:61-68
+            tq.push_back(q);
+            sq2 = std::fma(q, q, sq2);
+        }
+        wr.sq2 = sq2;
+        for (int j = 0; j < xth * 2 * kBlock; ++j) tq.push_back(0.0);  // ramp-out of tap_block
     }
     int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
@@ -825,7 +859,7 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     if ((rc = upload(h->tq, tq.data(), tq.size() * 8))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->recs.swap(recs);
-    h->pad = (kBlock * xmax + 1) & ~1;
+    h->pad = 2 * kBlock * xmax;
     h->nU = nU;
     h->M = M;
     h->prm = *prm;
@@ -882,10 +916,19 @@ int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
     const bool resident = h->N < 65536 && need <= h->max_smem;
     h->resident = resident;
     CUDA_TRY(cudaEventRecord(h->ev0, s));
+    a.w0 = h->w0;
+    auto launch = [&](auto kernel, size_t smem) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, kThreads, smem, s>>>(a);
+        return cudaGetLastError();
+    };
     if (resident) {
         a.NB = h->N;
-        CUDA_TRY(cudaFuncSetAttribute(tlsb_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        tlsb_search_kernel<true><<<grid, kThreads, need, s>>>(a);
+        if (h->uniform_w)
+            CUDA_TRY(launch(tlsb_search_kernel<true, true>, need));
+        else
+            CUDA_TRY(launch(tlsb_search_kernel<true, false>, need));
     } else {
         if (tail_bytes(h->nU) + 4096 > h->max_smem) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
         const size_t budget = h->max_smem - tail_bytes(h->nU) - 64;
@@ -894,8 +937,10 @@ int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
         if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
         a.scratch = h->scratch.as<unsigned char>();
         const size_t smem = align16((size_t)(a.NB + 1) * 4) + tail_bytes(h->nU);
-        CUDA_TRY(cudaFuncSetAttribute(tlsb_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tlsb_search_kernel<false><<<grid, kThreads, smem, s>>>(a);
+        if (h->uniform_w)
+            CUDA_TRY(launch(tlsb_search_kernel<false, true>, smem));
+        else
+            CUDA_TRY(launch(tlsb_search_kernel<false, false>, smem));
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev1, s));
