@@ -101,11 +101,21 @@ int tlsb_destroy(tlsb_handle *h);
 int tlsb_set_lightcurve(tlsb_handle *h, const tlsb_lightcurve *lc);
 int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_params *prm);
 int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods);
-/* Launch the search kernels on `cuda_stream` (a cudaStream_t, NULL = default stream);
- * asynchronous.  Results go to the handle's device buffer, or, when `records_dev` is not
- * NULL, to that device buffer of 3*n_periods 8-byte words laid out as three planes:
- * chi2 (f64), depth (f64), packed (int64: row in the low 32 bits, t0 index in the high). */
+/* Launch the plan + search kernels on `cuda_stream` (a cudaStream_t, NULL = default
+ * stream); asynchronous.  Results go to the handle's device buffer, or, when `records_dev`
+ * is not NULL, to that device buffer of 3*n_periods + 1 8-byte words: three planes
+ * chi2 (f64), depth (f64), packed (int64: row in the low 32 bits, t0 index in the high),
+ * then ONE status word (int64).  status != 0 means the device-side T14 limits
+ * (grid.py:9-32, core.py:143-156) of that many periods fell within 1e-9 (relative) of an
+ * integer, where the device pow() cannot be trusted to round like the host libm: the
+ * consumer must then call tlsb_set_plan_mode(h, 1) and search again (tlsb_get_results does
+ * this by itself for the handle's own buffer). */
 int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev);
+/* 0 = plan on the device (default); 1 = exact plan on the host (libm pow, bit-identical to
+ * the reference's T14); 2 = device plan that flags every period (exercises the fallback). */
+int tlsb_set_plan_mode(tlsb_handle *h, int32_t mode);
+/* How many times tlsb_get_results had to redo a search with the exact host plan. */
+int64_t tlsb_plan_fallback_count(const tlsb_handle *h);
 /* Wait for the stream and copy the handle's own result buffer to the host. */
 int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_t *row_out,
                      double *depth_out, int64_t *t0_index_out);
@@ -117,6 +127,9 @@ double tlsb_last_search_kernel_ms(tlsb_handle *h);
 /* 1 if the most recent search ran with the folded light curve resident in shared memory,
  * 0 if it streamed it through global scratch. */
 int32_t tlsb_last_path_resident(const tlsb_handle *h);
+/* Launch shape of the most recent search kernel (any pointer may be NULL). */
+int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,
+                     int64_t *smem_bytes);
 
 const char *tlsb_last_error(void);
 const char *tlsb_version(void);

@@ -44,9 +44,46 @@ def test_handle_api_equals_one_shot_and_is_repeatable():
         res = s.results()
         for a, b in zip(one, res):
             np.testing.assert_array_equal(a, b)
-    assert s.launch_count == 1
+    assert s.launch_count == 2  # plan + search
     assert s.kernel_ms > 0
     s.close()
+
+
+@pytest.mark.parametrize("name", ["small", "no_admissible", "cfg1_hetero"])
+def test_device_plan_equals_exact_host_plan_and_fallback(name):
+    """T14 limits on the device (plan kernel) vs the exact host plan (libm pow), and the
+    automatic fallback when the device flags a limit as too close to an integer."""
+    native = _native()
+    g = load_search_golden(name)
+    s = native.Searcher()
+    s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
+    s.set_periods(g["periods"])
+    out = {}
+    for mode in (0, 1, 2):
+        s.set_plan_mode(mode)
+        s.search_async()
+        out[mode] = s.results()
+    assert s.plan_fallbacks == 1  # only mode 2 (every period flagged) had to redo the search
+    for mode in (1, 2):
+        for a, b in zip(out[0], out[mode]):
+            np.testing.assert_array_equal(a, b)
+    assert_search_parity(out[0][:3], g, rtol=RTOL, label=name)
+    s.close()
+
+
+def test_equal_weight_specialisation_matches_general_path():
+    """dy=None gives equal weights and a specialised kernel; nudging one dy by one ulp forces
+    the general kernel on (numerically) the same problem."""
+    native = _native()
+    g = load_search_golden("cfg1_500ppm")
+    sel = slice(0, None, 8)
+    dy2 = g["dy"].copy()
+    dy2[17] = np.nextafter(dy2[17], 2.0)
+    a = native.search_periods(g["t"], g["y"], g["dy"], g["periods"][sel], g["templates"], g["params"])
+    b = native.search_periods(g["t"], g["y"], dy2, g["periods"][sel], g["templates"], g["params"])
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-10)
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-10)
 
 
 def test_period_order_does_not_matter():

@@ -2,27 +2,32 @@
 //
 // What one trial period costs in the reference (core.py:96-188, per period):
 //   fold (core.py:15-18) -> stable argsort (core.py:120) -> gathers (:121-123) -> patch (:126-132)
+//   -> T14 limits and the admissible widths (:143-156, grid.py:9-32)
 //   -> per admissible duration W: running_mean (helpers.py:70-73), out_of_transit_residuals
 //   (core.py:79-93), lowest_residuals_in_this_duration (core.py:28-76) -> min over durations.
 //
-// Here ONE persistent CTA handles one period at a time, entirely on chip when the folded
-// curve fits shared memory ("resident" path) or through a per-CTA global scratch that stays
-// in L2 ("streaming" path, any N):
+// Two kernels per search:
 //
-//   A. fold in fp64 with the reciprocal-multiply form numba emits, bucket-rank the phases
-//      (histogram -> scan -> scatter -> rank inside the bucket by (phase, index): a stable
-//      sort), gather d = 1-y and w = 1/dy^2 straight to their sorted slots, wrap the first M
-//      samples to the end, block-scan d into cumulative sums, block-reduce T = sum w d^2.
-//   B. warp-autonomous sweep over the admissible widths.  With d = 1-y, D = mean*overshoot and
-//      q_j = (1-signal_j)/SIGNAL_DEPTH the reference's statistic is algebraically
-//          chi2_i(W) = T + D^2 * sum_j q_j^2 w_{i+j} - 2 D * sum_j q_j (w d)_{i+j}
-//                        - sum_{k=L..W-1} (w d^2)_{i+k}
-//      (the sum over the window of w d^2 cancels against out_of_transit_residuals and the edge
-//      correction).  Each warp evaluates the gate mean_i > transit_depth_min
-//      from two cumulative-sum reads for 32 candidate offsets, ballot-compacts the survivors
-//      into a small shared-memory queue and runs the tap loop only on full warps of survivors.
-//   C. lexicographic (chi2, width order, offset) block arg-min = the reference's strict-<
-//      tie rules (core.py:71, :183), sentinel N / +inf handling (core.py:46, :139-140).
+//   tlsb_plan_kernel    per period: the T14 limits -> admissible range of unique widths, and a
+//                       counting sort of the periods by cost (most expensive first).
+//   tlsb_search_kernel  persistent CTAs, each takes one period at a time and keeps everything
+//                       on chip when the folded curve fits shared memory ("resident" path), or
+//                       in a per-CTA global scratch that stays in L2 ("streaming" path, any N):
+//     A. fold in fp64 with the reciprocal-multiply form numba emits, bucket the phases
+//        (histogram -> scan -> scatter), rank inside the bucket by (phase, index) = a stable
+//        sort, gather d = 1-y and w = 1/dy^2 to their sorted slots, wrap the first M samples
+//        to the end, block-scan d into cumulative sums, block-reduce T = sum w d^2.
+//     B. With d = 1-y, D = mean*overshoot and q_j = (1-signal_j)/SIGNAL_DEPTH the reference's
+//        statistic is algebraically
+//            chi2_i(W) = T + D^2 * sum_j q_j^2 w_{i+j} - 2 D * sum_j q_j (w d)_{i+j}
+//                          - sum_{k=L..W-1} (w d^2)_{i+k}
+//        (the sum over the window of w d^2 cancels against out_of_transit_residuals and the
+//        edge correction).  B1 gates every candidate offset from two
+//        cumulative-sum reads (mean_i > transit_depth_min) and appends the surviving blocks of
+//        kBlock neighbouring candidates to a CTA-wide queue; B2 runs the register-blocked,
+//        software-pipelined tap loop on full warps of survivors.
+//     C. lexicographic (chi2, width order, offset) block arg-min = the reference's strict-<
+//        tie rules (core.py:71, :183), sentinel N / +inf handling (core.py:46, :139-140).
 //
 // No tensor cores: there is no dense contraction here (per-offset depth, gate and stride).
 #include <cuda_runtime.h>
@@ -43,16 +48,16 @@
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
 constexpr int kBlock = 5;             // R: consecutive T0 candidates one lane carries through the tap loop
                                       // (odd: neighbouring lanes sit R*stride doubles apart in shared memory)
-constexpr int kTile = 32 * kBlock;    // candidates one warp gates per scheduler grab
-constexpr int kQueue = 4096;          // CTA-wide survivor queue (blocks of kBlock candidates)
-constexpr int kQueueStop = kQueue - kWarps * 32;  // gating pauses here: every warp can still add a tile
+constexpr int kTile = 32 * kBlock;    // candidates one warp gates at a time
+constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
+constexpr int kPlanThreads = 1024;
+constexpr int kPlanBins = 1024;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kSignalDepth = 0.5;  // tls_constants.py:71
+constexpr double kPlanEps = 1e-9;     // relative distance to an integer below which the device plan is "uncertain"
 
 thread_local std::string g_error;
 
@@ -88,6 +93,19 @@ struct WidthRec {
     double sq2;   // sum_j q_j^2 (the quadratic term when all weights are equal)
 };
 
+struct PlanArgs {
+    const double *periods;
+    int P;
+    const WidthRec *rec;
+    int nU;
+    int N;
+    double span;                                        // max(t) - min(t), core.py:148
+    double R_star_min, R_star_max, M_star_min, M_star_max;
+    double eps;                                         // kPlanEps (or huge: test mode)
+    int *ulo, *uhi, *order, *bin_of;                    // [P]
+    long long *status;                                  // records word 3P: number of uncertain periods
+};
+
 struct SearchArgs {
     // light curve, prepared once per curve by prepare_kernel
     const double *t;      // [N]
@@ -98,7 +116,7 @@ struct SearchArgs {
     const WidthRec *rec;  // [nU]
     int nU;
     int M;                // patch length (max width, made even) core.py:114-116
-    int pad;              // readable slack behind the patched arrays (kBlock * max stride)
+    int pad;              // readable slack behind the patched arrays
     // periods
     const double *periods;
     const int *ulo;       // [P] admissible unique-width index range [ulo, uhi)
@@ -106,18 +124,106 @@ struct SearchArgs {
     const int *order;     // [P] processing order (most expensive first)
     int P;
     double depth_min;
+    double w0;            // the common weight 1/dy^2 when every dy is the same (dy=None), else unused
     // outputs: three planes of P 8-byte words
     double *out_chi2;
     double *out_depth;
     long long *out_packed;
     // scheduling
-    double w0;            // the common weight 1/dy^2 when every dy is the same (dy=None), else unused
     int *counter;         // [2] next period, finished CTAs
+    int qcap;             // capacity of the CTA-wide survivor queue
     // streaming path scratch
     unsigned char *scratch;
     size_t scratch_per_cta;
     int NB;               // number of phase buckets
 };
+
+// tls_constants.py:20-25,78 and grid.py:9-32 (T14); same operation order on host and device
+__host__ __device__ inline double t14_fraction(double R_s, double M_s, double P, bool small)
+{
+    const double G = 6.673e-11, R_sun = 695508000.0, R_jup = 69911000.0, M_sun = 1.989e30;
+    const double pi = 3.141592653589793;
+    const double Ps = P * 86400.0, R = R_sun * R_s, Ms = M_sun * M_s;
+    const double cube = pow((4 * Ps) / (pi * G * Ms), 1.0 / 3);
+    const double t14 = small ? R * cube : (R + 2 * R_jup) * cube;
+    const double frac = t14 / Ps;
+    return frac > 0.12 ? 0.12 : frac;
+}
+
+// One CTA: admissible width range per period (core.py:143-156) and the processing order.
+// The device pow() may differ from the host libm in the last bits; a period whose limits sit
+// within eps of an integer is counted in *status and the host then redoes the plan exactly.
+__global__ void __launch_bounds__(kPlanThreads) tlsb_plan_kernel(const PlanArgs a)
+{
+    __shared__ int bins[kPlanBins];
+    __shared__ int warp_tot[32];
+    __shared__ int uncertain;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int b = tid; b < kPlanBins; b += kPlanThreads) bins[b] = 0;
+    if (tid == 0) uncertain = 0;
+    __syncthreads();
+    const int nU = a.nU;
+    const int total_tiles = nU > 0 ? a.rec[0].cum + a.rec[0].tiles : 0;
+    const double Nd = (double)a.N;
+    for (int p = tid; p < a.P; p += kPlanThreads) {
+        const double period = a.periods[p];
+        const double dmax = t14_fraction(a.R_star_max, a.M_star_max, period, false);
+        const double dmin = t14_fraction(a.R_star_min, a.M_star_min, period, true);
+        const double naive = a.span / period;
+        const double corr = (naive + 1) / naive;
+        const double xlo = dmin * Nd, xhi = dmax * Nd * corr;
+        const double wmin_f = floor(xlo), wmax_f = ceil(xhi);
+        const bool unsure = fabs(xlo - rint(xlo)) <= a.eps * fmax(1.0, fabs(xlo)) ||
+                            fabs(xhi - rint(xhi)) <= a.eps * fmax(1.0, fabs(xhi)) || !(xlo == xlo) || !(xhi == xhi);
+        // first u with W >= wmin_f, one past the last u with W <= wmax_f
+        int lo = 0, n = nU;
+        while (n > 0) {
+            const int half = n >> 1;
+            if ((double)a.rec[lo + half].W < wmin_f) { lo += half + 1; n -= half + 1; } else n = half;
+        }
+        int hi = 0;
+        n = nU;
+        while (n > 0) {
+            const int half = n >> 1;
+            if ((double)a.rec[hi + half].W <= wmax_f) { hi += half + 1; n -= half + 1; } else n = half;
+        }
+        if (!(wmax_f >= wmin_f) || hi < lo) hi = lo;  // NaN / empty
+        a.ulo[p] = lo;
+        a.uhi[p] = hi;
+        const int cost = hi > lo ? a.rec[lo].cum + a.rec[lo].tiles - a.rec[hi - 1].cum : 0;
+        int bin = (int)(((long long)cost * kPlanBins) / (total_tiles + 1));
+        bin = kPlanBins - 1 - (bin < kPlanBins ? bin : kPlanBins - 1);  // expensive periods first
+        a.bin_of[p] = bin;
+        atomicAdd(&bins[bin], 1);
+        if (unsure) atomicAdd(&uncertain, 1);
+    }
+    __syncthreads();
+    // exclusive scan of the 1024 bins (one per thread)
+    const int mine = bins[tid];
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(kFull, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const int wv = warp_tot[lane];
+        int wi = wv;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(kFull, wi, off);
+            if (lane >= off) wi += o;
+        }
+        warp_tot[lane] = wi - wv;
+    }
+    __syncthreads();
+    bins[tid] = warp_tot[wid] + incl - mine;
+    __syncthreads();
+    for (int p = tid; p < a.P; p += kPlanThreads) a.order[atomicAdd(&bins[a.bin_of[p]], 1)] = p;
+    if (tid == 0) *a.status = (long long)uncertain;
+}
 
 __device__ __forceinline__ double fold_phase(double t, double r)
 {
@@ -134,12 +240,13 @@ __device__ __forceinline__ int bucket_of(double phase, int NB)
 }
 
 // In-place block-wide inclusive scan of data[0..n) (all threads must call).
-template <typename T>
-__device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kWarps+1] shared */)
+template <int kT, typename T>
+__device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] shared */)
 {
+    constexpr int kW = kT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     T carry = T(0);
-    for (int base = 0; base < n; base += kThreads * kScanItems) {
+    for (int base = 0; base < n; base += kT * kScanItems) {
         const int first = base + tid * kScanItems;
         T v[kScanItems];
         T run = T(0);
@@ -159,15 +266,15 @@ __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kWarps+1] s
         if (lane == 31) warp_tot[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            T wv = (lane < kWarps) ? warp_tot[lane] : T(0);
+            T wv = (lane < kW) ? warp_tot[lane] : T(0);
             T wi = wv;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 T o = __shfl_up_sync(kFull, wi, off);
                 if (lane >= off) wi += o;
             }
-            if (lane < kWarps) warp_tot[lane] = wi - wv;  // exclusive warp offsets
-            if (lane == kWarps - 1) warp_tot[kWarps] = wi; // tile total
+            if (lane < kW) warp_tot[lane] = wi - wv;  // exclusive warp offsets
+            if (lane == kW - 1) warp_tot[kW] = wi;    // tile total
         }
         __syncthreads();
         T excl = __shfl_up_sync(kFull, incl, 1);  // exclusive prefix of this thread inside its warp
@@ -176,7 +283,7 @@ __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kWarps+1] s
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k)
             if (first + k < n) data[first + k] = v[k] + offset;
-        carry += warp_tot[kWarps];
+        carry += warp_tot[kW];
         __syncthreads();
     }
 }
@@ -198,8 +305,9 @@ __device__ __forceinline__ bool better(double c, int u, int i, const Best &b)
 // j = X*a + b; inside one class candidate r at step m = a + r reads sample i0 + b + X*m, so
 // every staged sample (w, w*d) feeds all kBlock candidates and the template value loaded at
 // step m is reused from registers for the next kBlock-1 steps.  Steps go in unguarded groups
-// of kBlock (loads of a whole group can be in flight together): templates are zero padded in
-// tq and the patched arrays have slack behind them, so ramp-in/ramp-out need no predicates.
+// of kBlock, and the loads of group g+1 are issued before the arithmetic of group g (software
+// pipeline): templates are zero padded in tq and the patched arrays have slack behind them,
+// so ramp-in/ramp-out and the one-group overshoot need no predicates.
 // kUniformW: all weights equal (dy=None) -> only B = sum q_j (w d)_{i+j} is accumulated.
 template <bool kUnit, bool kUniformW>
 __device__ __forceinline__ void tap_block(const WidthRec &wr, const double *__restrict__ tq,
@@ -218,46 +326,59 @@ __device__ __forceinline__ void tap_block(const WidthRec &wr, const double *__re
         double qw[kBlock], pw[kBlock];  // circular: the value loaded at step m lives in slot m % kBlock
 #pragma unroll
         for (int r = 0; r < kBlock; ++r) { qw[r] = 0.0; pw[r] = 0.0; }
-#pragma unroll 1
-        for (int g = 0; g < groups; ++g) {
-            double qk[kBlock], wv[kBlock], wdv[kBlock];
+        double qk[2][kBlock], wv[2][kBlock], wdv[2][kBlock];
+        auto load = [&](int buf) {
 #pragma unroll
             for (int mm = 0; mm < kBlock; ++mm) {
-                qk[mm] = __ldg(qp + mm * X);
-                wdv[mm] = wdp[mm * X];
-                if (!kUniformW) wv[mm] = wp[mm * X];
-            }
-#pragma unroll
-            for (int mm = 0; mm < kBlock; ++mm) {
-                qw[mm] = qk[mm];
-                if (!kUniformW) pw[mm] = qk[mm] * qk[mm];
-#pragma unroll
-                for (int r = 0; r < kBlock; ++r) {
-                    const int slot = (mm - r + kBlock) % kBlock;  // loaded r steps ago
-                    B[r] = fma(qw[slot], wdv[mm], B[r]);
-                    if (!kUniformW) A[r] = fma(pw[slot], wv[mm], A[r]);
-                }
+                qk[buf][mm] = __ldg(qp + mm * X);
+                wdv[buf][mm] = wdp[mm * X];
+                if (!kUniformW) wv[buf][mm] = wp[mm * X];
             }
             qp += kBlock * X;
             wp += kBlock * X;
             wdp += kBlock * X;
+        };
+        auto compute = [&](int buf) {
+#pragma unroll
+            for (int mm = 0; mm < kBlock; ++mm) {
+                qw[mm] = qk[buf][mm];
+                if (!kUniformW) pw[mm] = qk[buf][mm] * qk[buf][mm];
+#pragma unroll
+                for (int r = 0; r < kBlock; ++r) {
+                    const int slot = (mm - r + kBlock) % kBlock;  // loaded r steps ago
+                    B[r] = fma(qw[slot], wdv[buf][mm], B[r]);
+                    if (!kUniformW) A[r] = fma(pw[slot], wv[buf][mm], A[r]);
+                }
+            }
+        };
+        load(0);
+#pragma unroll 1
+        for (int g = 0; g < groups; g += 2) {
+            load(1);
+            compute(0);
+            if (g + 1 >= groups) break;
+            load(0);
+            compute(1);
         }
     }
 }
 
 // Samples L..W-1 of a window are in neither the in-transit nor the out-of-transit sum when a
 // template was trimmed to L < W (rare: L == W for the limb-darkened templates).
-__device__ __noinline__ double untouched_tail(const double *w, const double *wd, int from, int to)
+// w d^2 = (w d)^2 / w.
+template <bool kUniformW>
+__device__ __noinline__ double untouched_tail(const double *w, const double *wd, double w0, int from, int to)
 {
     double rest = 0.0;
 #pragma unroll 1
-    for (int k = from; k < to; ++k) rest += wd[k] * wd[k] / w[k];  // w d^2
+    for (int k = from; k < to; ++k) rest += wd[k] * wd[k] / (kUniformW ? w0 : w[k]);
     return rest;
 }
 
-template <bool kResident, bool kUniformW>
-__global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
+template <int kT, bool kResident, bool kUniformW>
+__global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
 {
+    constexpr int kW = kT / 32;
     using idx_t = typename std::conditional<kResident, unsigned short, unsigned int>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -266,50 +387,47 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
     const int NMP = NM + a.pad;
 
     // ---- carve memory ------------------------------------------------------------------
-    // cs  : (NM+1) doubles  cumulative sums of d (cs[0] = 0)
-    // w   : NMP doubles
-    // U   : union { wd : NMP doubles } / { skey : N doubles, sid : N idx, slot : N idx [, hist] }
-    // hist: NB+1 ints  (inside U on the resident path, in shared memory on the streaming path)
+    // cs   : (NM+1) doubles   cumulative sums of d, cs[0] = 0      [the sort keys while sorting]
+    // w    : NMP doubles      weights (not kept when all weights are equal)
+    // wd   : NMP doubles      w*d                                   [the sorted d before that]
+    // queue: qcap int2        survivor blocks                       [resident: H + sid while sorting]
     const size_t cs_elems = (size_t)(NM + 2) & ~(size_t)1;
-    double *cs, *w, *wd, *skey;
-    idx_t *sid, *slot;
-    int *hist;
+    double *cs, *w, *wd;
+    idx_t *sid;
+    int *H;
+    int2 *queue;
     unsigned char *tail;
     if (kResident) {
         cs = reinterpret_cast<double *>(smem_raw);
         w = cs + cs_elems;
-        unsigned char *U = reinterpret_cast<unsigned char *>(w + NMP);
-        wd = reinterpret_cast<double *>(U);
-        skey = reinterpret_cast<double *>(U);
-        hist = reinterpret_cast<int *>(skey + N);
-        sid = reinterpret_cast<idx_t *>(hist + NB + 1);
-        slot = sid + N;
-        size_t sort_bytes = (size_t)N * 8 + (size_t)(NB + 1) * 4 + (size_t)N * 2 * sizeof(idx_t);
-        size_t u_bytes = sort_bytes > (size_t)NMP * 8 ? sort_bytes : (size_t)NMP * 8;
-        tail = U + ((u_bytes + 15) & ~(size_t)15);
+        wd = kUniformW ? w : w + NMP;
+        queue = reinterpret_cast<int2 *>(wd + NMP);
+        H = reinterpret_cast<int *>(queue);
+        sid = reinterpret_cast<idx_t *>(H + NB + 1);
+        tail = reinterpret_cast<unsigned char *>(queue + a.qcap);
     } else {
         unsigned char *g = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
         cs = reinterpret_cast<double *>(g);
         w = cs + cs_elems;
-        unsigned char *U = reinterpret_cast<unsigned char *>(w + NMP);
-        wd = reinterpret_cast<double *>(U);
-        skey = reinterpret_cast<double *>(U);
-        sid = reinterpret_cast<idx_t *>(skey + N);
-        slot = sid + N;
-        hist = reinterpret_cast<int *>(smem_raw);
-        tail = smem_raw + (((size_t)(NB + 1) * 4 + 15) & ~(size_t)15);
+        wd = kUniformW ? w : w + NMP;
+        sid = reinterpret_cast<idx_t *>(wd + NMP);
+        queue = reinterpret_cast<int2 *>(smem_raw);
+        H = reinterpret_cast<int *>(queue + a.qcap);
+        tail = smem_raw + (size_t)a.qcap * 8 + (((size_t)(NB + 1) * 4 + 15) & ~(size_t)15);
     }
+    double *skey = cs;
+    double *dsorted = wd;
     WidthRec *rec = reinterpret_cast<WidthRec *>(tail);                       // [nU]
-    double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kWarps + 2]
-    int *red_i = reinterpret_cast<int *>(red_d + 2 * kWarps + 2);             // [2*kWarps]
-    int2 *queue = reinterpret_cast<int2 *>(red_i + 2 * kWarps);               // [kQueue]
-    int *s_next = reinterpret_cast<int *>(queue + kQueue);  // [4] period slot, tile counter, queue fill, queue head
+    double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
+    int *red_i = reinterpret_cast<int *>(red_d + 2 * kW + 2);                 // [2*kW]
+    int *s_next = red_i + 2 * kW;  // [4] period slot, "tiles left" flag, queue fill, queue head
 
-    for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kThreads)
+    for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
         reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
 
     const unsigned lt_mask = (1u << lane) - 1u;
     const double depth_min = a.depth_min;
+    const int qstop = a.qcap - kW * 32;  // gating pauses here: every warp can still add one tile
 
     for (;;) {
         if (tid == 0) {
@@ -337,68 +455,66 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
         }
 
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
-        for (int b = tid; b <= NB; b += kThreads) hist[b] = 0;
+        for (int b = tid; b <= NB; b += kT) H[b] = 0;
         __syncthreads();
-        for (int k = tid; k < N; k += kThreads) {
-            const double ph = fold_phase(a.t[k], r);
-            slot[k] = (idx_t)atomicAdd(&hist[bucket_of(ph, NB)], 1);
-        }
+        for (int k = tid; k < N; k += kT)
+            atomicAdd(&H[bucket_of(fold_phase(a.t[k], r), NB) + 1], 1);
         __syncthreads();
-        // exclusive scan: shift by one so hist[b] = number of keys in buckets < b
-        block_inclusive_scan<int>(hist, NB, reinterpret_cast<int *>(red_d));
-        // hist now inclusive; convert on the fly below: base(b) = b ? hist[b-1] : 0
-        for (int k = tid; k < N; k += kThreads) {
+        // inclusive scan of H[0..NB] (H[0] = 0): H[b] = number of keys in buckets < b
+        block_inclusive_scan<kT, int>(H, NB + 1, reinterpret_cast<int *>(red_d));
+        for (int k = tid; k < N; k += kT) {
             const double ph = fold_phase(a.t[k], r);
-            const int b = bucket_of(ph, NB);
-            const int pos = (b ? hist[b - 1] : 0) + (int)slot[k];
+            const int pos = atomicAdd(&H[bucket_of(ph, NB)], 1);  // any order inside the bucket
             skey[pos] = ph;
             sid[pos] = (idx_t)k;
         }
-        __syncthreads();
-        for (int q = tid; q < N; q += kThreads) {
+        __syncthreads();  // now H[b] = end of bucket b
+        for (int q = tid; q < N; q += kT) {
             const double key = skey[q];
             const int id = (int)sid[q];
             const int b = bucket_of(key, NB);
-            const int lo = b ? hist[b - 1] : 0, hi = hist[b];
+            const int lo = b ? H[b - 1] : 0, hi = H[b];
             int rank = lo;
             for (int s = lo; s < hi; ++s) {
                 const double ks = skey[s];
                 const int is = (int)sid[s];
-                rank += (ks < key) || (ks == key && is < id);
+                rank += (ks < key) || (ks == key && is < id);  // (phase, index): the stable order
             }
-            cs[rank + 1] = a.dval[id];   // d, scanned in place below
-            w[rank] = a.wval[id];
+            dsorted[rank] = a.dval[id];
+            if (!kUniformW) w[rank] = a.wval[id];
         }
-        __syncthreads();  // sort scratch is dead from here; wd may overwrite it
-        // wrap the first M samples to the end (core.py:126-132), build w*d, reduce T = sum w d^2
-        double tpart = 0.0;
-        for (int k = tid; k < NMP; k += kThreads) {
-            if (k < NM) {
-                const int src = k < N ? k : k - N;
-                const double d = cs[src + 1], wv = w[src];
-                const double x = wv * d;
-                if (k >= N) { cs[k + 1] = d; w[k] = wv; }
-                wd[k] = x;
-                if (k < N) tpart = fma(x, d, tpart);
-            } else {  // slack read (never used) by partially valid candidate blocks
-                w[k] = 0.0;
-                wd[k] = 0.0;
-            }
-        }
+        __syncthreads();  // keys are dead: cs may overwrite them
+        // wrap the first M samples to the end (core.py:126-132)
+        for (int k = tid; k < NM; k += kT) cs[k + 1] = dsorted[k < N ? k : k - N];
         if (tid == 0) cs[0] = 0.0;
+        __syncthreads();  // the sorted d are dead: wd may overwrite them
+        double tpart = 0.0;
+        for (int k = tid; k < NMP; k += kT) {
+            if (k < NM) {
+                const double d = cs[k + 1];
+                const double wv = kUniformW ? a.w0 : w[k < N ? k : k - N];
+                const double x = wv * d;
+                if (!kUniformW && k >= N) w[k] = wv;
+                wd[k] = x;
+                if (k < N) tpart = fma(x, d, tpart);  // T = sum w d^2 over the unpatched curve
+            } else {  // slack read (never used) by the unguarded tap groups
+                wd[k] = 0.0;
+                if (!kUniformW) w[k] = 0.0;
+            }
+        }
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
-        if (lane == 0) red_d[kWarps + 1 + wid] = tpart;
+        if (lane == 0) red_d[kW + 1 + wid] = tpart;
         __syncthreads();
-        block_inclusive_scan<double>(cs + 1, NM, red_d);
+        block_inclusive_scan<kT, double>(cs + 1, NM, red_d);
         double T = 0.0;
-        for (int k = 0; k < kWarps; ++k) T += red_d[kWarps + 1 + k];  // fixed order: deterministic
+        for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];  // fixed order: deterministic
 
         // ---- B. gate + survivor compaction + tap loop ----------------------------------------
-        // B1: warps grab tiles of kTile candidates of one width from a CTA-wide counter (wide
-        //     widths first), gate them from two cumulative-sum reads per candidate and append
-        //     the surviving blocks to a CTA-wide queue (one reservation per tile, so a tile's
-        //     survivors stay together and the queue is nearly sorted by width).
+        // B1: warp `wid` gates tiles wid, wid+kW, ... of the sweep (wide widths first) from two
+        //     cumulative-sum reads per candidate and appends the surviving blocks to the
+        //     CTA-wide queue (one reservation per tile, so a tile's survivors stay together and
+        //     the queue is nearly sorted by width).
         // B2: warps grab 32 consecutive queue entries - almost always one width, so template
         //     loads broadcast and the lanes run in lockstep - and run the tap loop.
         // The queue is bounded; B1/B2 alternate until all tiles are gated.
@@ -408,16 +524,17 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
         best.u = -1;  // "no model yet": loses every tie, so a candidate must be strictly below N
         best.i = -1;
 
-        const int tile_base = rec[uhi - 1].cum;
         const int tile_end = rec[ulo].cum + rec[ulo].tiles;
+        int g_next = rec[uhi - 1].cum + wid;
         int cur_u = uhi - 1;
         for (;;) {
             // B1
-            for (;;) {
-                int g = tile_end;
-                if (lane == 0 && *(volatile int *)&s_next[2] < kQueueStop) g = atomicAdd(&s_next[1], 1) + tile_base;
-                g = __shfl_sync(kFull, g, 0);
-                if (g >= tile_end) break;
+            while (g_next < tile_end) {
+                int fill = 0;
+                if (lane == 0) fill = *(volatile int *)&s_next[2];
+                if (__shfl_sync(kFull, fill, 0) >= qstop) break;
+                const int g = g_next;
+                g_next += kW;
                 while (g >= rec[cur_u].cum + rec[cur_u].tiles) --cur_u;
                 const int u = cur_u;
                 const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
@@ -441,9 +558,10 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
                     if (mask) queue[base + __popc(m & lt_mask)] = make_int2(c0, u | (mask << 16));
                 }
             }
+            if (lane == 0 && g_next < tile_end) s_next[1] = 1;  // this warp has tiles left
             __syncthreads();
             const int qfill = s_next[2];
-            const bool done = s_next[1] + tile_base >= tile_end;  // every tile has been handed out
+            const bool more = s_next[1] != 0;
             // B2
             for (;;) {
                 int h = 0;
@@ -468,15 +586,15 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
                             const double D = mean * wr.os;
                             const double Aq = kUniformW ? a.w0 * wr.sq2 : A[rr];
                             double chi = T + D * (D * Aq - 2.0 * B[rr]);
-                            if (wr.L < wr.W) chi -= untouched_tail(w, wd, i + wr.L, i + wr.W);
+                            if (wr.L < wr.W) chi -= untouched_tail<kUniformW>(w, wd, a.w0, i + wr.L, i + wr.W);
                             if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
                         }
                     }
                 }
             }
-            if (done) break;
+            if (!more) break;
             __syncthreads();  // everyone has left B2 before the queue is reused
-            if (tid == 0) { s_next[2] = 0; s_next[3] = 0; }
+            if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
             __syncthreads();
         }
 
@@ -490,22 +608,22 @@ __global__ void __launch_bounds__(kThreads, 1) tlsb_search_kernel(const __grid_c
             o.i = __shfl_xor_sync(kFull, best.i, off);
             if (better(o.chi2, o.u, o.i, best)) best = o;
         }
-        __syncthreads();  // everyone is done reading red_d (T) before it is reused
+        __syncthreads();  // everyone is done reading red_d (T) and the queue before they are reused
         if (lane == 0) {
             red_d[wid] = best.chi2;
-            red_d[kWarps + wid] = best.D;
+            red_d[kW + wid] = best.D;
             red_i[wid] = best.u;
-            red_i[kWarps + wid] = best.i;
+            red_i[kW + wid] = best.i;
         }
         __syncthreads();
         if (wid == 0) {
             Best b2;
             b2.chi2 = (double)N; b2.D = 0.0; b2.u = -1; b2.i = -1;
-            if (lane < kWarps) {
+            if (lane < kW) {
                 b2.chi2 = red_d[lane];
-                b2.D = red_d[kWarps + lane];
+                b2.D = red_d[kW + lane];
                 b2.u = red_i[lane];
-                b2.i = red_i[kWarps + lane];
+                b2.i = red_i[kW + lane];
             }
 #pragma unroll
             for (int off = 16; off; off >>= 1) {
@@ -584,23 +702,24 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-// tls_constants.py:20-25,78 and grid.py:9-32 (T14)
-double t14_fraction(double R_s, double M_s, double P, bool small)
-{
-    const double G = 6.673e-11, R_sun = 695508000.0, R_jup = 69911000.0, M_sun = 1.989e30;
-    const double Ps = P * 86400.0, R = R_sun * R_s, Ms = M_sun * M_s;
-    const double cube = std::pow((4 * Ps) / (M_PI * G * Ms), 1.0 / 3);
-    const double t14 = small ? R * cube : (R + 2 * R_jup) * cube;
-    const double frac = t14 / Ps;
-    return frac > 0.12 ? 0.12 : frac;
-}
+// How one search is laid out on the SM (chosen per search from N, M, the bank and the device).
+struct Layout {
+    bool resident = false;
+    int threads = 256;     // 256 (two CTAs per SM) or 512 (one)
+    int ctas_per_sm = 2;
+    int qcap = 4096;
+    int NB = 0;
+    size_t smem = 0;
+    size_t scratch_per_cta = 0;
+};
 
 }  // namespace
 
 struct tlsb_handle {
     int device = 0;
     int num_sms = 0;
-    size_t max_smem = 0;
+    size_t max_smem = 0;     // per CTA (opt-in)
+    size_t smem_per_sm = 0;
     // light curve
     int N = 0;
     double span = 0.0;
@@ -614,17 +733,20 @@ struct tlsb_handle {
     std::vector<WidthRec> recs;   // unique widths, ascending
     DevBuf tq, d_rec;
     bool have_tp = false;
+    bool recs_stale = true;       // ncand/tiles/cum depend on N + M
     // periods
     int P = 0;
     std::vector<double> h_periods;
-    DevBuf periods, ulo, uhi, order;
+    DevBuf periods, ulo, uhi, order, bin_of;
     bool have_periods = false;
-    bool periods_stale = true;  // admissible ranges depend on light curve + templates + params
+    int plan_mode = 0;            // 0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)
+    bool host_plan_valid = false;
     // outputs / scheduling / scratch
     DevBuf out, counter, scratch;
     // bookkeeping
     int64_t launches = 0;
-    bool resident = false;
+    int64_t fallbacks = 0;
+    Layout layout;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
 };
@@ -638,23 +760,31 @@ int upload(DevBuf &buf, const void *src, size_t bytes, cudaStream_t s = nullptr)
     return 0;
 }
 
-// admissible unique-width range per period (core.py:143-156) + processing order
-int refresh_periods(tlsb_handle *h)
+// candidates and scheduler tiles per width (depend on N + M), wide -> narrow prefix
+int refresh_records(tlsb_handle *h)
 {
-    const int P = h->P, N = h->N;
-    // candidates and scheduler tiles per width (depend on N + M), wide -> narrow prefix
     int cum = 0;
     for (int u = h->nU - 1; u >= 0; --u) {
         WidthRec &wr = h->recs[u];
-        wr.ncand = (N + h->M - wr.W) / wr.X + 1;  // offsets i = c*X, i in [0, N+M-W]
+        wr.ncand = (h->N + h->M - wr.W) / wr.X + 1;  // offsets i = c*X, i in [0, N+M-W]
         wr.tiles = (wr.ncand + kTile - 1) / kTile;
         wr.cum = cum;
         cum += wr.tiles;
     }
-    {
-        int rc0;
-        if ((rc0 = upload(h->d_rec, h->recs.data(), sizeof(WidthRec) * (size_t)h->nU))) return rc0;
-    }
+    int rc;
+    if ((rc = upload(h->d_rec, h->recs.data(), sizeof(WidthRec) * (size_t)h->nU))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->recs_stale = false;
+    h->host_plan_valid = false;
+    return 0;
+}
+
+// The exact plan on the host (libm pow, bit-identical to the reference's T14): admissible
+// unique-width range per period (core.py:143-156) + processing order.  Used when the device
+// plan reports a limit too close to an integer to trust its pow(), and by plan_mode 1.
+int host_plan(tlsb_handle *h)
+{
+    const int P = h->P, N = h->N;
     std::vector<int> lo(P), hi(P), order(P);
     for (int p = 0; p < P; ++p) {
         const double period = h->h_periods[p];
@@ -683,33 +813,144 @@ int refresh_periods(tlsb_handle *h)
     if ((rc = upload(h->uhi, hi.data(), sizeof(int) * P))) return rc;
     if ((rc = upload(h->order, order.data(), sizeof(int) * P))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));  // the vectors above go out of scope
-    h->periods_stale = false;
+    h->host_plan_valid = true;
     return 0;
 }
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-size_t tail_bytes(int nU)
+size_t tail_bytes(int nU, int threads)
 {
-    return (size_t)nU * sizeof(WidthRec) + (2 * kWarps + 2) * 8 + 2 * kWarps * 4 + (size_t)kQueue * 8 + 32;
+    const int kW = threads / 32;
+    return (size_t)nU * sizeof(WidthRec) + (size_t)(2 * kW + 2) * 8 + (size_t)2 * kW * 4 + 16;
 }
 
-size_t resident_smem_bytes(int N, int M, int pad, int NB, int nU)
+size_t resident_smem_bytes(int N, int M, int pad, int nU, bool uniform, int qcap, int threads)
 {
     const size_t NM = (size_t)N + M, NMP = NM + pad;
-    const size_t cs = ((NM + 2) & ~(size_t)1) * 8, w = NMP * 8;
-    const size_t sort_bytes = (size_t)N * 8 + (size_t)(NB + 1) * 4 + (size_t)N * 2 * 2;
-    const size_t u = std::max(sort_bytes, NMP * 8);
-    return cs + w + align16(u) + tail_bytes(nU);
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
+    return cs + (uniform ? 1 : 2) * NMP * 8 + (size_t)qcap * 8 + tail_bytes(nU, threads);
 }
 
-size_t streaming_scratch_bytes(int N, int M, int pad)
+// Pick the on-chip layout: two 256-thread CTAs per SM when two folded curves fit the SM's
+// shared memory, else one 512-thread CTA, else the streaming path (global scratch in L2).
+Layout choose_layout(const tlsb_handle *h)
 {
-    const size_t NM = (size_t)N + M, NMP = NM + pad;
-    const size_t cs = ((NM + 2) & ~(size_t)1) * 8, w = NMP * 8;
-    const size_t sort_bytes = (size_t)N * 8 + (size_t)N * 2 * 4;
-    const size_t u = std::max(sort_bytes, NMP * 8);
-    return (cs + w + align16(u) + 255) & ~(size_t)255;
+    Layout best;
+    const int N = h->N;
+    if (N < 65536) {
+        const int tries[2][2] = {{256, 2}, {512, 1}};
+        const int qcaps[3] = {4096, 3072, 2048};
+        for (const auto &t : tries) {
+            for (int qcap : qcaps) {
+                const size_t bytes = resident_smem_bytes(N, h->M, h->pad, h->nU, h->uniform_w, qcap, t[0]);
+                if (bytes > h->max_smem) continue;
+                if ((bytes + 1024) * (size_t)t[1] > h->smem_per_sm) continue;
+                // the sort borrows the queue: H (NB+1 ints) + sid (N u16)
+                const long long room = (long long)qcap * 8 - 2LL * N - 8;
+                if (room < 4LL * 64) continue;
+                int NB = (int)std::min<long long>(N, room / 4 - 1);
+                if (NB < N / 16) continue;
+                best.resident = true;
+                best.threads = t[0];
+                best.ctas_per_sm = t[1];
+                best.qcap = qcap;
+                best.NB = NB;
+                best.smem = bytes;
+                return best;
+            }
+        }
+    }
+    best.resident = false;
+    best.threads = 256;
+    best.ctas_per_sm = 2;
+    best.qcap = 4096;
+    const size_t fixed = (size_t)best.qcap * 8 + tail_bytes(h->nU, best.threads) + 64;
+    const size_t per_cta = std::min(h->max_smem, h->smem_per_sm / 2 - 1024);
+    const size_t budget = per_cta > fixed ? per_cta - fixed : 0;
+    best.NB = (int)std::min<size_t>((size_t)N, budget / 4 > 2 ? budget / 4 - 2 : 0);
+    best.smem = (size_t)best.qcap * 8 + align16((size_t)(best.NB + 1) * 4) + tail_bytes(h->nU, best.threads);
+    const size_t NM = (size_t)N + h->M, NMP = NM + h->pad;
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
+    best.scratch_per_cta = (cs + (h->uniform_w ? 1 : 2) * NMP * 8 + (size_t)N * 4 + 255) & ~(size_t)255;
+    return best;
+}
+
+template <typename K>
+cudaError_t launch_search(K kernel, const SearchArgs &a, int grid, int threads, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, threads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// plan (unless the exact host plan is in force) + search, asynchronous on `s`
+int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact_plan)
+{
+    int rc;
+    if (h->recs_stale && (rc = refresh_records(h))) return rc;
+    const int P = h->P;
+    double *rec_words = reinterpret_cast<double *>(records_dev);
+    long long *status = reinterpret_cast<long long *>(rec_words + 3 * (size_t)P);
+    if (h->ulo.ensure(sizeof(int) * (size_t)P) || h->uhi.ensure(sizeof(int) * (size_t)P) ||
+        h->order.ensure(sizeof(int) * (size_t)P) || h->bin_of.ensure(sizeof(int) * (size_t)P))
+        return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    h->launches = 0;
+    if (exact_plan) {
+        if (!h->host_plan_valid && (rc = host_plan(h))) return rc;
+        CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));
+    } else {
+        PlanArgs pa{};
+        pa.periods = h->periods.as<double>(); pa.P = P; pa.rec = h->d_rec.as<WidthRec>(); pa.nU = h->nU;
+        pa.N = h->N; pa.span = h->span;
+        pa.R_star_min = h->prm.R_star_min; pa.R_star_max = h->prm.R_star_max;
+        pa.M_star_min = h->prm.M_star_min; pa.M_star_max = h->prm.M_star_max;
+        pa.eps = h->plan_mode == 2 ? 1e300 : kPlanEps;
+        pa.ulo = h->ulo.as<int>(); pa.uhi = h->uhi.as<int>(); pa.order = h->order.as<int>();
+        pa.bin_of = h->bin_of.as<int>(); pa.status = status;
+        tlsb_plan_kernel<<<1, kPlanThreads, 0, s>>>(pa);
+        CUDA_TRY(cudaGetLastError());
+        h->host_plan_valid = false;
+        h->launches += 1;
+    }
+
+    const Layout lay = choose_layout(h);
+    h->layout = lay;
+    SearchArgs a{};
+    a.t = h->t.as<double>(); a.dval = h->dval.as<double>(); a.wval = h->wval.as<double>(); a.N = h->N;
+    a.tq = h->tq.as<double>(); a.rec = h->d_rec.as<WidthRec>(); a.nU = h->nU; a.M = h->M; a.pad = h->pad;
+    a.periods = h->periods.as<double>(); a.ulo = h->ulo.as<int>(); a.uhi = h->uhi.as<int>();
+    a.order = h->order.as<int>(); a.P = P; a.depth_min = h->prm.transit_depth_min; a.w0 = h->w0;
+    a.out_chi2 = rec_words;
+    a.out_depth = rec_words + P;
+    a.out_packed = reinterpret_cast<long long *>(rec_words + 2 * (size_t)P);
+    a.counter = h->counter.as<int>();
+    a.qcap = lay.qcap;
+    a.NB = lay.NB;
+    const int grid = std::min(P, h->num_sms * lay.ctas_per_sm);
+    if (!lay.resident) {
+        if (lay.NB < 1) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
+        a.scratch_per_cta = lay.scratch_per_cta;
+        if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
+        a.scratch = h->scratch.as<unsigned char>();
+    }
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    const bool uni = h->uniform_w;
+    if (lay.resident && lay.threads == 256) {
+        if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<256, true, true>, a, grid, 256, lay.smem, s));
+        else CUDA_TRY(launch_search(tlsb_search_kernel<256, true, false>, a, grid, 256, lay.smem, s));
+    } else if (lay.resident) {
+        if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<512, true, true>, a, grid, 512, lay.smem, s));
+        else CUDA_TRY(launch_search(tlsb_search_kernel<512, true, false>, a, grid, 512, lay.smem, s));
+    } else {
+        if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<256, false, true>, a, grid, 256, lay.smem, s));
+        else CUDA_TRY(launch_search(tlsb_search_kernel<256, false, false>, a, grid, 256, lay.smem, s));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    h->launches += 1;
+    h->timed = true;
+    return 0;
 }
 
 }  // namespace
@@ -717,7 +958,7 @@ size_t streaming_scratch_bytes(int N, int M, int pad)
 extern "C" {
 
 const char *tlsb_last_error(void) { return g_error.c_str(); }
-const char *tlsb_version(void) { return "tlsb200 0.1 (sm_100a)"; }
+const char *tlsb_version(void) { return "tlsb200 0.2 (sm_100a)"; }
 
 int32_t tlsb_device_count(void)
 {
@@ -748,6 +989,7 @@ int tlsb_create(tlsb_handle **out, int32_t device)
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     h->max_smem = prop.sharedMemPerBlockOptin;
+    h->smem_per_sm = prop.sharedMemPerMultiprocessor;
     CUDA_TRY(cudaEventCreate(&h->ev0));
     CUDA_TRY(cudaEventCreate(&h->ev1));
     if (h->counter.ensure(16)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
@@ -760,8 +1002,8 @@ int tlsb_destroy(tlsb_handle *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo, &h->uhi,
-                      &h->order, &h->out, &h->counter, &h->scratch})
+    for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo,
+                      &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -791,13 +1033,14 @@ int tlsb_set_lightcurve(tlsb_handle *h, const tlsb_lightcurve *lc)
         tmax = std::max(tmax, lc->t[k]);
         uniform = uniform && lc->dy[k] == lc->dy[0];
     }
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->uniform_w = uniform;
     h->w0 = 1.0 / (lc->dy[0] * lc->dy[0]);
-    CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->N = n;
     h->span = tmax - tmin;
     h->have_lc = true;
-    h->periods_stale = true;
+    h->recs_stale = true;
+    h->host_plan_valid = false;
     return 0;
 }
 
@@ -840,7 +1083,7 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
         }
         wr.X = xth;
         xmax = std::max(xmax, xth);
-        wr.ncand = 0;  // needs N: filled by refresh_periods
+        wr.ncand = 0;  // need N: refresh_records
         wr.tiles = 0;
         wr.cum = 0;
         const double *s = tp->signal + tp->offset[r];
@@ -851,7 +1094,7 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
             sq2 = std::fma(q, q, sq2);
         }
         wr.sq2 = sq2;
-        for (int j = 0; j < xth * 2 * kBlock; ++j) tq.push_back(0.0);  // ramp-out of tap_block
+        for (int j = 0; j < xth * kPadGroups * kBlock; ++j) tq.push_back(0.0);  // ramp-out + pipeline overshoot
     }
     int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
@@ -859,12 +1102,13 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     if ((rc = upload(h->tq, tq.data(), tq.size() * 8))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->recs.swap(recs);
-    h->pad = 2 * kBlock * xmax;
+    h->pad = kPadGroups * kBlock * xmax;
     h->nU = nU;
     h->M = M;
     h->prm = *prm;
     h->have_tp = true;
-    h->periods_stale = true;
+    h->recs_stale = true;
+    h->host_plan_valid = false;
     return 0;
 }
 
@@ -879,7 +1123,14 @@ int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods)
     if ((rc = upload(h->periods, periods, sizeof(double) * (size_t)n_periods))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->have_periods = true;
-    h->periods_stale = true;
+    h->host_plan_valid = false;
+    return 0;
+}
+
+int tlsb_set_plan_mode(tlsb_handle *h, int32_t mode)
+{
+    if (!h || mode < 0 || mode > 2) return fail(TLSB_ERR_ARG, "tlsb_set_plan_mode: mode must be 0, 1 or 2");
+    h->plan_mode = mode;
     return 0;
 }
 
@@ -894,59 +1145,11 @@ int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
     h->timed = false;
     if (h->P == 0) return 0;
     if (h->M > h->N) return fail(TLSB_ERR_ARG, "widest template is longer than the light curve");
-    int rc;
-    if (h->periods_stale && (rc = refresh_periods(h))) return rc;
     if (!records_dev) {
-        if (h->out.ensure((size_t)h->P * 24)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+        if (h->out.ensure(((size_t)h->P * 3 + 1) * 8)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
         records_dev = h->out.p;
     }
-
-    SearchArgs a{};
-    a.t = h->t.as<double>(); a.dval = h->dval.as<double>(); a.wval = h->wval.as<double>(); a.N = h->N;
-    a.tq = h->tq.as<double>(); a.rec = h->d_rec.as<WidthRec>(); a.nU = h->nU; a.M = h->M; a.pad = h->pad;
-    a.periods = h->periods.as<double>(); a.ulo = h->ulo.as<int>(); a.uhi = h->uhi.as<int>();
-    a.order = h->order.as<int>(); a.P = h->P; a.depth_min = h->prm.transit_depth_min;
-    a.out_chi2 = reinterpret_cast<double *>(records_dev);
-    a.out_depth = a.out_chi2 + h->P;
-    a.out_packed = reinterpret_cast<long long *>(a.out_depth + h->P);
-    a.counter = h->counter.as<int>();
-
-    const int grid = std::min(h->P, h->num_sms);
-    const size_t need = resident_smem_bytes(h->N, h->M, h->pad, h->N, h->nU);
-    const bool resident = h->N < 65536 && need <= h->max_smem;
-    h->resident = resident;
-    CUDA_TRY(cudaEventRecord(h->ev0, s));
-    a.w0 = h->w0;
-    auto launch = [&](auto kernel, size_t smem) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kernel<<<grid, kThreads, smem, s>>>(a);
-        return cudaGetLastError();
-    };
-    if (resident) {
-        a.NB = h->N;
-        if (h->uniform_w)
-            CUDA_TRY(launch(tlsb_search_kernel<true, true>, need));
-        else
-            CUDA_TRY(launch(tlsb_search_kernel<true, false>, need));
-    } else {
-        if (tail_bytes(h->nU) + 4096 > h->max_smem) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
-        const size_t budget = h->max_smem - tail_bytes(h->nU) - 64;
-        a.NB = (int)std::min<size_t>((size_t)h->N, budget / 4 - 2);
-        a.scratch_per_cta = streaming_scratch_bytes(h->N, h->M, h->pad);
-        if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
-        a.scratch = h->scratch.as<unsigned char>();
-        const size_t smem = align16((size_t)(a.NB + 1) * 4) + tail_bytes(h->nU);
-        if (h->uniform_w)
-            CUDA_TRY(launch(tlsb_search_kernel<false, true>, smem));
-        else
-            CUDA_TRY(launch(tlsb_search_kernel<false, false>, smem));
-    }
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(h->ev1, s));
-    h->launches = 1;
-    h->timed = true;
-    return 0;
+    return enqueue_search(h, s, records_dev, h->plan_mode == 1);
 }
 
 int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_t *row_out,
@@ -958,11 +1161,18 @@ int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_
     const size_t P = (size_t)h->P;
     if (P == 0) return 0;
     if (!h->out.p) return fail(TLSB_ERR_STATE, "tlsb_get_results: no search has written the handle's buffer");
-    std::vector<long long> packed(P);
-    CUDA_TRY(cudaMemcpyAsync(chi2_out, h->out.p, P * 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(depth_out, h->out.as<double>() + P, P * 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(packed.data(), h->out.as<double>() + 2 * P, P * 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<long long> packed(P + 1);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CUDA_TRY(cudaMemcpyAsync(chi2_out, h->out.p, P * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(depth_out, h->out.as<double>() + P, P * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(packed.data(), h->out.as<double>() + 2 * P, (P + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (packed[P] == 0 || attempt == 1) break;
+        // the device plan was not sure about some period's limits: redo with the exact host plan
+        h->fallbacks += 1;
+        int rc = enqueue_search(h, s, h->out.p, true);
+        if (rc) return rc;
+    }
     for (size_t p = 0; p < P; ++p) {
         row_out[p] = (int64_t)(uint32_t)(packed[p] & 0xffffffffLL);
         if (t0_index_out) t0_index_out[p] = (int64_t)(int32_t)(packed[p] >> 32);
@@ -971,7 +1181,19 @@ int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_
 }
 
 int64_t tlsb_last_launch_count(const tlsb_handle *h) { return h ? h->launches : 0; }
-int32_t tlsb_last_path_resident(const tlsb_handle *h) { return h && h->resident ? 1 : 0; }
+int32_t tlsb_last_path_resident(const tlsb_handle *h) { return h && h->layout.resident ? 1 : 0; }
+int64_t tlsb_plan_fallback_count(const tlsb_handle *h) { return h ? h->fallbacks : 0; }
+
+int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,
+                     int64_t *smem_bytes)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_last_layout: NULL handle");
+    if (threads) *threads = h->layout.threads;
+    if (ctas_per_sm) *ctas_per_sm = h->layout.ctas_per_sm;
+    if (queue_capacity) *queue_capacity = h->layout.qcap;
+    if (smem_bytes) *smem_bytes = (int64_t)h->layout.smem;
+    return 0;
+}
 
 double tlsb_last_search_kernel_ms(tlsb_handle *h)
 {
@@ -1014,8 +1236,8 @@ static int search_on_device(int device, const tlsb_lightcurve *lc, const double 
 {
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) {
         cudaGetLastError();
-        if (err) *err = "no CUDA device available (this library has no CPU fallback)";
-        g_error = *err;
+        g_error = "no CUDA device available (this library has no CPU fallback)";
+        if (err) *err = g_error;
         return TLSB_ERR_CUDA;
     }
     tlsb_handle *h = pool_take(device);

@@ -14,7 +14,13 @@ from __future__ import annotations
 
 import numpy as np
 
-WORDS_PER_PERIOD = 3  # chi2 | depth | packed(row, t0 index): three planes of 8-byte words
+WORDS_PER_PERIOD = 3  # chi2 | depth | packed(row, t0 index): three planes of 8-byte words,
+                      # followed by ONE status word per shard (include/tlsb200.h: tlsb_search_async)
+
+
+def record_words(capacity):
+    """8-byte words of one shard's record buffer."""
+    return WORDS_PER_PERIOD * capacity + 1
 
 
 def shard_indices(n_periods, rank, world):
@@ -31,7 +37,7 @@ def pack_records(chi2, row, depth, t0_index, capacity):
     """Host-side mirror of the kernel's record layout: int64[3 * capacity], three planes with
     the plane stride equal to the shard's own period count (as the kernel writes them)."""
     n = len(chi2)
-    out = np.zeros(WORDS_PER_PERIOD * capacity, dtype=np.int64)
+    out = np.zeros(record_words(capacity), dtype=np.int64)
     out[0:n] = np.ascontiguousarray(chi2, np.float64).view(np.int64)
     out[n:2 * n] = np.ascontiguousarray(depth, np.float64).view(np.int64)
     packed = (np.asarray(row, np.int64) & 0xFFFFFFFF) | (np.asarray(t0_index, np.int64) << 32)
@@ -40,10 +46,10 @@ def pack_records(chi2, row, depth, t0_index, capacity):
 
 
 def unpack_gathered(gathered, n_periods, world):
-    """Undo the interleaved partition: ``gathered`` is int64[world * 3 * capacity] (rank-major).
-    Returns (chi2, row, depth, t0_index) in the order of the job's period list."""
+    """Undo the interleaved partition: ``gathered`` is int64[world * (3 * capacity + 1)]
+    (rank-major).  Returns (chi2, row, depth, t0_index) in the order of the job's period list."""
     cap = shard_capacity(n_periods, world)
-    g = np.asarray(gathered, dtype=np.int64).reshape(world, WORDS_PER_PERIOD * cap)
+    g = np.asarray(gathered, dtype=np.int64).reshape(world, record_words(cap))
     chi2 = np.empty(n_periods, np.float64)
     depth = np.empty(n_periods, np.float64)
     row = np.empty(n_periods, np.int64)
@@ -57,6 +63,13 @@ def unpack_gathered(gathered, n_periods, world):
         row[idx] = packed & 0xFFFFFFFF
         t0[idx] = packed >> 32
     return chi2, row, depth, t0
+
+
+def gathered_status(gathered, n_periods, world):
+    """Sum of the shards' status words (non-zero: redo the search with the exact host plan)."""
+    cap = shard_capacity(n_periods, world)
+    g = np.asarray(gathered, dtype=np.int64).reshape(world, record_words(cap))
+    return int(sum(g[r, WORDS_PER_PERIOD * len(shard_indices(n_periods, r, world))] for r in range(world)))
 
 
 def all_gather_records(local_records, dist, world):
@@ -88,7 +101,7 @@ class ShardedSearch(object):
         self.searcher = native.Searcher(device=device)
         self.searcher.set_inputs(t, y, dy, templates, params)
         self.searcher.set_periods(self.local_periods)
-        self.records = torch.zeros(WORDS_PER_PERIOD * self.capacity, dtype=torch.int64, device="cuda:%d" % device)
+        self.records = torch.zeros(record_words(self.capacity), dtype=torch.int64, device="cuda:%d" % device)
         self.gathered = None
         if world > 1:
             self.gathered = torch.empty(world * self.records.numel(), dtype=torch.int64, device=self.records.device)
@@ -116,13 +129,31 @@ class ShardedSearch(object):
         from . import native
 
         rec = self.records.cpu().numpy()
-        return native.unpack_records(rec[: WORDS_PER_PERIOD * self.n_local], self.n_local)
+        if rec[WORDS_PER_PERIOD * self.n_local] != 0:
+            rec = self._redo_exact(lambda: self.records.cpu().numpy())
+        return native.unpack_records(rec, self.n_local)
 
     def results(self):
         """All periods' (chi2, row, depth, t0_index) in the job's period order (every rank)."""
         if self.world == 1:
             return self.local_results()
-        return unpack_gathered(self.gathered.cpu().numpy(), len(self.all_periods), self.world)
+        n = len(self.all_periods)
+        g = self.gathered.cpu().numpy()
+        if gathered_status(g, n, self.world) != 0:  # every rank sees the same flags: a collective decision
+            g = self._redo_exact(lambda: self.gathered.cpu().numpy())
+        return unpack_gathered(g, n, self.world)
+
+    def _redo_exact(self, fetch):
+        """The device plan flagged a T14 limit too close to an integer: search again with the
+        exact host plan (include/tlsb200.h: tlsb_set_plan_mode)."""
+        import torch
+
+        self.searcher.set_plan_mode(1)
+        try:
+            self.step(torch.cuda.current_stream(self.records.device))
+            return fetch()
+        finally:
+            self.searcher.set_plan_mode(0)
 
     def gather_host(self, local_out):
         """All-gather host-side results (the e2e path: results already copied back)."""

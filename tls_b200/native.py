@@ -17,7 +17,8 @@ EXPORTS = (
     "tlsb_search_periods", "tlsb_create", "tlsb_destroy", "tlsb_set_lightcurve",
     "tlsb_set_templates", "tlsb_set_periods", "tlsb_search_async", "tlsb_get_results",
     "tlsb_last_launch_count", "tlsb_last_search_kernel_ms", "tlsb_last_path_resident",
-    "tlsb_last_error", "tlsb_version", "tlsb_device_count",
+    "tlsb_last_error", "tlsb_version", "tlsb_device_count", "tlsb_set_plan_mode",
+    "tlsb_plan_fallback_count", "tlsb_last_layout",
 )
 
 _c_i64 = ctypes.c_int64
@@ -68,6 +69,10 @@ def lib():
     L.tlsb_last_search_kernel_ms.argtypes = [_c_vp]
     L.tlsb_last_path_resident.restype = ctypes.c_int32
     L.tlsb_last_path_resident.argtypes = [_c_vp]
+    L.tlsb_plan_fallback_count.restype = _c_i64
+    L.tlsb_plan_fallback_count.argtypes = [_c_vp]
+    L.tlsb_set_plan_mode.argtypes = [_c_vp, ctypes.c_int32]
+    L.tlsb_last_layout.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_create.argtypes = [ctypes.POINTER(_c_vp), ctypes.c_int32]
     L.tlsb_destroy.argtypes = [_c_vp]
     L.tlsb_set_lightcurve.argtypes = [_c_vp, ctypes.POINTER(LightCurve)]
@@ -194,6 +199,23 @@ class Searcher(object):
                "tlsb_get_results")
         return chi2, row, depth, t0
 
+    def set_plan_mode(self, mode):
+        """0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)."""
+        _check(lib().tlsb_set_plan_mode(self._h, int(mode)), "tlsb_set_plan_mode")
+
+    @property
+    def plan_fallbacks(self):
+        return int(lib().tlsb_plan_fallback_count(self._h))
+
+    @property
+    def layout(self):
+        th, cp, qc = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        sm = ctypes.c_int64()
+        _check(lib().tlsb_last_layout(self._h, ctypes.byref(th), ctypes.byref(cp), ctypes.byref(qc), ctypes.byref(sm)),
+               "tlsb_last_layout")
+        return dict(threads=th.value, ctas_per_sm=cp.value, queue_capacity=qc.value, smem_bytes=sm.value,
+                    resident=self.resident)
+
     @property
     def launch_count(self):
         return int(lib().tlsb_last_launch_count(self._h))
@@ -208,8 +230,8 @@ class Searcher(object):
 
 
 def unpack_records(records, n_periods):
-    """Split the 3-plane device record layout (chi2 | depth | row+t0<<32) copied to host."""
-    rec = np.asarray(records).reshape(3, n_periods)
+    """Split the 3-plane device record layout (chi2 | depth | row+t0<<32 [| status]) copied to host."""
+    rec = np.asarray(records)[: 3 * n_periods].reshape(3, n_periods)
     chi2 = rec[0].view(np.float64)
     depth = rec[1].view(np.float64)
     packed = rec[2].view(np.int64)
