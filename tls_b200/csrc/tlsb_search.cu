@@ -50,7 +50,8 @@ namespace {
 
 constexpr int kBlock = 5;             // R: consecutive T0 candidates one lane carries through the tap loop
                                       // (odd: neighbouring lanes sit R*stride doubles apart in shared memory)
-constexpr int kTile = 32 * kBlock;    // candidates one warp gates at a time
+constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per queue reservation
+constexpr int kTile = 32 * kBlock * kSub;  // candidates one warp gates at a time
 constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr int kPlanThreads = 1024;
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
 
     const unsigned lt_mask = (1u << lane) - 1u;
     const double depth_min = a.depth_min;
-    const int qstop = a.qcap - kW * 32;  // gating pauses here: every warp can still add one tile
+    const int qstop = a.qcap - kW * 32 * kSub;  // gating pauses here: every warp can still add one tile
 
     for (;;) {
         if (tid == 0) {
@@ -457,21 +458,28 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
         for (int b = tid; b <= NB; b += kT) H[b] = 0;
         __syncthreads();
-        for (int k = tid; k < N; k += kT)
-            atomicAdd(&H[bucket_of(fold_phase(a.t[k], r), NB) + 1], 1);
+        double *ph_unsorted = dsorted;  // [N], free until the ranking step writes the sorted d
+        for (int k = tid; k < N; k += kT) {
+            const double ph = fold_phase(a.t[k], r);
+            ph_unsorted[k] = ph;
+            atomicAdd(&H[bucket_of(ph, NB) + 1], 1);
+        }
         __syncthreads();
         // inclusive scan of H[0..NB] (H[0] = 0): H[b] = number of keys in buckets < b
         block_inclusive_scan<kT, int>(H, NB + 1, reinterpret_cast<int *>(red_d));
         for (int k = tid; k < N; k += kT) {
-            const double ph = fold_phase(a.t[k], r);
+            const double ph = ph_unsorted[k];
             const int pos = atomicAdd(&H[bucket_of(ph, NB)], 1);  // any order inside the bucket
             skey[pos] = ph;
             sid[pos] = (idx_t)k;
         }
-        __syncthreads();  // now H[b] = end of bucket b
+        __syncthreads();  // now H[b] = end of bucket b; the unsorted phases are dead
         for (int q = tid; q < N; q += kT) {
             const double key = skey[q];
             const int id = (int)sid[q];
+            const double dv = a.dval[id];  // issued early: the gather overlaps the ranking loop
+            double wv = 0.0;
+            if (!kUniformW) wv = a.wval[id];
             const int b = bucket_of(key, NB);
             const int lo = b ? H[b - 1] : 0, hi = H[b];
             int rank = lo;
@@ -480,8 +488,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                 const int is = (int)sid[s];
                 rank += (ks < key) || (ks == key && is < id);  // (phase, index): the stable order
             }
-            dsorted[rank] = a.dval[id];
-            if (!kUniformW) w[rank] = a.wval[id];
+            dsorted[rank] = dv;
+            if (!kUniformW) w[rank] = wv;
         }
         __syncthreads();  // keys are dead: cs may overwrite them
         // wrap the first M samples to the end (core.py:126-132)
@@ -527,6 +535,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         const int tile_end = rec[ulo].cum + rec[ulo].tiles;
         int g_next = rec[uhi - 1].cum + wid;
         int cur_u = uhi - 1;
+        int u_begin = rec[cur_u].cum, u_end = u_begin + rec[cur_u].tiles;  // tile range of width cur_u
         for (;;) {
             // B1
             while (g_next < tile_end) {
@@ -535,27 +544,46 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                 if (__shfl_sync(kFull, fill, 0) >= qstop) break;
                 const int g = g_next;
                 g_next += kW;
-                while (g >= rec[cur_u].cum + rec[cur_u].tiles) --cur_u;
+                while (g >= u_end) {
+                    --cur_u;
+                    u_begin = u_end;
+                    u_end = u_begin + rec[cur_u].tiles;
+                }
                 const int u = cur_u;
                 const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
                 const double invW = rec[u].invW;
-                const int c0 = (g - rec[u].cum) * kTile + lane * kBlock;
-                int mask = 0;
+                const int c_tile = (g - u_begin) * kTile + lane * kBlock;
+                int masks[kSub];
+                unsigned votes[kSub];
+                int total = 0;
 #pragma unroll
-                for (int rr = 0; rr < kBlock; ++rr) {
-                    const int c = c0 + rr;
-                    if (c < ncand) {
-                        const int i = c * X;
-                        const double mean = (cs[i + W] - cs[i]) * invW;
-                        if (mean > depth_min) mask |= 1 << rr;  // core.py:58 (the stride is built into c)
+                for (int sb = 0; sb < kSub; ++sb) {
+                    const int c0 = c_tile + sb * 32 * kBlock;
+                    int mask = 0;
+#pragma unroll
+                    for (int rr = 0; rr < kBlock; ++rr) {
+                        const int c = c0 + rr;
+                        if (c < ncand) {
+                            const int i = c * X;
+                            const double mean = (cs[i + W] - cs[i]) * invW;
+                            if (mean > depth_min) mask |= 1 << rr;  // core.py:58 (the stride is built into c)
+                        }
                     }
+                    masks[sb] = mask;
+                    votes[sb] = __ballot_sync(kFull, mask != 0);
+                    total += __popc(votes[sb]);
                 }
-                const unsigned m = __ballot_sync(kFull, mask != 0);
-                if (m) {
+                if (total) {
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_next[2], __popc(m));
+                    if (lane == 0) base = atomicAdd(&s_next[2], total);
                     base = __shfl_sync(kFull, base, 0);
-                    if (mask) queue[base + __popc(m & lt_mask)] = make_int2(c0, u | (mask << 16));
+#pragma unroll
+                    for (int sb = 0; sb < kSub; ++sb) {
+                        if (masks[sb])
+                            queue[base + __popc(votes[sb] & lt_mask)] =
+                                make_int2(c_tile + sb * 32 * kBlock, u | (masks[sb] << 16));
+                        base += __popc(votes[sb]);
+                    }
                 }
             }
             if (lane == 0 && g_next < tile_end) s_next[1] = 1;  // this warp has tiles left
@@ -840,7 +868,7 @@ Layout choose_layout(const tlsb_handle *h)
     const int N = h->N;
     if (N < 65536) {
         const int tries[2][2] = {{256, 2}, {512, 1}};
-        const int qcaps[3] = {4096, 3072, 2048};
+        const int qcaps[3] = {4096, 3584, 3072};
         for (const auto &t : tries) {
             for (int qcap : qcaps) {
                 const size_t bytes = resident_smem_bytes(N, h->M, h->pad, h->nU, h->uniform_w, qcap, t[0]);
