@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         __syncthreads();
         double *ph_unsorted = dsorted;  // [N], free until the ranking step writes the sorted d
         for (int k = tid; k < N; k += kT) {
-            const double ph = fold_phase(a.t[k], r);
+            const double ph = fold_phase(__ldcs(a.t + k), r);  // streamed: keep L1 for the templates
             ph_unsorted[k] = ph;
             atomicAdd(&H[bucket_of(ph, NB) + 1], 1);
         }
@@ -477,9 +477,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         for (int q = tid; q < N; q += kT) {
             const double key = skey[q];
             const int id = (int)sid[q];
-            const double dv = a.dval[id];  // issued early: the gather overlaps the ranking loop
+            const double dv = __ldcs(a.dval + id);  // issued early: the gather overlaps the ranking loop
             double wv = 0.0;
-            if (!kUniformW) wv = a.wval[id];
+            if (!kUniformW) wv = __ldcs(a.wval + id);
             const int b = bucket_of(key, NB);
             const int lo = b ? H[b - 1] : 0, hi = H[b];
             int rank = lo;
@@ -560,13 +560,21 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                 for (int sb = 0; sb < kSub; ++sb) {
                     const int c0 = c_tile + sb * 32 * kBlock;
                     int mask = 0;
+                    if (c0 + kBlock <= ncand) {  // straight line: ten loads in flight, then the compares
+                        const double *__restrict__ lo = cs + (size_t)c0 * X;
+                        const double *__restrict__ hi = lo + W;
+                        double mean[kBlock];
 #pragma unroll
-                    for (int rr = 0; rr < kBlock; ++rr) {
-                        const int c = c0 + rr;
-                        if (c < ncand) {
-                            const int i = c * X;
-                            const double mean = (cs[i + W] - cs[i]) * invW;
-                            if (mean > depth_min) mask |= 1 << rr;  // core.py:58 (the stride is built into c)
+                        for (int rr = 0; rr < kBlock; ++rr) mean[rr] = (hi[rr * X] - lo[rr * X]) * invW;
+#pragma unroll
+                        for (int rr = 0; rr < kBlock; ++rr) mask |= (mean[rr] > depth_min ? 1 : 0) << rr;  // core.py:58
+                    } else {  // the last, partial block of this width (or nothing)
+                        for (int rr = 0; rr < kBlock; ++rr) {
+                            const int c = c0 + rr;
+                            if (c < ncand) {
+                                const int i = c * X;
+                                if ((cs[i + W] - cs[i]) * invW > depth_min) mask |= 1 << rr;
+                            }
                         }
                     }
                     masks[sb] = mask;
