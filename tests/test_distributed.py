@@ -1,0 +1,78 @@
+"""Host logic of the one-process-per-GPU path (tls_b200/distributed.py) on CPU: interleaved
+period partition, the kernel's record layout, ONE all-gather (gloo, world_size 2 and 3), and the
+un-interleave.  The per-rank search is stood in by the oracle (test infrastructure)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REPO, load_search_golden
+from tls_b200 import distributed as D
+
+
+def test_partition_covers_every_period_once():
+    for n, world in ((10, 1), (10, 3), (9679, 8), (5, 8)):
+        seen = np.concatenate([D.shard_indices(n, r, world) for r in range(world)])
+        assert sorted(seen) == list(range(n))
+        assert max(len(D.shard_indices(n, r, world)) for r in range(world)) == D.shard_capacity(n, world)
+
+
+def test_pack_unpack_round_trip():
+    rng = np.random.RandomState(0)
+    n, world = 1001, 4
+    chi2 = rng.rand(n) * 1e4
+    chi2[3] = np.inf
+    depth = rng.rand(n)
+    row = rng.randint(0, 200, n)
+    t0 = rng.randint(-1, 70000, n)
+    cap = D.shard_capacity(n, world)
+    shards = []
+    for r in range(world):
+        idx = D.shard_indices(n, r, world)
+        shards.append(D.pack_records(chi2[idx], row[idx], depth[idx], t0[idx], cap))
+    got = D.unpack_gathered(np.concatenate(shards), n, world)
+    for a, b in zip(got, (chi2, row, depth, t0)):
+        np.testing.assert_array_equal(a, b)
+    assert D.gathered_status(np.concatenate(shards), n, world) == 0
+    shards[2][3 * len(D.shard_indices(n, 2, world))] = 5  # a shard flags 5 uncertain periods
+    assert D.gathered_status(np.concatenate(shards), n, world) == 5
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = load_search_golden("small")
+    n = len(g["periods"])
+    idx = D.shard_indices(n, rank, world)
+    chi2, row, depth = oracle.search_periods_c(g["t"], g["y"], g["dy"], g["periods"][idx], g["templates"], g["params"], threads=1)
+    rec = torch.from_numpy(D.pack_records(chi2, row, depth, np.full(len(idx), -1), D.shard_capacity(n, world)))
+    gathered = D.all_gather_records(rec, dist, world)  # the one collective of the search
+    full = D.unpack_gathered(gathered.numpy(), n, world)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), chi2=full[0], row=full[1], depth=full[2])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_over_gloo_equals_single_process(world, tmp_path):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = load_search_golden("small")
+    for rank in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        np.testing.assert_array_equal(z["row"], g["row"])
+        np.testing.assert_allclose(z["chi2"], g["chi2"], rtol=1e-9)
+        np.testing.assert_allclose(z["depth"], g["depth"], rtol=1e-9)
