@@ -36,6 +36,7 @@ if REPO not in sys.path:
 
 import numpy as np  # noqa: E402
 
+_emit = print
 METRIC = "trial-periods/sec (full duration x T0 scan)"
 UNIT = "periods/s"
 
@@ -169,7 +170,9 @@ def cpu_sample(inp, periods, seconds, threads=0):
     for about `seconds` of wall time.  Returns (periods/s, sample size, threads)."""
     from oracle import oracle
 
-    cores = oracle.host_threads() if threads == 0 else threads
+    if threads == 0:
+        threads = os.cpu_count() or 1  # explicit: torchrun exports OMP_NUM_THREADS=1
+    cores = threads
     probe = periods[np.linspace(0, len(periods) - 1, min(len(periods), 8 * cores)).astype(int)]
     oracle.search_periods_c(inp.t, inp.y, inp.dy, probe[:cores], inp.templates, inp.params, threads=threads)  # warm
     t0 = time.perf_counter()
@@ -217,16 +220,16 @@ def run_reference(args):
         periods = periods[: args.max_periods * args.gpus]
     from oracle import oracle
 
-    cores = oracle.host_threads()
+    cores = os.cpu_count() or 1
     # size one step for a few seconds of CPU work
     rate, n0, _ = cpu_sample(inp, periods, 2.0)
     per_step = int(min(len(periods), max(cores * 8, rate * 3.0)))
     sample = periods[np.linspace(0, len(periods) - 1, per_step).astype(int)]
     for _ in range(max(1, min(args.warmup, 3))):
-        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample[: max(cores * 4, per_step // 8)], inp.templates, inp.params)
+        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample[: max(cores * 4, per_step // 8)], inp.templates, inp.params, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample, inp.templates, inp.params)
+        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample, inp.templates, inp.params, threads=cores)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     what = "%d of %d periods per step (evenly spread), C restatement of core.search_period, OpenMP" % (per_step, len(periods))
@@ -240,7 +243,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     return 0
 
 
@@ -401,7 +404,7 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "parity": parity,
         }
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     job.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -410,6 +413,16 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    # Only the JSON line may reach stdout (NCCL / libraries print there): park the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+
+    def _emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
+
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

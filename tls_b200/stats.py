@@ -52,8 +52,8 @@ def rp_rs_from_depth(depth, law, params):
     """Planet/star radius ratio from the maximum depth, Heller (2019)
     (stats.py:21-69; same validation messages)."""
     laws = "linear, quadratic, squareroot, logarithmic, nonlinear"
-    values = list(np.atleast_1d(params)) if not isinstance(params, (int, float)) else [params]
-    if not all(isinstance(v, (float, int)) for v in values):
+    values = [params] if isinstance(params, (int, float)) else list(params)
+    if not all(isinstance(v, (float, int, np.floating, np.integer)) and not isinstance(v, bool) for v in values):
         raise ValueError("All limb-darkening parameters must be numbers")
     if law not in laws:
         raise ValueError("Please provide a supported limb-darkening law:", laws)
