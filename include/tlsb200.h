@@ -131,6 +131,29 @@ int32_t tlsb_last_path_resident(const tlsb_handle *h);
 int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,
                      int64_t *smem_bytes);
 
+/* ---- final_T0_fit (stats.py:135-204, called from main.py:273-283) ----
+ * After the period search the reference scans `n_trials` mid-transit epochs at the best
+ * period: fold(t, period, Tx) (core.py:9-12), stable argsort (stats.py:173), roll the sorted
+ * flux by int(dur/2)+1 (stats.py:186-190), sum (flux - model)^2 / weight^2 over the first
+ * `dur` slots and (flux - 1)^2 / weight^2 over the rest (stats.py:193-195), where the
+ * reference's weight is the rolled flux rolled once more (stats.py:191 — dy has no effect;
+ * kept).  One CUDA launch does all trials against the handle's resident light curve.
+ *   model_in[dur]   1 - (1 - signal) / (SIGNAL_DEPTH / (1 - depth))          (stats.py:141-143)
+ *   trials[n]       numpy.linspace(min(t), min(t) + period, points)            (stats.py:154-156)
+ *   residuals_out   residuals_total of every trial, in trial order            (stats.py:195)
+ *   best_index_out  optional: first index of the minimum (strict '<', stats.py:200-202), -1 if
+ *                   no residual is below +inf.  T0 = trials[best_index].
+ * Synchronous: returns after the results are on the host. */
+int tlsb_final_t0_fit(tlsb_handle *h, void *cuda_stream, const double *model_in, int64_t dur,
+                      double period, const double *trials, int64_t n_trials,
+                      double *residuals_out, int64_t *best_index_out);
+/* Same, one-shot with HOST light-curve buffers (device < 0: current device). */
+int tlsb_final_t0_fit_lc(const tlsb_lightcurve *lc, int32_t device, const double *model_in,
+                         int64_t dur, double period, const double *trials, int64_t n_trials,
+                         double *residuals_out, int64_t *best_index_out);
+/* Device time [ms] of the most recent T0-fit kernel of this handle (CUDA events). */
+double tlsb_last_t0_fit_ms(const tlsb_handle *h);
+
 const char *tlsb_last_error(void);
 const char *tlsb_version(void);
 int32_t tlsb_device_count(void);

@@ -252,11 +252,70 @@ def case_power():
     save_power("sentinel", t, y, dy, "no-fit branch", transit_depth_min=1000e-6, T0_fit_margin=0.1)
 
 
+# ------------------------------------------------------------------ final_T0_fit goldens
+def save_t0fit(name, t, y, signal, depth, period, margin, note):
+    """Reference stats.final_T0_fit (stats.py:135-204, unmodified) -> T0; the per-trial residuals
+    come from the oracle's restatement, which must pick the same T0."""
+    from transitleastsquares.stats import final_T0_fit as ref_fit
+
+    from oracle import oracle
+
+    t0 = time.time()
+    dy = np.full(len(y), np.std(y))
+    T0_ref = ref_fit(signal=np.array(signal, float), depth=depth, t=t, y=y, dy=dy.copy(), period=period,
+                     T0_fit_margin=margin, show_progress_bar=False, verbose=False)
+    T0_orc, resid, trials = oracle.final_T0_fit_numpy(signal, depth, t, y, dy, period, margin)
+    assert T0_ref == T0_orc, (name, T0_ref, T0_orc)
+    np.savez_compressed(os.path.join(OUT, "t0fit_%s.npz" % name), t=t, y=y, signal=np.asarray(signal, float),
+                        depth=np.float64(depth), period=np.float64(period), margin=np.float64(margin),
+                        T0=np.float64(T0_ref), residuals=resid, trials=trials, note=np.array(note))
+    print("%-22s N=%6d dur=%4d trials=%6d T0=%.6f  (%.1fs)" % (name, len(y), len(signal), len(trials), T0_ref, time.time() - t0))
+
+
+def _best_of(inp, stride=1):
+    """Best (signal, depth, period) of a search over every `stride`-th period (oracle C port)."""
+    from oracle import oracle
+
+    per = inp.periods[::stride]
+    chi2, row, depth = oracle.search_periods_c(inp.t, inp.y, inp.dy, per, inp.templates, inp.params)
+    k = int(np.argmin(chi2))
+    return inp.lc_arr[int(row[k])], float(depth[k]), float(per[k])
+
+
+def case_t0fit():
+    t, y, dy, kw = workloads.lightcurve("cfg1")
+    inp = prepared(t, y, dy, **kw)
+    sig, depth, period = _best_of(inp)
+    save_t0fit("cfg1", inp.t, inp.y, sig, depth, period, 0.01, "cfg-1 best model, default margin (points = N)")
+    save_t0fit("cfg1_margin1", inp.t, inp.y, sig, depth, period, 1.0, "cfg-1, T0_fit_margin=1 (coarse scan)")
+    t, y, dy, kw = workloads.lightcurve("small", hetero=True)
+    inp = prepared(t, y, dy, **kw)
+    sig, depth, period = _best_of(inp)
+    save_t0fit("small_margin0", inp.t, inp.y, sig, depth, period, 0.0, "N=720, T0_fit_margin=0 (every sample)")
+    # repeated and unsorted time stamps: the stable order of equal phases matters
+    rng = np.random.RandomState(5)
+    tt = np.round(inp.t, 1)
+    perm = rng.permutation(len(tt))
+    save_t0fit("ties_unsorted", tt[perm], inp.y[perm], sig, depth, 2.0, 0.01, "time stamps rounded to 0.1 d and shuffled, period 2 d")
+    t, y, dy = k2_multi_planet()
+    inp = prepared(t, y, dy)
+    sig, depth, period = _best_of(inp, 9)
+    save_t0fit("k2_epic201367065", inp.t, inp.y, sig, depth, period, 0.01, "EPIC 201367065 (irregular sampling)")
+    t, y, dy, kw = workloads.lightcurve("cfg3")
+    inp = prepared(t, y, dy, **kw)
+    sig, depth, period = _best_of(inp, 20)
+    save_t0fit("cfg3_margin02", inp.t, inp.y, sig, depth, period, 0.2, "cfg-3 (N=19440), margin 0.2")
+    t, y, dy, kw = workloads.lightcurve("cfg2")
+    inp = prepared(t, y, dy, **kw)
+    row = int(np.argmin(np.abs(inp.overview["width_in_samples"] - 24)))
+    save_t0fit("cfg2_margin1", inp.t, inp.y, inp.lc_arr[row], 1 - 8.4e-5, 10.123, 1.0, "cfg-2 (N=70128, streaming path), injected period, margin 1")
+
+
 CASES = {
     "cfg1_50ppm": case_cfg1_50ppm, "cfg1_500ppm": case_cfg1_500ppm, "cfg1_hetero": case_cfg1_hetero,
     "sentinel": case_sentinel, "margins": case_margins, "small": case_small_and_ties,
     "ragged": case_ragged_templates, "no_admissible": case_no_admissible, "cfg3": case_cfg3,
-    "cfg2": case_cfg2, "k2": case_k2, "power": case_power,
+    "cfg2": case_cfg2, "k2": case_k2, "power": case_power, "t0fit": case_t0fit,
 }
 
 if __name__ == "__main__":

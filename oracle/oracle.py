@@ -165,3 +165,46 @@ def search_period_numpy(period, t, y, dy, templates, params):
         if this < best:
             best, best_row, best_depth = this, row, this_depth
     return best, best_row, best_depth
+
+
+# ---------------------------------------------------------------- final_T0_fit restatement
+SIGNAL_DEPTH = 0.5  # tls_constants.py:71
+
+
+def final_T0_fit_numpy(signal, depth, t, y, dy, period, T0_fit_margin, trials=None):
+    """stats.py:135-204 statement by statement; returns ``(T0, residuals_total per trial, trials)``.
+
+    ``fold`` (core.py:9-12) is written in the reciprocal-multiply form numba's fastmath build
+    executes.  The ``dy`` overwrite of stats.py:191 is kept: after the first iteration the
+    weights are the rolled flux rolled again, and because ``dy = dy[sort_index]`` is itself
+    overwritten before use (stats.py:175 then :191), ``dy`` never reaches the residuals."""
+    signal = np.asarray(signal, dtype=float)
+    dur = len(signal)
+    scale = SIGNAL_DEPTH / (1 - depth)
+    model_in = 1 - ((1 - signal) / scale)
+    n = np.size(y)
+    if trials is None:
+        if T0_fit_margin == 0:
+            points = n
+        else:
+            points = int(n / (T0_fit_margin * dur))
+        if points > n:
+            points = n
+        trials = np.linspace(start=np.min(t), stop=np.min(t) + period, num=points)
+    ones = np.ones(len(y[dur:]))
+    lowest, T0 = float("inf"), 0
+    out = np.empty(len(trials))
+    r = 1.0 / period
+    for k, Tx in enumerate(trials):
+        x = (t - Tx) * r
+        phases = x - np.floor(x)
+        idx = np.argsort(phases, kind="mergesort")
+        flux = y[idx]
+        roll = int(dur / 2) + 1
+        flux = np.concatenate([flux[-roll:], flux[:-roll]])
+        w = np.concatenate([flux[-roll:], flux[:-roll]])
+        total = np.sum((flux[:dur] - model_in) ** 2 / w[:dur] ** 2) + np.sum((flux[dur:] - ones) ** 2 / w[dur:] ** 2)
+        out[k] = total
+        if total < lowest:
+            lowest, T0 = total, Tx
+    return T0, out, trials

@@ -51,3 +51,13 @@ def has_cuda():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def t0fit_goldens():
+    return sorted(os.path.basename(p)[len("t0fit_"):-4] for p in glob.glob(os.path.join(GOLDEN, "t0fit_*.npz")))
+
+
+def load_t0fit_golden(name):
+    """Inputs of stats.final_T0_fit + the reference's T0 and the oracle's per-trial residuals."""
+    z = np.load(os.path.join(GOLDEN, "t0fit_%s.npz" % name))
+    return {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}

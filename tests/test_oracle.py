@@ -3,7 +3,7 @@ produced by the reference's own numba path (oracle/make_golden.py)."""
 import numpy as np
 import pytest
 
-from conftest import assert_search_parity, load_search_golden, search_goldens
+from conftest import assert_search_parity, load_search_golden, load_t0fit_golden, search_goldens, t0fit_goldens
 from oracle import oracle
 
 
@@ -31,3 +31,14 @@ def test_single_thread_equals_all_threads():
     b = oracle.search_periods_c(g["t"], g["y"], g["dy"], g["periods"], g["templates"], g["params"], threads=0)
     for x, y in zip(a, b):
         np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.parametrize("name", [n for n in t0fit_goldens() if n != "cfg2_margin1"])
+def test_numpy_t0_fit_matches_reference(name):
+    """oracle.final_T0_fit_numpy against T0 returned by the reference's stats.final_T0_fit."""
+    g = load_t0fit_golden(name)
+    dy = np.full(len(g["y"]), np.std(g["y"]))
+    T0, resid, trials = oracle.final_T0_fit_numpy(g["signal"], g["depth"], g["t"], g["y"], dy, g["period"], g["margin"])
+    assert T0 == g["T0"]
+    np.testing.assert_array_equal(trials, g["trials"])
+    np.testing.assert_allclose(resid, g["residuals"], rtol=1e-12)

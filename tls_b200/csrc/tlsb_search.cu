@@ -289,6 +289,56 @@ __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] sh
     }
 }
 
+// Phase fold + stable sort of one trial (core.py:15-18 + :120-123, or stats.py:172-176 with an
+// epoch): histogram of NB phase buckets -> block scan -> scatter (any order inside a bucket) ->
+// rank inside the bucket by (phase, index) = numpy's stable mergesort order; src1 (and src2) are
+// gathered to their sorted slots in dst1 (dst2).  dst1 doubles as the store of the unsorted
+// phases until the ranking step; skey/sid/H are scratch.  Ends WITHOUT a barrier.
+template <int kT, typename idx_t, bool kTwo, bool kEpoch>
+__device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, double T0, double r, int N, int NB,
+                                                 int *H, double *skey, idx_t *sid,
+                                                 const double *__restrict__ src1, const double *__restrict__ src2,
+                                                 double *dst1, double *dst2, int *scan_scratch)
+{
+    const int tid = threadIdx.x;
+    for (int b = tid; b <= NB; b += kT) H[b] = 0;
+    __syncthreads();
+    double *ph_unsorted = dst1;  // [N], free until the ranking step writes the sorted values
+    for (int k = tid; k < N; k += kT) {
+        const double tk = __ldcs(t + k);  // streamed: keep L1 for the templates
+        const double ph = fold_phase(kEpoch ? tk - T0 : tk, r);
+        ph_unsorted[k] = ph;
+        atomicAdd(&H[bucket_of(ph, NB) + 1], 1);
+    }
+    __syncthreads();
+    // inclusive scan of H[0..NB] (H[0] = 0): H[b] = number of keys in buckets < b
+    block_inclusive_scan<kT, int>(H, NB + 1, scan_scratch);
+    for (int k = tid; k < N; k += kT) {
+        const double ph = ph_unsorted[k];
+        const int pos = atomicAdd(&H[bucket_of(ph, NB)], 1);  // any order inside the bucket
+        skey[pos] = ph;
+        sid[pos] = (idx_t)k;
+    }
+    __syncthreads();  // now H[b] = end of bucket b; the unsorted phases are dead
+    for (int q = tid; q < N; q += kT) {
+        const double key = skey[q];
+        const int id = (int)sid[q];
+        const double v1 = __ldcs(src1 + id);  // issued early: the gather overlaps the ranking loop
+        double v2 = 0.0;
+        if (kTwo) v2 = __ldcs(src2 + id);
+        const int b = bucket_of(key, NB);
+        const int lo = b ? H[b - 1] : 0, hi = H[b];
+        int rank = lo;
+        for (int s = lo; s < hi; ++s) {
+            const double ks = skey[s];
+            const int is = (int)sid[s];
+            rank += (ks < key) || (ks == key && is < id);  // (phase, index): the stable order
+        }
+        dst1[rank] = v1;
+        if (kTwo) dst2[rank] = v2;
+    }
+}
+
 struct Best {
     double chi2;
     double D;
@@ -456,41 +506,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         }
 
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
-        for (int b = tid; b <= NB; b += kT) H[b] = 0;
-        __syncthreads();
-        double *ph_unsorted = dsorted;  // [N], free until the ranking step writes the sorted d
-        for (int k = tid; k < N; k += kT) {
-            const double ph = fold_phase(__ldcs(a.t + k), r);  // streamed: keep L1 for the templates
-            ph_unsorted[k] = ph;
-            atomicAdd(&H[bucket_of(ph, NB) + 1], 1);
-        }
-        __syncthreads();
-        // inclusive scan of H[0..NB] (H[0] = 0): H[b] = number of keys in buckets < b
-        block_inclusive_scan<kT, int>(H, NB + 1, reinterpret_cast<int *>(red_d));
-        for (int k = tid; k < N; k += kT) {
-            const double ph = ph_unsorted[k];
-            const int pos = atomicAdd(&H[bucket_of(ph, NB)], 1);  // any order inside the bucket
-            skey[pos] = ph;
-            sid[pos] = (idx_t)k;
-        }
-        __syncthreads();  // now H[b] = end of bucket b; the unsorted phases are dead
-        for (int q = tid; q < N; q += kT) {
-            const double key = skey[q];
-            const int id = (int)sid[q];
-            const double dv = __ldcs(a.dval + id);  // issued early: the gather overlaps the ranking loop
-            double wv = 0.0;
-            if (!kUniformW) wv = __ldcs(a.wval + id);
-            const int b = bucket_of(key, NB);
-            const int lo = b ? H[b - 1] : 0, hi = H[b];
-            int rank = lo;
-            for (int s = lo; s < hi; ++s) {
-                const double ks = skey[s];
-                const int is = (int)sid[s];
-                rank += (ks < key) || (ks == key && is < id);  // (phase, index): the stable order
-            }
-            dsorted[rank] = dv;
-            if (!kUniformW) w[rank] = wv;
-        }
+        fold_sort_gather<kT, idx_t, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, dsorted, w,
+                                                       reinterpret_cast<int *>(red_d));
         __syncthreads();  // keys are dead: cs may overwrite them
         // wrap the first M samples to the end (core.py:126-132)
         for (int k = tid; k < NM; k += kT) cs[k + 1] = dsorted[k < N ? k : k - N];
@@ -697,6 +714,105 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// final_T0_fit (stats.py:135-204): at the best period, every trial epoch Tx folds the light
+// curve with fold(t, period, Tx) (core.py:9-12), sorts it stably (stats.py:173), rolls the
+// sorted flux by dur/2+1 (stats.py:186-190), and sums the weighted residuals against the
+// in-transit model (first dur samples) and against 1 (the rest).  The reference overwrites
+// its weights with a SECOND roll of the rolled flux (stats.py:191), so the weight of slot k is
+// 1 / flux_sorted[k - 2*shift]^2 and dy plays no part; that quirk is kept.
+// One CTA per trial epoch, persistent; same fold + bucket-rank sort as the search kernel.
+struct T0Args {
+    const double *t;       // [N]
+    const double *y;       // [N]
+    int N;
+    const double *trials;  // [n_trials] numpy.linspace(min(t), min(t)+period, points), made on the host
+    int n_trials;
+    const double *model;   // [dur] 1 - (1 - signal) / (SIGNAL_DEPTH / (1 - depth)), stats.py:141-143
+    int dur;
+    int shift;             // int(dur / 2) + 1
+    double period;
+    double *residuals;     // [n_trials]
+    int *counter;          // [2] next trial, finished CTAs
+    int NB;
+    unsigned char *scratch;
+    size_t scratch_per_cta;
+};
+
+template <int kT, bool kResident>
+__global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_t0fit_kernel(const __grid_constant__ T0Args a)
+{
+    constexpr int kW = kT / 32;
+    using idx_t = typename std::conditional<kResident, unsigned short, unsigned int>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = a.N, NB = a.NB;
+    const size_t n_even = ((size_t)N + 1) & ~(size_t)1;
+
+    double *skey, *ys;
+    idx_t *sid;
+    int *H;
+    unsigned char *tail;
+    if (kResident) {
+        skey = reinterpret_cast<double *>(smem_raw);
+        ys = skey + n_even;
+        H = reinterpret_cast<int *>(ys + n_even);
+        sid = reinterpret_cast<idx_t *>(H + ((NB + 2) & ~1));
+        tail = reinterpret_cast<unsigned char *>(sid) + (((size_t)N * sizeof(idx_t) + 15) & ~(size_t)15);
+    } else {
+        unsigned char *g = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
+        skey = reinterpret_cast<double *>(g);
+        ys = skey + n_even;
+        sid = reinterpret_cast<idx_t *>(ys + n_even);
+        H = reinterpret_cast<int *>(smem_raw);
+        tail = smem_raw + (((size_t)(NB + 1) * 4 + 15) & ~(size_t)15);
+    }
+    double *red_d = reinterpret_cast<double *>(tail);  // [kW + 2]
+    int *s_next = reinterpret_cast<int *>(red_d + kW + 2);
+
+    const double r = 1.0 / a.period;
+    const int dur = a.dur, sh1 = a.shift % N, sh2 = (2 * (a.shift % N)) % N;
+    for (;;) {
+        if (tid == 0) s_next[0] = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int trial = s_next[0];
+        if (trial >= a.n_trials) break;
+        const double T0 = a.trials[trial];
+        fold_sort_gather<kT, idx_t, false, true>(a.t, T0, r, N, NB, H, skey, sid, a.y, nullptr, ys, nullptr,
+                                                 reinterpret_cast<int *>(red_d));
+        __syncthreads();
+        double part = 0.0;
+        for (int k = tid; k < N; k += kT) {
+            int k1 = k - sh1, k2 = k - sh2;
+            if (k1 < 0) k1 += N;
+            if (k2 < 0) k2 += N;
+            const double flux = ys[k1], wsrc = ys[k2];
+            const double ref = k < dur ? __ldg(a.model + k) : 1.0;
+            const double diff = flux - ref;
+            part += (diff * diff) / (wsrc * wsrc);  // stats.py:193-194
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(kFull, part, off);
+        if (lane == 0) red_d[wid] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double total = 0.0;
+            for (int k = 0; k < kW; ++k) total += red_d[k];  // fixed order: deterministic
+            a.residuals[trial] = total;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        __threadfence();
+        const int done = atomicAdd(a.counter + 1, 1);
+        if (done == (int)gridDim.x - 1) {
+            a.counter[0] = 0;
+            a.counter[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // d = 1 - y, w = 1/dy^2 (core.py:127 computes 1/dy**2 the same way), once per light curve.
 __global__ void tlsb_prepare_kernel(const double *__restrict__ y, const double *__restrict__ dy,
                                     double *__restrict__ dval, double *__restrict__ wval, int n)
@@ -779,6 +895,10 @@ struct tlsb_handle {
     bool host_plan_valid = false;
     // outputs / scheduling / scratch
     DevBuf out, counter, scratch;
+    // final_T0_fit
+    DevBuf t0_trials, t0_model, t0_resid;
+    bool t0_resident = false;
+    double t0_ms = 0.0;
     // bookkeeping
     int64_t launches = 0;
     int64_t fallbacks = 0;
@@ -1028,8 +1148,8 @@ int tlsb_create(tlsb_handle **out, int32_t device)
     h->smem_per_sm = prop.sharedMemPerMultiprocessor;
     CUDA_TRY(cudaEventCreate(&h->ev0));
     CUDA_TRY(cudaEventCreate(&h->ev1));
-    if (h->counter.ensure(16)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
-    CUDA_TRY(cudaMemset(h->counter.p, 0, 16));
+    if (h->counter.ensure(32)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    CUDA_TRY(cudaMemset(h->counter.p, 0, 32));  // [0,1] search kernel, [2,3] T0-fit kernel
     *out = h;
     return 0;
 }
@@ -1039,7 +1159,8 @@ int tlsb_destroy(tlsb_handle *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo,
-                      &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch})
+                      &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch, &h->t0_trials, &h->t0_model,
+                      &h->t0_resid})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1338,6 +1459,126 @@ int tlsb_search_periods(const tlsb_lightcurve *lc, const double *periods, int64_
     for (int g = 0; g < G; ++g)
         if (rcs[g]) return fail(rcs[g], errs[g]);
     return 0;
+}
+
+}  // extern "C"
+
+// ---- final_T0_fit -------------------------------------------------------------------------
+namespace {
+
+template <typename K>
+cudaError_t launch_t0(K kernel, const T0Args &a, int grid, int threads, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, threads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+int run_t0_fit(tlsb_handle *h, cudaStream_t s, const double *model_in, int64_t dur, double period,
+               const double *trials, int64_t n_trials, double *residuals_out, int64_t *best_index_out)
+{
+    if (!h->have_lc) return fail(TLSB_ERR_STATE, "tlsb_final_t0_fit: set the light curve first");
+    if (!model_in || !trials || !residuals_out) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: NULL argument");
+    const int N = h->N;
+    if (dur < 1 || dur > N) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: need 1 <= dur <= n");
+    if (n_trials < 1 || n_trials > (int64_t)1 << 30) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: bad trial count");
+    if (!(period > 0)) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: period must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload(h->t0_trials, trials, sizeof(double) * (size_t)n_trials, s))) return rc;
+    if ((rc = upload(h->t0_model, model_in, sizeof(double) * (size_t)dur, s))) return rc;
+    if (h->t0_resid.ensure(sizeof(double) * (size_t)n_trials)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+
+    T0Args a{};
+    a.t = h->t.as<double>(); a.y = h->y.as<double>(); a.N = N;
+    a.trials = h->t0_trials.as<double>(); a.n_trials = (int)n_trials;
+    a.model = h->t0_model.as<double>(); a.dur = (int)dur; a.shift = (int)(dur / 2) + 1;  // stats.py:186
+    a.period = period;
+    a.residuals = h->t0_resid.as<double>();
+    a.counter = h->counter.as<int>() + 2;
+
+    // layout: sort keys + sorted flux (+ ids, histogram) in shared memory when they fit
+    const size_t n_even = ((size_t)N + 1) & ~(size_t)1;
+    bool resident = false;
+    int threads = 256, per_sm = 2;
+    size_t smem = 0;
+    if (N < 65536) {
+        const int tries[2][2] = {{256, 2}, {512, 1}};
+        for (const auto &t : tries) {
+            const size_t tail = (size_t)(t[0] / 32 + 2) * 8 + 32;
+            const size_t bytes = 2 * n_even * 8 + (size_t)((N + 2) & ~1) * 4 + align16((size_t)N * 2) + tail;
+            if (bytes > h->max_smem || (bytes + 1024) * (size_t)t[1] > h->smem_per_sm) continue;
+            resident = true; threads = t[0]; per_sm = t[1]; smem = bytes; a.NB = N;
+            break;
+        }
+    }
+    const int grid = (int)std::min<int64_t>(n_trials, (int64_t)h->num_sms * per_sm);
+    if (!resident) {
+        threads = 256; per_sm = 2;
+        const size_t tail = (size_t)(threads / 32 + 2) * 8 + 32;
+        const size_t per_cta = std::min(h->max_smem, h->smem_per_sm / 2 - 1024);
+        a.NB = (int)std::min<size_t>((size_t)N, (per_cta - tail - 64) / 4 - 2);
+        smem = align16((size_t)(a.NB + 1) * 4) + tail;
+        a.scratch_per_cta = (2 * n_even * 8 + (size_t)N * 4 + 255) & ~(size_t)255;
+        if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
+        a.scratch = h->scratch.as<unsigned char>();
+    }
+    h->t0_resident = resident;
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    if (resident && threads == 256) CUDA_TRY(launch_t0(tlsb_t0fit_kernel<256, true>, a, grid, 256, smem, s));
+    else if (resident) CUDA_TRY(launch_t0(tlsb_t0fit_kernel<512, true>, a, grid, 512, smem, s));
+    else CUDA_TRY(launch_t0(tlsb_t0fit_kernel<256, false>, a, grid, 256, smem, s));
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    CUDA_TRY(cudaMemcpyAsync(residuals_out, h->t0_resid.p, sizeof(double) * (size_t)n_trials, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->t0_ms = ms; else cudaGetLastError();
+    h->timed = false;
+    if (best_index_out) {  // stats.py:200-202: strict '<' from +inf, so the first minimum wins and NaN never does
+        int64_t best = -1;
+        double lowest = INFINITY;
+        for (int64_t k = 0; k < n_trials; ++k)
+            if (residuals_out[k] < lowest) { lowest = residuals_out[k]; best = k; }
+        *best_index_out = best;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tlsb_final_t0_fit(tlsb_handle *h, void *cuda_stream, const double *model_in, int64_t dur, double period,
+                      const double *trials, int64_t n_trials, double *residuals_out, int64_t *best_index_out)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: NULL handle");
+    return run_t0_fit(h, reinterpret_cast<cudaStream_t>(cuda_stream), model_in, dur, period, trials, n_trials,
+                      residuals_out, best_index_out);
+}
+
+double tlsb_last_t0_fit_ms(const tlsb_handle *h) { return h ? h->t0_ms : 0.0; }
+
+int tlsb_final_t0_fit_lc(const tlsb_lightcurve *lc, int32_t device, const double *model_in, int64_t dur,
+                         double period, const double *trials, int64_t n_trials, double *residuals_out,
+                         int64_t *best_index_out)
+{
+    if (!lc) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit_lc: NULL light curve");
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(TLSB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    tlsb_handle *h = pool_take(device);
+    int rc = h ? 0 : tlsb_create(&h, device);
+    if (!rc) rc = tlsb_set_lightcurve(h, lc);
+    if (!rc) rc = run_t0_fit(h, nullptr, model_in, dur, period, trials, n_trials, residuals_out, best_index_out);
+    if (rc) {
+        std::string keep = g_error;
+        tlsb_destroy(h);
+        g_error = keep;
+    } else
+        pool_give(h);
+    return rc;
 }
 
 }  // extern "C"

@@ -108,6 +108,7 @@ class transitleastsquares(object):
             print("Using the B200 search kernels (use_threads=%d is accepted and ignored)" % self.use_threads)
 
         chi2_by_input, rows_by_input, depths_by_input = self._search(inputs, devices)
+        self._t0_device = None if devices is None else int(np.atleast_1d(devices)[0])
 
         # main.py:190-196: ascending period order
         order = np.argsort(periods)
@@ -159,7 +160,7 @@ class transitleastsquares(object):
             T0 = stats.final_T0_fit(
                 signal=lc_arr[best_row], depth=depth, t=t, y=y, dy=dy, period=period,
                 T0_fit_margin=self.T0_fit_margin, show_progress_bar=self.show_progress_bar,
-                verbose=self.verbose,
+                verbose=self.verbose, device=getattr(self, "_t0_device", None),
             )
             transit_times = stats.all_transit_times(T0, t, period)
             transit_duration = stats.calculate_transit_duration_in_days(t, period, transit_times, duration)

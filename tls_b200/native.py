@@ -19,6 +19,7 @@ EXPORTS = (
     "tlsb_last_launch_count", "tlsb_last_search_kernel_ms", "tlsb_last_path_resident",
     "tlsb_last_error", "tlsb_version", "tlsb_device_count", "tlsb_set_plan_mode",
     "tlsb_plan_fallback_count", "tlsb_last_layout",
+    "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
 )
 
 _c_i64 = ctypes.c_int64
@@ -83,6 +84,11 @@ def lib():
     L.tlsb_search_periods.argtypes = [
         ctypes.POINTER(LightCurve), _c_vp, _c_i64, ctypes.POINTER(Templates), ctypes.POINTER(Params),
         ctypes.POINTER(Exec), _c_vp, _c_vp, _c_vp, _c_vp]
+    L.tlsb_final_t0_fit.argtypes = [_c_vp, _c_vp, _c_vp, _c_i64, ctypes.c_double, _c_vp, _c_i64, _c_vp, _c_vp]
+    L.tlsb_final_t0_fit_lc.argtypes = [ctypes.POINTER(LightCurve), ctypes.c_int32, _c_vp, _c_i64, ctypes.c_double,
+                                       _c_vp, _c_i64, _c_vp, _c_vp]
+    L.tlsb_last_t0_fit_ms.restype = ctypes.c_double
+    L.tlsb_last_t0_fit_ms.argtypes = [_c_vp]
     _LIB = L
     return L
 
@@ -150,6 +156,22 @@ def search_periods(t, y, dy, periods, templates, params, devices=None, return_t0
     return (chi2, row, depth, t0) if return_t0_index else (chi2, row, depth)
 
 
+def final_t0_fit(t, y, dy, model_in, period, trials, device=None):
+    """All trial epochs of stats.py:165-202 in one launch (``tlsb_final_t0_fit_lc``, HOST buffers).
+
+    Returns ``(best_index, residuals)``; ``T0 = trials[best_index]``."""
+    t, y, dy = _f64(t), _f64(y), _f64(dy)
+    model_in, trials = _f64(model_in), _f64(trials)
+    lc = LightCurve(_ptr(t), _ptr(y), _ptr(dy), len(t))
+    resid = np.empty(len(trials), np.float64)
+    best = ctypes.c_int64(-1)
+    rc = lib().tlsb_final_t0_fit_lc(ctypes.byref(lc), -1 if device is None else int(device), _ptr(model_in),
+                                    len(model_in), float(period), _ptr(trials), len(trials), _ptr(resid),
+                                    ctypes.byref(best))
+    _check(rc, "tlsb_final_t0_fit_lc")
+    return int(best.value), resid
+
+
 class Searcher(object):
     """Handle API: inputs stay resident in HBM between searches."""
 
@@ -198,6 +220,20 @@ class Searcher(object):
         _check(lib().tlsb_get_results(self._h, _c_vp(stream or 0), _ptr(chi2), _ptr(row), _ptr(depth), _ptr(t0)),
                "tlsb_get_results")
         return chi2, row, depth, t0
+
+    def final_t0_fit(self, model_in, period, trials, stream=None):
+        """``tlsb_final_t0_fit`` on the resident light curve -> ``(best_index, residuals)``."""
+        model_in, trials = _f64(model_in), _f64(trials)
+        resid = np.empty(len(trials), np.float64)
+        best = ctypes.c_int64(-1)
+        _check(lib().tlsb_final_t0_fit(self._h, _c_vp(stream or 0), _ptr(model_in), len(model_in), float(period),
+                                       _ptr(trials), len(trials), _ptr(resid), ctypes.byref(best)),
+               "tlsb_final_t0_fit")
+        return int(best.value), resid
+
+    @property
+    def t0_fit_ms(self):
+        return float(lib().tlsb_last_t0_fit_ms(self._h))
 
     def set_plan_mode(self, mode):
         """0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)."""

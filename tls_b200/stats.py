@@ -5,7 +5,7 @@ Everything here runs AFTER the GPU period search and turns its per-period
 the results object.  Each function restates, in behaviour including quirks, the
 function of the same name in ``/root/reference/transitleastsquares/stats.py``
 (line ranges in the docstrings).  Out of scope as GPU work in this round
-(SURVEY.md §8f); ``final_T0_fit`` is the first candidate to move.
+(SURVEY.md §8f); ``final_T0_fit`` already runs on the GPU.
 """
 from __future__ import annotations
 
@@ -113,45 +113,37 @@ def spectra(chi2, oversampling_factor):
     return SR, power_raw, power, SDE_raw, SDE
 
 
-def final_T0_fit(signal, depth, t, y, dy, period, T0_fit_margin, show_progress_bar, verbose):
-    """Scan mid-transit epochs at the best period and return the best T0
-    (stats.py:135-204).
-
-    Quirk kept on purpose: the reference overwrites its weights
-    with a second roll of the already rolled flux (stats.py:191), so the
-    residuals are weighted by 1/flux^2 and the ``dy`` argument has no effect."""
+def t0_fit_inputs(signal, depth, t, y, period, T0_fit_margin):
+    """Host-side inputs of the T0 scan (stats.py:141-156): the in-transit model scaled to the
+    fitted depth and the grid of trial epochs."""
     dur = len(signal)
     scale = C.SIGNAL_DEPTH / (1 - depth)
-    model_in = 1 - ((1 - signal) / scale)
+    model_in = 1 - ((1 - np.asarray(signal, dtype=float)) / scale)
     n = np.size(y)
     points = n if T0_fit_margin == 0 else int(n / (T0_fit_margin * dur))
     points = min(points, n)
     trials = np.linspace(start=np.min(t), stop=np.min(t) + period, num=points)
+    return model_in, trials
 
+
+def final_T0_fit(signal, depth, t, y, dy, period, T0_fit_margin, show_progress_bar, verbose, device=None):
+    """Scan mid-transit epochs at the best period and return the best T0 (stats.py:135-204).
+
+    The loop over trial epochs (stats.py:165-202: fold, stable argsort, roll, weighted
+    residuals) runs on the B200 in ONE launch through ``tlsb_final_t0_fit_lc``
+    (``include/tlsb200.h``); there is no CPU fallback.  Quirk kept on purpose (SURVEY.md
+    §3.3): the reference overwrites its weights with a second roll of the already rolled
+    flux (stats.py:191), so the residuals are weighted by 1/flux^2 and ``dy`` has no effect.
+    ``show_progress_bar`` is accepted and ignored (the scan takes a millisecond)."""
+    from . import native
+
+    model_in, trials = t0_fit_inputs(signal, depth, t, y, period, T0_fit_margin)
     if verbose:
         print("Searching for best T0 for period", format(period, ".5f"), "days")
-    bar = None
-    if points > C.PROGRESSBAR_THRESHOLD and show_progress_bar:
-        from tqdm import tqdm
-
-        bar = tqdm(total=np.size(trials))
-
-    shift = int(dur / 2) + 1
-    best, T0 = float("inf"), 0
-    for Tx in trials:
-        order = np.argsort(fold(t, period, Tx), kind="mergesort")
-        flux = np.roll(y[order], shift)
-        weight_src = np.roll(flux, shift)  # stats.py:191
-        inside = np.sum((flux[:dur] - model_in) ** 2 / weight_src[:dur] ** 2)
-        outside = np.sum((flux[dur:] - 1.0) ** 2 / weight_src[dur:] ** 2)
-        total = inside + outside
-        if bar is not None:
-            bar.update(1)
-        if total < best:
-            best, T0 = total, Tx
-    if bar is not None:
-        bar.close()
-    return T0
+    if len(trials) == 0:
+        return 0
+    best, _ = native.final_t0_fit(t, y, dy, model_in, period, trials, device=device)
+    return trials[best] if best >= 0 else 0  # stats.py:163: T0 = 0 when nothing is below +inf
 
 
 def all_transit_times(T0, t, period):
