@@ -378,7 +378,10 @@ def run_b200(args):
             "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
             "algorithmic_bytes_per_period": alg_bytes / P_rank, "mean_admissible_widths": mean_widths,
             "kernel_share_of_step": k_ms * args.steps / float(sum(step_ms)),
-            "path": "resident (folded curve in shared memory)" if job.resident else "streaming (per-CTA L2 scratch)",
+            "path": {"resident": "resident (folded curve in shared memory)",
+                     "tiled": "tiled (phase A in L2 scratch, phase B from bulk-copy staged shared-memory chunks)",
+                     "streaming": "streaming (per-CTA L2 scratch)"}[job.searcher.path],
+            "layout": job.searcher.layout,
         }
         traffic_file = os.path.join(REPO, "profiles", "traffic_%s.json" % args.workload)
         if os.path.exists(traffic_file):

@@ -127,6 +127,16 @@ double tlsb_last_search_kernel_ms(tlsb_handle *h);
 /* 1 if the most recent search ran with the folded light curve resident in shared memory,
  * 0 if it streamed it through global scratch. */
 int32_t tlsb_last_path_resident(const tlsb_handle *h);
+/* Which kernel layout the most recent search used: 1 = resident (folded curve in shared memory),
+ * 2 = tiled (phase A in global scratch, phase B from shared-memory chunks staged with bulk async
+ * copies), 3 = streaming (everything through L1/L2; last resort for windows wider than a chunk). */
+int32_t tlsb_last_path(const tlsb_handle *h);
+/* Chunk capacity [doubles per staged array] of the most recent tiled search (0 otherwise). */
+int32_t tlsb_last_chunk(const tlsb_handle *h);
+/* Force a layout (tests, experiments): path 0 = automatic (default), 1..3 as above; a search
+ * fails with TLSB_ERR_ARG if the forced layout cannot hold the inputs.  chunk_doubles > 0 caps
+ * the tiled path's chunk capacity so that small inputs exercise several chunks. */
+int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles);
 /* Launch shape of the most recent search kernel (any pointer may be NULL). */
 int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,
                      int64_t *smem_bytes);

@@ -126,3 +126,68 @@ def test_cuda_matches_c_oracle_on_seeded_inputs(workload, hetero, count):
     got = native.search_periods(inp.t, inp.y, inp.dy, periods, inp.templates, inp.params)
     ref = dict(y=inp.y, chi2=want[0], row=want[1], depth=want[2])
     assert_search_parity(got, ref, rtol=RTOL, label=workload)
+
+
+def _search_with_path(native, g, path, chunk=0):
+    s = native.Searcher()
+    s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
+    s.set_periods(g["periods"])
+    s.set_path(path, chunk)
+    s.search_async()
+    out = s.results()
+    info = s.layout
+    s.close()
+    return out, info
+
+
+@pytest.mark.parametrize("name", [n for n in search_goldens() if n not in ("cfg2",)])
+def test_tiled_path_matches_reference_golden(name):
+    """Every golden through the TILED kernel (bulk-copy staged chunks) with a chunk capacity small
+    enough that the folded curve spans several chunks; results must equal the automatic path's."""
+    native = _native()
+    g = load_search_golden(name)
+    if len(g["periods"]) > 600:
+        sel = np.linspace(0, len(g["periods"]) - 1, 600).astype(int)
+        g = dict(g, periods=g["periods"][sel], chi2=g["chi2"][sel], row=g["row"][sel], depth=g["depth"][sel])
+    n = len(g["y"])
+    out, info = _search_with_path(native, g, "tiled", chunk=max(256, n // 3))
+    assert info["path"] == "tiled"
+    assert_search_parity(out[:3], g, rtol=RTOL, label=name + " tiled")
+    auto, _ = _search_with_path(native, g, "auto")
+    np.testing.assert_array_equal(out[1], auto[1])
+    np.testing.assert_array_equal(out[3], auto[3])  # same best window start
+    np.testing.assert_allclose(out[0], auto[0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["small", "cfg1_hetero", "ragged_L", "ties_unsorted", "cfg3"])
+def test_streaming_path_matches_reference_golden(name):
+    """The last-resort layout (everything through L1/L2) stays correct."""
+    native = _native()
+    g = load_search_golden(name)
+    if len(g["periods"]) > 300:
+        sel = np.linspace(0, len(g["periods"]) - 1, 300).astype(int)
+        g = dict(g, periods=g["periods"][sel], chi2=g["chi2"][sel], row=g["row"][sel], depth=g["depth"][sel])
+    out, info = _search_with_path(native, g, "streaming")
+    assert info["path"] == "streaming"
+    assert_search_parity(out[:3], g, rtol=RTOL, label=name + " streaming")
+
+
+def test_automatic_layout_choice():
+    native = _native()
+    for name, want in (("small", "resident"), ("cfg1_50ppm", "resident"), ("cfg3", "tiled"), ("cfg2", "tiled")):
+        g = load_search_golden(name)
+        g = dict(g, periods=g["periods"][:8])
+        _, info = _search_with_path(native, g, "auto")
+        assert info["path"] == want, (name, info)
+
+
+def test_forced_resident_path_refuses_what_does_not_fit():
+    native = _native()
+    g = load_search_golden("cfg2")
+    s = native.Searcher()
+    s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
+    s.set_periods(g["periods"][:4])
+    s.set_path("resident")
+    with pytest.raises(RuntimeError, match="resident"):
+        s.search_async()
+    s.close()

@@ -36,6 +36,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -137,6 +138,7 @@ struct SearchArgs {
     unsigned char *scratch;
     size_t scratch_per_cta;
     int NB;               // number of phase buckets
+    int chunk;            // tiled path: doubles per staged array (cs / w / wd) in shared memory
 };
 
 // tls_constants.py:20-25,78 and grid.py:9-32 (T14); same operation order on host and device
@@ -715,6 +717,367 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------
+// Tiled path (light curves too long for the resident path): phase A runs in a per-CTA global
+// scratch; phase B walks the folded curve in POSITION CHUNKS.  One elected thread stages
+// cs[a0, a0+C), wd[a0, a0+C) (and w) of the chunk into shared memory with 1-D bulk async
+// copies (TMA, cp.async.bulk -> mbarrier complete_tx), then the same gate / survivor queue /
+// register-blocked tap loop as the resident kernel runs from shared memory for every
+// candidate block that STARTS inside [a0, a0+TP), TP = C - (widest admissible window + the
+// tap loop's overshoot).  Each folded sample is read from L2 once per chunk instead of twice
+// per admissible width.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TLSB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TLSB_DONE;\n"
+        "bra TLSB_WAIT;\n"
+        "TLSB_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// what a candidate block of width record wr may read behind its start offset
+__host__ __device__ inline int window_need(int W, int X) { return W + kPadGroups * kBlock * X + 2; }
+
+template <int kT, bool kUniformW>
+__global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_kernel(const __grid_constant__ SearchArgs a)
+{
+    constexpr int kW = kT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = a.N, M = a.M, NM = N + M, NB = a.NB, nU = a.nU;
+    const int NMP = NM + a.pad;
+    const int C = a.chunk;
+
+    // ---- global scratch of this CTA: cs | [w] | wd | sid  (every array 16-byte aligned) -------
+    const size_t cs_elems = ((size_t)NM + 2) & ~(size_t)1;
+    const size_t nmp_even = ((size_t)NMP + 1) & ~(size_t)1;
+    unsigned char *g = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
+    double *cs = reinterpret_cast<double *>(g);
+    double *w = cs + cs_elems;
+    double *wd = kUniformW ? w : w + nmp_even;
+    unsigned *sid = reinterpret_cast<unsigned *>(wd + nmp_even);
+    double *skey = cs;
+    double *dsorted = wd;
+
+    // ---- shared: queue | chunk of cs | [chunk of w] | chunk of wd | records, tables, scratch ----
+    int2 *queue = reinterpret_cast<int2 *>(smem_raw);
+    double *cs_s = reinterpret_cast<double *>(queue + a.qcap);
+    double *w_s = cs_s + C;
+    double *wd_s = kUniformW ? w_s : w_s + C;
+    int *H = reinterpret_cast<int *>(cs_s);  // phase A only: the histogram borrows the chunk area
+    WidthRec *rec = reinterpret_cast<WidthRec *>(wd_s + C);                   // [nU]
+    double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(red_d + 2 * kW + 2);
+    int *red_i = reinterpret_cast<int *>(bar + 1);                            // [2*kW]
+    int *s_next = red_i + 2 * kW;  // [8] period slot, "tiles left" flag, queue fill, queue head, chunk tiles
+    int *ch_lo = s_next + 8;       // [nU] first candidate of the chunk, per width
+    int *ch_hi = ch_lo + nU;       // [nU] one past the last
+    int *ch_tiles = ch_hi + nU;    // [nU]
+
+    for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
+        reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned parity = 0;
+
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double depth_min = a.depth_min;
+    const int qstop = a.qcap - kW * 32 * kSub;
+
+    for (;;) {
+        if (tid == 0) s_next[0] = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int slot_p = s_next[0];
+        if (slot_p >= a.P) break;
+        const int p = a.order[slot_p];
+        const double period = a.periods[p];
+        const double r = 1.0 / period;
+        const int ulo = a.ulo[p], uhi = a.uhi[p];
+
+        if (ulo >= uhi) {  // core.py:139-140,158-160
+            if (tid == 0) {
+                a.out_chi2[p] = INFINITY;
+                a.out_depth[p] = 0.0;
+                a.out_packed[p] = (long long)0 | ((long long)(unsigned)-1 << 32);
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- A. fold + stable sort + gather, wrap, w*d, T, cumulative sums (global scratch) ----
+        fold_sort_gather<kT, unsigned, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, dsorted, w,
+                                                          reinterpret_cast<int *>(red_d));
+        __syncthreads();
+        for (int k = tid; k < NM; k += kT) cs[k + 1] = dsorted[k < N ? k : k - N];
+        if (tid == 0) cs[0] = 0.0;
+        __syncthreads();
+        double tpart = 0.0;
+        for (int k = tid; k < (int)nmp_even; k += kT) {
+            if (k < NM) {
+                const double d = cs[k + 1];
+                const double wv = kUniformW ? a.w0 : w[k < N ? k : k - N];
+                const double x = wv * d;
+                if (!kUniformW && k >= N) w[k] = wv;
+                wd[k] = x;
+                if (k < N) tpart = fma(x, d, tpart);
+            } else {
+                wd[k] = 0.0;
+                if (!kUniformW) w[k] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
+        if (lane == 0) red_d[kW + 1 + wid] = tpart;
+        __syncthreads();
+        block_inclusive_scan<kT, double>(cs + 1, NM, red_d);
+        double T = 0.0;
+        for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];
+        fence_proxy_async();  // this thread's global writes -> visible to the bulk copies below
+
+        // ---- B. chunks ---------------------------------------------------------------------
+        Best best;
+        best.chi2 = (double)N;
+        best.D = 0.0;
+        best.u = -1;
+        best.i = -1;
+        const int TP = (C - window_need(rec[uhi - 1].W, rec[uhi - 1].X)) & ~1;
+        const int i_last = NM - rec[ulo].W;  // the narrowest admissible width has the most offsets
+        for (int a0 = 0; a0 <= i_last; a0 += TP) {
+            fence_proxy_async();
+            __syncthreads();  // phase A / the previous chunk are done with the staging area and the tables
+            if (tid == 0) {
+                const int len_cs = min(C, (int)cs_elems - a0);
+                const int len_wd = min(C, (int)nmp_even - a0);
+                mbar_expect_tx(bar, 8u * (unsigned)(len_cs + (kUniformW ? 1 : 2) * len_wd));
+                bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
+                if (!kUniformW) bulk_copy_g2s(w_s, w + a0, 8u * (unsigned)len_wd, bar);
+                bulk_copy_g2s(wd_s, wd + a0, 8u * (unsigned)len_wd, bar);
+                s_next[1] = 0;
+                s_next[2] = 0;
+                s_next[3] = 0;
+            }
+            if (wid == kW - 1) {  // candidate range and tiles of every admissible width in this chunk
+                int total = 0;
+                for (int base = 0; base < uhi - ulo; base += 32) {
+                    const int idx = base + lane;
+                    int tiles = 0;
+                    if (idx < uhi - ulo) {
+                        const int u = uhi - 1 - idx;
+                        const int X = rec[u].X;
+                        int lo = (a0 + X - 1) / X;
+                        int hi = (a0 + TP + X - 1) / X;
+                        if (hi > rec[u].ncand) hi = rec[u].ncand;
+                        if (hi < lo) hi = lo;
+                        tiles = (hi - lo + kTile - 1) / kTile;
+                        ch_lo[u] = lo;
+                        ch_hi[u] = hi;
+                        ch_tiles[u] = tiles;
+                    }
+#pragma unroll
+                    for (int off = 16; off; off >>= 1) tiles += __shfl_xor_sync(kFull, tiles, off);
+                    total += tiles;
+                }
+                if (lane == 0) s_next[4] = total;
+            }
+            __syncthreads();
+            const int tile_end = s_next[4];
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            const double *csb = cs_s - a0, *wb = w_s - a0, *wdb = wd_s - a0;  // indexable by global offsets
+
+            int g_next = wid;
+            int cur_u = uhi - 1;
+            int u_begin = 0, u_end = ch_tiles[cur_u];
+            for (;;) {
+                // B1: gate
+                while (g_next < tile_end) {
+                    int fill = 0;
+                    if (lane == 0) fill = *(volatile int *)&s_next[2];
+                    if (__shfl_sync(kFull, fill, 0) >= qstop) break;
+                    const int gt = g_next;
+                    g_next += kW;
+                    while (gt >= u_end) {
+                        --cur_u;
+                        u_begin = u_end;
+                        u_end = u_begin + ch_tiles[cur_u];
+                    }
+                    const int u = cur_u;
+                    const int W = rec[u].W, X = rec[u].X, c_end = ch_hi[u];
+                    const double invW = rec[u].invW;
+                    const int c_tile = ch_lo[u] + (gt - u_begin) * kTile + lane * kBlock;
+                    int masks[kSub];
+                    unsigned votes[kSub];
+                    int total = 0;
+#pragma unroll
+                    for (int sb = 0; sb < kSub; ++sb) {
+                        const int c0 = c_tile + sb * 32 * kBlock;
+                        int mask = 0;
+                        if (c0 + kBlock <= c_end) {
+                            const double *__restrict__ lo = csb + (size_t)c0 * X;
+                            const double *__restrict__ hi = lo + W;
+                            double mean[kBlock];
+#pragma unroll
+                            for (int rr = 0; rr < kBlock; ++rr) mean[rr] = (hi[rr * X] - lo[rr * X]) * invW;
+#pragma unroll
+                            for (int rr = 0; rr < kBlock; ++rr) mask |= (mean[rr] > depth_min ? 1 : 0) << rr;  // core.py:58
+                        } else {
+                            for (int rr = 0; rr < kBlock; ++rr) {
+                                const int c = c0 + rr;
+                                if (c < c_end) {
+                                    const int i = c * X;
+                                    if ((csb[i + W] - csb[i]) * invW > depth_min) mask |= 1 << rr;
+                                }
+                            }
+                        }
+                        masks[sb] = mask;
+                        votes[sb] = __ballot_sync(kFull, mask != 0);
+                        total += __popc(votes[sb]);
+                    }
+                    if (total) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_next[2], total);
+                        base = __shfl_sync(kFull, base, 0);
+#pragma unroll
+                        for (int sb = 0; sb < kSub; ++sb) {
+                            if (masks[sb])
+                                queue[base + __popc(votes[sb] & lt_mask)] =
+                                    make_int2(c_tile + sb * 32 * kBlock, u | (masks[sb] << 16));
+                            base += __popc(votes[sb]);
+                        }
+                    }
+                }
+                if (lane == 0 && g_next < tile_end) s_next[1] = 1;
+                __syncthreads();
+                const int qfill = s_next[2];
+                const bool more = s_next[1] != 0;
+                // B2: taps
+                for (;;) {
+                    int h = 0;
+                    if (lane == 0) h = atomicAdd(&s_next[3], 32);
+                    h = __shfl_sync(kFull, h, 0);
+                    if (h >= qfill) break;
+                    if (h + lane < qfill) {
+                        const int2 e = queue[h + lane];
+                        const int u = e.y & 0xffff, mask = e.y >> 16;
+                        const WidthRec wr = rec[u];
+                        const int i0 = e.x * wr.X;
+                        double A[kBlock], B[kBlock];
+                        if (wr.X == 1)
+                            tap_block<true, kUniformW>(wr, a.tq, wb, wdb, i0, A, B);
+                        else
+                            tap_block<false, kUniformW>(wr, a.tq, wb, wdb, i0, A, B);
+#pragma unroll
+                        for (int rr = 0; rr < kBlock; ++rr) {
+                            if (mask & (1 << rr)) {
+                                const int i = i0 + rr * wr.X;
+                                const double mean = (csb[i + wr.W] - csb[i]) * wr.invW;
+                                const double D = mean * wr.os;
+                                const double Aq = kUniformW ? a.w0 * wr.sq2 : A[rr];
+                                double chi = T + D * (D * Aq - 2.0 * B[rr]);
+                                if (wr.L < wr.W) chi -= untouched_tail<kUniformW>(wb, wdb, a.w0, i + wr.L, i + wr.W);
+                                if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
+                            }
+                        }
+                    }
+                }
+                if (!more) break;
+                __syncthreads();
+                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
+                __syncthreads();
+            }
+        }
+
+        // ---- C. block arg-min with the reference's tie order ---------------------------
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            Best o;
+            o.chi2 = __shfl_xor_sync(kFull, best.chi2, off);
+            o.D = __shfl_xor_sync(kFull, best.D, off);
+            o.u = __shfl_xor_sync(kFull, best.u, off);
+            o.i = __shfl_xor_sync(kFull, best.i, off);
+            if (better(o.chi2, o.u, o.i, best)) best = o;
+        }
+        __syncthreads();
+        if (lane == 0) {
+            red_d[wid] = best.chi2;
+            red_d[kW + wid] = best.D;
+            red_i[wid] = best.u;
+            red_i[kW + wid] = best.i;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            Best b2;
+            b2.chi2 = (double)N; b2.D = 0.0; b2.u = -1; b2.i = -1;
+            if (lane < kW) {
+                b2.chi2 = red_d[lane];
+                b2.D = red_d[kW + lane];
+                b2.u = red_i[lane];
+                b2.i = red_i[kW + lane];
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                Best o;
+                o.chi2 = __shfl_xor_sync(kFull, b2.chi2, off);
+                o.D = __shfl_xor_sync(kFull, b2.D, off);
+                o.u = __shfl_xor_sync(kFull, b2.u, off);
+                o.i = __shfl_xor_sync(kFull, b2.i, off);
+                if (better(o.chi2, o.u, o.i, b2)) b2 = o;
+            }
+            if (lane == 0) {
+                if (b2.u >= 0) {
+                    a.out_chi2[p] = b2.chi2;
+                    a.out_depth[p] = 1.0 - b2.D;  // core.py:74
+                    a.out_packed[p] = (long long)(unsigned)rec[b2.u].row | ((long long)b2.i << 32);
+                } else {
+                    a.out_chi2[p] = (double)N;
+                    a.out_depth[p] = 0.0;
+                    a.out_packed[p] = (long long)(unsigned)rec[ulo].row | ((long long)(unsigned)-1 << 32);
+                }
+            }
+        }
+        fence_proxy_async();  // chunk reads (generic proxy) before the next period's bulk copies
+        __syncthreads();
+    }
+
+    if (tid == 0) {
+        __threadfence();
+        const int done = atomicAdd(a.counter + 1, 1);
+        if (done == (int)gridDim.x - 1) {
+            a.counter[0] = 0;
+            a.counter[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // final_T0_fit (stats.py:135-204): at the best period, every trial epoch Tx folds the light
 // curve with fold(t, period, Tx) (core.py:9-12), sorts it stably (stats.py:173), rolls the
 // sorted flux by dur/2+1 (stats.py:186-190), and sums the weighted residuals against the
@@ -857,6 +1220,8 @@ struct DevBuf {
 // How one search is laid out on the SM (chosen per search from N, M, the bank and the device).
 struct Layout {
     bool resident = false;
+    bool tiled = false;    // not resident: phase B from shared-memory chunks staged by bulk async copies
+    int chunk = 0;         // doubles per staged array
     int threads = 256;     // 256 (two CTAs per SM) or 512 (one)
     int ctas_per_sm = 2;
     int qcap = 4096;
@@ -891,6 +1256,8 @@ struct tlsb_handle {
     std::vector<double> h_periods;
     DevBuf periods, ulo, uhi, order, bin_of;
     bool have_periods = false;
+    int path_mode = 0;            // 0 auto, 1 resident, 2 tiled, 3 streaming (tlsb_set_path)
+    int chunk_cap = 0;            // tiled path: cap of the chunk capacity in doubles (tests), 0 = none
     int plan_mode = 0;            // 0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)
     bool host_plan_valid = false;
     // outputs / scheduling / scratch
@@ -994,7 +1361,7 @@ Layout choose_layout(const tlsb_handle *h)
 {
     Layout best;
     const int N = h->N;
-    if (N < 65536) {
+    if (N < 65536 && h->path_mode <= 1) {
         const int tries[2][2] = {{256, 2}, {512, 1}};
         const int qcaps[3] = {4096, 3584, 3072};
         for (const auto &t : tries) {
@@ -1017,7 +1384,44 @@ Layout choose_layout(const tlsb_handle *h)
             }
         }
     }
+    // Tiled path: phase A in global scratch, phase B from staged chunks.  The chunk must hold the
+    // widest window of the bank plus a useful number of start offsets.
+    const size_t NM = (size_t)N + h->M, NMP = NM + h->pad;
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
+    const size_t nmp_even = (NMP + 1) & ~(size_t)1;
+    const int narr = h->uniform_w ? 2 : 3;
+    int need_max = 0;
+    for (const WidthRec &wr : h->recs) need_max = std::max(need_max, window_need(wr.W, wr.X));
+    const char *force = std::getenv("TLSB_TILED");  // "0": never, "256"/"512": force that CTA size (experiments)
+    const int forced = force ? std::atoi(force) : -1;
+    if (forced != 0 && h->path_mode != 3) {
+        const int tries[2][3] = {{256, 2, 3072}, {512, 1, 4096}};  // threads, CTAs per SM, queue entries
+        for (const auto &t : tries) {
+            if (forced > 0 && forced != t[0]) continue;
+            const size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);
+            const size_t fixed = (size_t)t[2] * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128;
+            if (per_cta <= fixed) continue;
+            long long C = (long long)(((per_cta - fixed) / (8 * (size_t)narr)) & ~(size_t)1);
+            if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~1LL);
+            const long long TP = C - need_max;
+            if (h->chunk_cap > 0 && TP < 2) continue;
+            // two CTAs per SM only when a chunk still starts a few thousand offsets; one big CTA otherwise
+            if (h->chunk_cap <= 0 && TP < (t[1] == 2 && forced < 0 ? 2048 : 256)) continue;
+            best.resident = false;
+            best.tiled = true;
+            best.threads = t[0];
+            best.ctas_per_sm = t[1];
+            best.qcap = t[2];
+            best.chunk = (int)C;
+            best.NB = (int)std::min<long long>(N, (long long)narr * C * 2 - 2);
+            best.smem = (size_t)t[2] * 8 + (size_t)narr * (size_t)C * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128;
+            best.scratch_per_cta = (cs + (size_t)(narr - 1) * nmp_even * 8 + (size_t)N * 4 + 255) & ~(size_t)255;
+            return best;
+        }
+    }
+    // Last resort (a window wider than shared memory can stage): everything through L1/L2.
     best.resident = false;
+    best.tiled = false;
     best.threads = 256;
     best.ctas_per_sm = 2;
     best.qcap = 4096;
@@ -1026,8 +1430,6 @@ Layout choose_layout(const tlsb_handle *h)
     const size_t budget = per_cta > fixed ? per_cta - fixed : 0;
     best.NB = (int)std::min<size_t>((size_t)N, budget / 4 > 2 ? budget / 4 - 2 : 0);
     best.smem = (size_t)best.qcap * 8 + align16((size_t)(best.NB + 1) * 4) + tail_bytes(h->nU, best.threads);
-    const size_t NM = (size_t)N + h->M, NMP = NM + h->pad;
-    const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
     best.scratch_per_cta = (cs + (h->uniform_w ? 1 : 2) * NMP * 8 + (size_t)N * 4 + 255) & ~(size_t)255;
     return best;
 }
@@ -1073,6 +1475,8 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
 
     const Layout lay = choose_layout(h);
     h->layout = lay;
+    if (h->path_mode == 1 && !lay.resident) return fail(TLSB_ERR_ARG, "tlsb_set_path: the folded curve does not fit shared memory (resident path)");
+    if (h->path_mode == 2 && !lay.tiled) return fail(TLSB_ERR_ARG, "tlsb_set_path: the widest window does not fit a shared-memory chunk (tiled path)");
     SearchArgs a{};
     a.t = h->t.as<double>(); a.dval = h->dval.as<double>(); a.wval = h->wval.as<double>(); a.N = h->N;
     a.tq = h->tq.as<double>(); a.rec = h->d_rec.as<WidthRec>(); a.nU = h->nU; a.M = h->M; a.pad = h->pad;
@@ -1084,6 +1488,7 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     a.counter = h->counter.as<int>();
     a.qcap = lay.qcap;
     a.NB = lay.NB;
+    a.chunk = lay.chunk;
     const int grid = std::min(P, h->num_sms * lay.ctas_per_sm);
     if (!lay.resident) {
         if (lay.NB < 1) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
@@ -1099,6 +1504,12 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     } else if (lay.resident) {
         if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<512, true, true>, a, grid, 512, lay.smem, s));
         else CUDA_TRY(launch_search(tlsb_search_kernel<512, true, false>, a, grid, 512, lay.smem, s));
+    } else if (lay.tiled && lay.threads == 256) {
+        if (uni) CUDA_TRY(launch_search(tlsb_search_tiled_kernel<256, true>, a, grid, 256, lay.smem, s));
+        else CUDA_TRY(launch_search(tlsb_search_tiled_kernel<256, false>, a, grid, 256, lay.smem, s));
+    } else if (lay.tiled) {
+        if (uni) CUDA_TRY(launch_search(tlsb_search_tiled_kernel<512, true>, a, grid, 512, lay.smem, s));
+        else CUDA_TRY(launch_search(tlsb_search_tiled_kernel<512, false>, a, grid, 512, lay.smem, s));
     } else {
         if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<256, false, true>, a, grid, 256, lay.smem, s));
         else CUDA_TRY(launch_search(tlsb_search_kernel<256, false, false>, a, grid, 256, lay.smem, s));
@@ -1291,6 +1702,14 @@ int tlsb_set_plan_mode(tlsb_handle *h, int32_t mode)
     return 0;
 }
 
+int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles)
+{
+    if (!h || path < 0 || path > 3 || chunk_doubles < 0) return fail(TLSB_ERR_ARG, "tlsb_set_path: path must be 0..3, chunk >= 0");
+    h->path_mode = path;
+    h->chunk_cap = chunk_doubles;
+    return 0;
+}
+
 int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
 {
     if (!h) return fail(TLSB_ERR_ARG, "tlsb_search_async: NULL handle");
@@ -1339,6 +1758,8 @@ int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_
 
 int64_t tlsb_last_launch_count(const tlsb_handle *h) { return h ? h->launches : 0; }
 int32_t tlsb_last_path_resident(const tlsb_handle *h) { return h && h->layout.resident ? 1 : 0; }
+int32_t tlsb_last_path(const tlsb_handle *h) { return !h ? 0 : h->layout.resident ? 1 : h->layout.tiled ? 2 : 3; }
+int32_t tlsb_last_chunk(const tlsb_handle *h) { return h ? h->layout.chunk : 0; }
 int64_t tlsb_plan_fallback_count(const tlsb_handle *h) { return h ? h->fallbacks : 0; }
 
 int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,

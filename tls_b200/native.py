@@ -20,6 +20,7 @@ EXPORTS = (
     "tlsb_last_error", "tlsb_version", "tlsb_device_count", "tlsb_set_plan_mode",
     "tlsb_plan_fallback_count", "tlsb_last_layout",
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
+    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path",
 )
 
 _c_i64 = ctypes.c_int64
@@ -87,6 +88,11 @@ def lib():
     L.tlsb_final_t0_fit.argtypes = [_c_vp, _c_vp, _c_vp, _c_i64, ctypes.c_double, _c_vp, _c_i64, _c_vp, _c_vp]
     L.tlsb_final_t0_fit_lc.argtypes = [ctypes.POINTER(LightCurve), ctypes.c_int32, _c_vp, _c_i64, ctypes.c_double,
                                        _c_vp, _c_i64, _c_vp, _c_vp]
+    L.tlsb_last_path.restype = ctypes.c_int32
+    L.tlsb_last_path.argtypes = [_c_vp]
+    L.tlsb_last_chunk.restype = ctypes.c_int32
+    L.tlsb_last_chunk.argtypes = [_c_vp]
+    L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
     L.tlsb_last_t0_fit_ms.restype = ctypes.c_double
     L.tlsb_last_t0_fit_ms.argtypes = [_c_vp]
     _LIB = L
@@ -239,6 +245,22 @@ class Searcher(object):
         """0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)."""
         _check(lib().tlsb_set_plan_mode(self._h, int(mode)), "tlsb_set_plan_mode")
 
+    PATHS = {0: "auto", 1: "resident", 2: "tiled", 3: "streaming"}
+
+    def set_path(self, path, chunk=0):
+        """Force a kernel layout: 'auto', 'resident', 'tiled' or 'streaming'; ``chunk`` caps the tiled
+        path's chunk capacity in doubles (tests)."""
+        code = {v: k for k, v in self.PATHS.items()}[path] if isinstance(path, str) else int(path)
+        _check(lib().tlsb_set_path(self._h, code, int(chunk)), "tlsb_set_path")
+
+    @property
+    def path(self):
+        return self.PATHS.get(int(lib().tlsb_last_path(self._h)), "?")
+
+    @property
+    def chunk(self):
+        return int(lib().tlsb_last_chunk(self._h))
+
     @property
     def plan_fallbacks(self):
         return int(lib().tlsb_plan_fallback_count(self._h))
@@ -250,7 +272,7 @@ class Searcher(object):
         _check(lib().tlsb_last_layout(self._h, ctypes.byref(th), ctypes.byref(cp), ctypes.byref(qc), ctypes.byref(sm)),
                "tlsb_last_layout")
         return dict(threads=th.value, ctas_per_sm=cp.value, queue_capacity=qc.value, smem_bytes=sm.value,
-                    resident=self.resident)
+                    resident=self.resident, path=self.path, chunk=self.chunk)
 
     @property
     def launch_count(self):
