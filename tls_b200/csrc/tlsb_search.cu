@@ -365,14 +365,27 @@ __device__ __forceinline__ bool better(double c, int u, int i, const Best &b)
 template <bool kUnit, bool kUniformW>
 __device__ __forceinline__ void tap_block(const WidthRec &wr, const double *__restrict__ tq,
                                           const double *__restrict__ w, const double *__restrict__ wd,
-                                          int i0, double (&A)[kBlock], double (&B)[kBlock])
+                                          int c0, double (&A)[kBlock], double (&B)[kBlock])
 {
     const int L = wr.L, X = kUnit ? 1 : wr.X;
+    const int i0 = c0 * X;
 #pragma unroll
     for (int r = 0; r < kBlock; ++r) { A[r] = 0.0; B[r] = 0.0; }
     const int nb = X < L ? X : L;
-    for (int b = 0; b < nb; ++b) {
-        const int groups = ((L - b + X - 1) / X + 2 * kBlock - 2) / kBlock;  // ceil((taps + kBlock-1) / kBlock)
+    // Strided widths: neighbouring lanes sit kBlock*X doubles apart, which maps onto only
+    // 16/gcd(X,16) of the 16 eight-byte banks.  Lanes therefore walk the X residue classes in
+    // ROTATED order, starting at b0 = (block / (16/g)) mod g (a function of the candidate, not of
+    // the lane, so results do not depend on queue order): the lanes that share a bank through
+    // the stride get distinct residues and the half-warp is conflict free again.
+    int b0 = 0;
+    if (!kUnit && nb == X) {
+        const int g = min(X & -X, 16);
+        b0 = ((c0 / kBlock) / (16 / g)) & (g - 1);
+    }
+    const int groups = ((L + X - 1) / X + 2 * kBlock - 2) / kBlock;  // ceil((taps + kBlock-1) / kBlock), widest class
+    for (int t = 0; t < nb; ++t) {
+        int b = b0 + t;
+        if (b >= nb) b -= nb;
         const double *__restrict__ qp = tq + wr.q + b;
         const double *__restrict__ wp = w + i0 + b;
         const double *__restrict__ wdp = wd + i0 + b;
@@ -630,9 +643,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                     const int i0 = e.x * wr.X;
                     double A[kBlock], B[kBlock];
                     if (wr.X == 1)
-                        tap_block<true, kUniformW>(wr, a.tq, w, wd, i0, A, B);
+                        tap_block<true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
                     else
-                        tap_block<false, kUniformW>(wr, a.tq, w, wd, i0, A, B);
+                        tap_block<false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
 #pragma unroll
                     for (int rr = 0; rr < kBlock; ++rr) {
                         if (mask & (1 << rr)) {
@@ -990,9 +1003,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                         const int i0 = e.x * wr.X;
                         double A[kBlock], B[kBlock];
                         if (wr.X == 1)
-                            tap_block<true, kUniformW>(wr, a.tq, wb, wdb, i0, A, B);
+                            tap_block<true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
                         else
-                            tap_block<false, kUniformW>(wr, a.tq, wb, wdb, i0, A, B);
+                            tap_block<false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
 #pragma unroll
                         for (int rr = 0; rr < kBlock; ++rr) {
                             if (mask & (1 << rr)) {
