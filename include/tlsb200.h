@@ -164,6 +164,19 @@ int tlsb_final_t0_fit_lc(const tlsb_lightcurve *lc, int32_t device, const double
 /* Device time [ms] of the most recent T0-fit kernel of this handle (CUDA events). */
 double tlsb_last_t0_fit_ms(const tlsb_handle *h);
 
+/* ---- spectra (stats.py:105-132 + helpers.running_median, helpers.py:93-108) ----
+ * chi2 (ascending-period order, as main.py:190-196 leaves it) -> SR = min(chi2)/chi2,
+ * SDE_raw, power_raw, and the median-detrended, re-normalised `power` with its SDE; all on
+ * the device, batched over `n_curves` rows of `n_periods` values each (HOST buffers in and out).
+ *   median_window   the reference's `kernel` (oversampling_factor * SDE_MEDIAN_KERNEL_SIZE, made
+ *                   odd, stats.py:115-117); detrending applies when n_periods > 2 * window
+ *   SR_out, power_raw_out, power_out   [n_curves][n_periods], any may be NULL
+ *   SDE_raw_out, SDE_out               [n_curves]
+ *   argmax_out      optional [n_curves]: first index of the maximum of `power` (main.py:271) */
+int tlsb_spectra(int32_t device, const double *chi2, int64_t n_periods, int64_t n_curves,
+                 int64_t median_window, double *SR_out, double *power_raw_out, double *power_out,
+                 double *SDE_raw_out, double *SDE_out, int64_t *argmax_out);
+
 const char *tlsb_last_error(void);
 const char *tlsb_version(void);
 int32_t tlsb_device_count(void);

@@ -208,3 +208,37 @@ def final_T0_fit_numpy(signal, depth, t, y, dy, period, T0_fit_margin, trials=No
         if total < lowest:
             lowest, T0 = total, Tx
     return T0, out, trials
+
+
+# ---------------------------------------------------------------- spectra restatement
+def running_median_numpy(data, kernel):
+    """helpers.py:93-108"""
+    idx = np.arange(kernel) + np.arange(len(data) - kernel + 1)[:, None]
+    idx = idx.astype(np.int64)
+    med = np.median(data[idx], axis=1)
+    missing = len(data) - len(med)
+    front = int(missing * 0.5)
+    med = np.append(np.full(front, med[0]), med)
+    return np.append(med, np.full(missing - front, med[-1]))
+
+
+def spectra_numpy(chi2, oversampling_factor, kernel=None):
+    """stats.py:105-132 statement by statement -> (SR, power_raw, power, SDE_raw, SDE)."""
+    SR = np.min(chi2) / chi2
+    SDE_raw = (1 - np.mean(SR)) / np.std(SR)
+    power_raw = SR - np.mean(SR)
+    scale = SDE_raw / np.max(power_raw)
+    power_raw = power_raw * scale
+    if kernel is None:
+        kernel = oversampling_factor * 30  # tls_constants.py:100
+        if kernel % 2 == 0:
+            kernel = kernel + 1
+    if len(power_raw) > 2 * kernel:
+        power = power_raw - running_median_numpy(power_raw, kernel)
+        power = power - np.mean(power)
+        SDE = np.max(power / np.std(power))
+        scale = SDE / np.max(power)
+        power = power * scale
+    else:
+        power, SDE = power_raw, SDE_raw
+    return SR, power_raw, power, SDE_raw, SDE

@@ -42,3 +42,18 @@ def test_numpy_t0_fit_matches_reference(name):
     assert T0 == g["T0"]
     np.testing.assert_array_equal(trials, g["trials"])
     np.testing.assert_allclose(resid, g["residuals"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["cfg1_50ppm", "small_hetero", "k2_epic201367065", "k2_epic206154641_box"])
+def test_numpy_spectra_matches_reference(name):
+    """oracle.spectra_numpy against the reference's own SR / power_raw / power / SDE (power_*.npz)."""
+    import os
+    from conftest import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, "power_%s.npz" % name))
+    kw = eval(str(z["kwargs"]), {"__builtins__": {}})
+    SR, pr, pw, sde_raw, sde = oracle.spectra_numpy(z["a_chi2"], kw.get("oversampling_factor", 3))
+    np.testing.assert_allclose(SR, z["a_SR"], rtol=1e-13)
+    np.testing.assert_allclose(pr, z["a_power_raw"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(pw, z["a_power"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose([sde_raw, sde], [float(z["s_SDE_raw"]), float(z["s_SDE"])], rtol=1e-12)

@@ -8,8 +8,8 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "tlsb_search.cu")]
-HEADERS = [os.path.join(os.path.dirname(HERE), "include", "tlsb200.h")]
+SRC = [os.path.join(HERE, "csrc", "tlsb_search.cu"), os.path.join(HERE, "csrc", "tlsb_spectra.cu")]
+HEADERS = [os.path.join(os.path.dirname(HERE), "include", "tlsb200.h"), os.path.join(HERE, "csrc", "tlsb_internal.h")]
 LIB = os.path.join(HERE, "libtlsb200.so")
 
 NVCC_FLAGS = [

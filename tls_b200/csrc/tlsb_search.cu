@@ -46,6 +46,7 @@
 #include <vector>
 
 #include "../../include/tlsb200.h"
+#include "tlsb_internal.h"
 
 namespace {
 
@@ -61,6 +62,9 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr double kSignalDepth = 0.5;  // tls_constants.py:71
 constexpr double kPlanEps = 1e-9;     // relative distance to an integer below which the device plan is "uncertain"
 
+}  // namespace
+
+namespace tlsb {  // shared with the other translation units (tlsb_internal.h)
 thread_local std::string g_error;
 
 int fail(int code, const std::string &msg)
@@ -68,6 +72,11 @@ int fail(int code, const std::string &msg)
     g_error = msg;
     return code;
 }
+}  // namespace tlsb
+
+namespace {
+using tlsb::fail;
+using tlsb::g_error;
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \

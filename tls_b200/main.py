@@ -153,7 +153,8 @@ class transitleastsquares(object):
             duration = nan
             in_count = after_count = before_count = nan
         else:
-            SR, power_raw, power, SDE_raw, SDE = stats.spectra(chi2, self.oversampling_factor)
+            SR, power_raw, power, SDE_raw, SDE = stats.spectra(
+                chi2, self.oversampling_factor, device=getattr(self, "_t0_device", None))
             top = np.argmax(power)
             period = test_statistic_periods[top]
             depth = depths[top]

@@ -20,7 +20,7 @@ EXPORTS = (
     "tlsb_last_error", "tlsb_version", "tlsb_device_count", "tlsb_set_plan_mode",
     "tlsb_plan_fallback_count", "tlsb_last_layout",
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
-    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path",
+    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra",
 )
 
 _c_i64 = ctypes.c_int64
@@ -93,6 +93,7 @@ def lib():
     L.tlsb_last_chunk.restype = ctypes.c_int32
     L.tlsb_last_chunk.argtypes = [_c_vp]
     L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
+    L.tlsb_spectra.argtypes = [ctypes.c_int32, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_last_t0_fit_ms.restype = ctypes.c_double
     L.tlsb_last_t0_fit_ms.argtypes = [_c_vp]
     _LIB = L
@@ -160,6 +161,24 @@ def search_periods(t, y, dy, periods, templates, params, devices=None, return_t0
                                _ptr(chi2), _ptr(row), _ptr(depth), _ptr(t0))
     _check(rc, "tlsb_search_periods")
     return (chi2, row, depth, t0) if return_t0_index else (chi2, row, depth)
+
+
+def spectra(chi2, median_window, device=None):
+    """``tlsb_spectra``: chi2 ``[P]`` or ``[curves, P]`` -> ``(SR, power_raw, power, SDE_raw, SDE, argmax)``
+    (stats.py:105-132 on the device).  Scalars come back as arrays of length ``curves`` for 2-D input."""
+    chi2 = _f64(chi2)
+    single = chi2.ndim == 1
+    rows = np.atleast_2d(chi2)
+    C, P = rows.shape
+    SR, pr, pw = np.empty_like(rows), np.empty_like(rows), np.empty_like(rows)
+    sde_raw, sde = np.empty(C), np.empty(C)
+    amax = np.empty(C, np.int64)
+    rc = lib().tlsb_spectra(-1 if device is None else int(device), _ptr(rows), P, C, int(median_window),
+                            _ptr(SR), _ptr(pr), _ptr(pw), _ptr(sde_raw), _ptr(sde), _ptr(amax))
+    _check(rc, "tlsb_spectra")
+    if single:
+        return SR[0], pr[0], pw[0], float(sde_raw[0]), float(sde[0]), int(amax[0])
+    return SR, pr, pw, sde_raw, sde, amax
 
 
 def final_t0_fit(t, y, dy, model_in, period, trials, device=None):

@@ -93,23 +93,23 @@ def period_uncertainty(periods, power):
         return float("inf")
 
 
-def spectra(chi2, oversampling_factor):
-    """chi2[P] -> (SR, power_raw, power, SDE_raw, SDE)  (stats.py:105-132)."""
-    SR = np.min(chi2) / chi2
-    SDE_raw = (1 - np.mean(SR)) / np.std(SR)
-    power_raw = SR - np.mean(SR)
-    power_raw = power_raw * (SDE_raw / np.max(power_raw))
-
+def median_window(oversampling_factor):
+    """The reference's running-median kernel (stats.py:115-117)."""
     kernel = oversampling_factor * C.SDE_MEDIAN_KERNEL_SIZE
     if kernel % 2 == 0:
         kernel = kernel + 1
-    if len(power_raw) > 2 * kernel:
-        power = power_raw - running_median(power_raw, kernel)
-        power = power - np.mean(power)
-        SDE = np.max(power / np.std(power))
-        power = power * (SDE / np.max(power))
-    else:
-        power, SDE = power_raw, SDE_raw
+    return int(kernel)
+
+
+def spectra(chi2, oversampling_factor, device=None):
+    """chi2[P] -> (SR, power_raw, power, SDE_raw, SDE)  (stats.py:105-132).
+
+    Runs on the B200 through ``tlsb_spectra`` (``include/tlsb200.h``): SR, its mean and
+    population std, the running median of width ``median_window`` (helpers.py:93-108) and the
+    re-normalisation are three small kernels; no CPU fallback."""
+    from . import native
+
+    SR, power_raw, power, SDE_raw, SDE, _ = native.spectra(chi2, median_window(oversampling_factor), device=device)
     return SR, power_raw, power, SDE_raw, SDE
 
 
