@@ -177,6 +177,30 @@ int tlsb_spectra(int32_t device, const double *chi2, int64_t n_periods, int64_t 
                  int64_t median_window, double *SR_out, double *power_raw_out, double *power_out,
                  double *SDE_raw_out, double *SDE_out, int64_t *argmax_out);
 
+/* ---- batches (BASELINE.json config "1,000 independent K2-like light curves") ----
+ * Several light curves of the SAME length stay resident on one handle; they share the handle's
+ * period grid and template bank (the reference builds both from the time span and the sample
+ * count only, main.py:53-88, so curves of one campaign share them).
+ *   t   f64[n] when shared_t != 0 (one time axis for all curves), else f64[n_curves][n]
+ *   y, dy   f64[n_curves][n]
+ * tlsb_select_lightcurve picks the curve that tlsb_search_async and tlsb_final_t0_fit work on
+ * (0 after tlsb_set_lightcurves / tlsb_set_lightcurve). */
+int tlsb_set_lightcurves(tlsb_handle *h, const double *t, const double *y, const double *dy, int64_t n,
+                         int64_t n_curves, int32_t shared_t);
+int tlsb_select_lightcurve(tlsb_handle *h, int64_t index);
+int64_t tlsb_lightcurve_count(const tlsb_handle *h);
+/* The whole batch in one call: for every resident curve the plan + search kernels (the period
+ * loop of main.py:140-185), then stats.spectra for all curves at once (stats.py:105-132), all
+ * queued on `cuda_stream` with ONE synchronisation at the end.  Outputs (HOST buffers):
+ *   chi2_out, row_out, depth_out, t0_index_out   [n_curves][n_periods], order of periods[], any may be NULL
+ *   power_out               [n_curves][n_periods] in ASCENDING-period order (results.power), may be NULL
+ *   SDE_raw_out, SDE_out    [n_curves]
+ *   best_period_index_out   optional [n_curves]: index into periods[] of the highest `power` peak
+ *                           (main.py:271-272: period = periods[argmax(power)]) */
+int tlsb_search_batch(tlsb_handle *h, void *cuda_stream, int64_t median_window, double *chi2_out,
+                      int64_t *row_out, double *depth_out, int64_t *t0_index_out, double *power_out,
+                      double *SDE_raw_out, double *SDE_out, int64_t *best_period_index_out);
+
 const char *tlsb_last_error(void);
 const char *tlsb_version(void);
 int32_t tlsb_device_count(void);

@@ -76,3 +76,39 @@ def test_sharded_search_over_gloo_equals_single_process(world, tmp_path):
         np.testing.assert_array_equal(z["row"], g["row"])
         np.testing.assert_allclose(z["chi2"], g["chi2"], rtol=1e-9)
         np.testing.assert_allclose(z["depth"], g["depth"], rtol=1e-9)
+
+
+def _batch_worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+
+    from tls_b200 import batch
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_rows = 7
+    rows = np.full((n_rows, 3), np.nan)
+    mine = batch.shard_curves(n_rows, rank, world)
+    rows[mine] = np.arange(n_rows * 3, dtype=float).reshape(n_rows, 3)[mine]  # what this rank computed
+    full = batch._all_gather_rows(rows, mine, n_rows, dist, None)
+    np.save(os.path.join(out_dir, "batch_rank%d.npy" % rank), full)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_batch_summaries_all_gather_over_gloo(world, tmp_path):
+    """Curves are dealt to the ranks round-robin; ONE all-gather returns every curve's row to every rank."""
+    import torch.multiprocessing as mp
+
+    from tls_b200 import batch
+
+    seen = np.concatenate([batch.shard_curves(7, r, world) for r in range(world)])
+    assert sorted(seen) == list(range(7))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_batch_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    want = np.arange(21, dtype=float).reshape(7, 3)
+    for rank in range(world):
+        np.testing.assert_array_equal(np.load(os.path.join(str(tmp_path), "batch_rank%d.npy" % rank)), want)

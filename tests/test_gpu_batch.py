@@ -1,0 +1,123 @@
+"""Batches and the iterative multi-planet search on the GPU (tls_b200/batch.py over
+``tlsb_search_batch`` / ``tlsb_select_lightcurve`` / ``tlsb_final_t0_fit``).
+
+A batch must give, curve by curve, exactly what ``.power()`` gives for that curve alone (same
+kernels, same inputs), and ``.power()`` itself is held to the reference by test_gpu_power.py."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_search_parity, load_search_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _curves(n_curves, hetero=False):
+    from tls_b200 import workloads
+
+    t, _, _, kw = workloads.lightcurve("small")
+    rng = np.random.RandomState(42)
+    ys, dys = [], []
+    for c in range(n_curves):
+        period = rng.uniform(2.0, 9.0)
+        sigma = 10 ** rng.uniform(np.log10(50e-6), np.log10(500e-6))
+        flux = workloads.inject(t, period, t[0] + rng.uniform(0, period), rp=0.03)
+        ys.append(flux + rng.normal(0, sigma, len(t)))
+        dys.append(sigma * rng.uniform(0.5, 2.0, len(t)) if hetero else np.full(len(t), np.std(ys[-1])))
+    return t, np.array(ys), np.array(dys), kw
+
+
+@pytest.mark.parametrize("hetero", [False, True])
+def test_batch_equals_curve_by_curve_power(hetero):
+    from tls_b200 import batch_power, transitleastsquares
+
+    t, ys, dys, kw = _curves(5, hetero)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = batch_power(t, ys, dys if hetero else None, return_power=True, **kw)
+        assert res.n_curves == 5
+        for c in range(5):
+            one = transitleastsquares(t, ys[c], dys[c] if hetero else None, verbose=False).power(
+                show_progress_bar=False, verbose=False, **kw)
+            np.testing.assert_array_equal(res.periods, one.periods)
+            np.testing.assert_allclose(res.power[c], one.power, rtol=1e-12, atol=1e-12)
+            for key in ("SDE", "SDE_raw", "period", "T0", "depth", "duration", "chi2_min", "chi2red_min", "rp_rs"):
+                np.testing.assert_allclose(res[key][c], one[key], rtol=1e-12, err_msg="%s of curve %d" % (key, c))
+            assert int(res.transit_count[c]) == one.transit_count
+
+
+def test_batch_with_per_curve_time_axes_and_records():
+    """tlsb_search_batch with one time axis per curve (same span): records equal the one-shot call's."""
+    from tls_b200 import native, stats
+
+    g = load_search_golden("small")
+    rng = np.random.RandomState(3)
+    n = len(g["t"])
+    ts, ys, dys = [], [], []
+    for c in range(3):
+        jitter = np.zeros(n)
+        jitter[1:-1] = rng.uniform(-1e-3, 1e-3, n - 2)  # inner samples move, the span does not
+        ts.append(g["t"] + jitter)
+        ys.append(g["y"] + rng.normal(0, 2e-5, n))
+        dys.append(g["dy"])
+    s = native.Searcher()
+    s.set_templates(g["templates"], g["params"])
+    s.set_periods(g["periods"])
+    s.set_lightcurves(np.array(ts), np.array(ys), np.array(dys))
+    assert s.n_curves == 3
+    out = s.search_batch(stats.median_window(3))
+    for c in range(3):
+        chi2, row, depth, t0 = native.search_periods(ts[c], ys[c], dys[c], g["periods"], g["templates"], g["params"],
+                                                     return_t0_index=True)
+        np.testing.assert_array_equal(out["chi2"][c], chi2)
+        np.testing.assert_array_equal(out["row"][c], row)
+        np.testing.assert_array_equal(out["depth"][c], depth)
+        np.testing.assert_array_equal(out["t0_index"][c], t0)
+        order = np.argsort(g["periods"])
+        SR, pr, pw, sde_raw, sde, amax = native.spectra(chi2[order], stats.median_window(3))
+        np.testing.assert_array_equal(out["power"][c], pw)
+        np.testing.assert_array_equal([out["SDE"][c], out["SDE_raw"][c]], [sde, sde_raw])
+        assert np.isfinite(sde) and chi2.min() < len(g["y"])
+        assert out["best_index"][c] == order[amax]
+    # the device plan is reused inside a batch but a fresh search afterwards plans again
+    s.select(1)
+    s.search_async()
+    chi2b = s.results()[0]
+    np.testing.assert_array_equal(chi2b, out["chi2"][1])
+    s.set_plan_mode(2)  # every period flagged: the batch redoes itself with the exact host plan
+    out2 = s.search_batch(stats.median_window(3), want_power=False)
+    np.testing.assert_array_equal(out2["chi2"], out["chi2"])
+    assert s.plan_fallbacks >= 1
+    s.close()
+
+
+def test_batch_first_curve_of_golden_matches_reference():
+    from tls_b200 import native, stats
+
+    g = load_search_golden("cfg1_hetero")
+    s = native.Searcher()
+    s.set_templates(g["templates"], g["params"])
+    s.set_periods(g["periods"])
+    s.set_lightcurves(g["t"], np.array([g["y"], g["y"][::-1].copy()]), np.array([g["dy"], g["dy"]]))
+    out = s.search_batch(stats.median_window(3), want_power=False)
+    assert_search_parity((out["chi2"][0], out["row"][0], out["depth"][0]), g, rtol=1e-5, label="batch curve 0")
+    s.close()
+
+
+def test_multi_planet_known_answers_of_the_reference():
+    """transitleastsquares/tests/test_multi_planet.py:33-49: mask the first planet of EPIC 201367065,
+    search again; the reference's own numbers to 3 decimals."""
+    from tls_b200 import search_planets
+
+    z = np.load(os.path.join(GOLDEN, "power_k2_epic201367065.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        found = search_planets(z["in_t"], z["in_y"], n_planets=2)
+    assert len(found) == 2
+    np.testing.assert_allclose(found[0].period, float(z["s_period"]), rtol=1e-5)
+    np.testing.assert_allclose(found[0].SDE, float(z["s_SDE"]), rtol=1e-5)
+    np.testing.assert_almost_equal(found[1].duration, 0.15061016994013998, decimal=3)
+    np.testing.assert_almost_equal(found[1].SDE, 34.9911304598618, decimal=3)
+    np.testing.assert_almost_equal(found[1].rp_rs, 0.025852178872027086, decimal=3)

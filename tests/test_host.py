@@ -140,8 +140,19 @@ def test_package_exports():
 
 # ---- full .power() host logic against the reference's own results -----------------------------
 class _OracleBacked(transitleastsquares):
-    """The GPU call replaced by the CPU oracle so that the HOST orchestration can be pinned
-    without a device.  Test infrastructure only; the product class has no such path."""
+    """The three GPU calls (period search, spectra, final_T0_fit) replaced by the CPU oracle so that
+    the HOST orchestration can be pinned without a device.  Test infrastructure only; the product
+    class has no such path."""
+
+    def _spectra(self, chi2):
+        from oracle import oracle
+
+        return oracle.spectra_numpy(chi2, self.oversampling_factor)
+
+    def _final_T0_fit(self, signal, depth, period):
+        from oracle import oracle
+
+        return oracle.final_T0_fit_numpy(signal, depth, self.t, self.y, self.dy, period, self.T0_fit_margin)[0]
 
     def _search(self, inputs, devices):
         from oracle import oracle

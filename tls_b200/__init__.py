@@ -8,8 +8,9 @@ from .helpers import cleaned_array, resample, transit_mask
 from .grid import duration_grid, period_grid
 from .stats import FAP, fold
 from .results import transitleastsquaresresults
+from .batch import batch_power, search_planets  # extras: batches and the iterative multi-planet recipe
 
 __all__ = [
     "transitleastsquares", "cleaned_array", "resample", "transit_mask", "duration_grid",
-    "period_grid", "FAP", "fold", "transitleastsquaresresults",
+    "period_grid", "FAP", "fold", "transitleastsquaresresults", "batch_power", "search_planets",
 ]

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <string>
 
 namespace tlsb {
@@ -31,6 +32,11 @@ struct DeviceBuffer {
     }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
+
+// stats.spectra on device buffers (tlsb_spectra.cu): chi2 [n_curves][P] in ascending-period order ->
+// SR, power_raw, power [n_curves][P]; scal [n_curves][4] = SDE_raw, SDE, min chi2, peak; first arg-max.
+int spectra_device(const double *chi2, int64_t P, int64_t n_curves, int64_t win, double *SR, double *power_raw,
+                   double *power, double *scal, long long *argmax, cudaStream_t s);
 
 }  // namespace tlsb
 

@@ -1200,9 +1200,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_t0fit_kernel(con
 
 // d = 1 - y, w = 1/dy^2 (core.py:127 computes 1/dy**2 the same way), once per light curve.
 __global__ void tlsb_prepare_kernel(const double *__restrict__ y, const double *__restrict__ dy,
-                                    double *__restrict__ dval, double *__restrict__ wval, int n)
+                                    double *__restrict__ dval, double *__restrict__ wval, size_t n)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) {
         dval[k] = 1.0 - y[k];
         const double e = dy[k];
@@ -1264,8 +1264,17 @@ struct tlsb_handle {
     double span = 0.0;
     bool uniform_w = false;  // every dy identical (dy=None -> std(y) everywhere, validate.py:39-40)
     double w0 = 0.0;         // 1/dy^2 in that case
-    DevBuf t, y, dy, dval, wval;
+    DevBuf t, y, dy, dval, wval;   // n_curves light curves back to back (t: one copy when shared)
     bool have_lc = false;
+    int n_curves = 1;              // tlsb_set_lightcurves
+    bool shared_t = true;          // every curve uses the same time stamps
+    int cur = 0;                   // the curve tlsb_search_async / tlsb_final_t0_fit work on
+    std::vector<double> c_span, c_w0;
+    std::vector<char> c_uniform;
+    bool dev_plan_valid = false;   // ulo/uhi/order on the device match (periods, templates, span)
+    double dev_plan_span = 0.0;
+    DevBuf asc_order, brec, bchi, bSR, bpr, bpw, bscal, bamax;  // batch pipeline
+    std::vector<int> h_asc_order;
     // templates
     tlsb_params prm{};
     int nU = 0, M = 0, pad = 0;
@@ -1321,6 +1330,7 @@ int refresh_records(tlsb_handle *h)
     CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->recs_stale = false;
     h->host_plan_valid = false;
+    h->dev_plan_valid = false;
     return 0;
 }
 
@@ -1359,6 +1369,7 @@ int host_plan(tlsb_handle *h)
     if ((rc = upload(h->order, order.data(), sizeof(int) * P))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));  // the vectors above go out of scope
     h->host_plan_valid = true;
+    h->dev_plan_valid = false;
     return 0;
 }
 
@@ -1480,6 +1491,8 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     if (exact_plan) {
         if (!h->host_plan_valid && (rc = host_plan(h))) return rc;
         CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));
+    } else if (h->dev_plan_valid && h->dev_plan_span == h->span && h->plan_mode == 0) {
+        CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));  // same periods, bank and span as the previous launch
     } else {
         PlanArgs pa{};
         pa.periods = h->periods.as<double>(); pa.P = P; pa.rec = h->d_rec.as<WidthRec>(); pa.nU = h->nU;
@@ -1493,6 +1506,8 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
         CUDA_TRY(cudaGetLastError());
         h->host_plan_valid = false;
         h->launches += 1;
+        h->dev_plan_valid = false;  // becomes valid only once its status word has been seen clean (batch)
+        h->dev_plan_span = h->span;
     }
 
     const Layout lay = choose_layout(h);
@@ -1500,7 +1515,9 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     if (h->path_mode == 1 && !lay.resident) return fail(TLSB_ERR_ARG, "tlsb_set_path: the folded curve does not fit shared memory (resident path)");
     if (h->path_mode == 2 && !lay.tiled) return fail(TLSB_ERR_ARG, "tlsb_set_path: the widest window does not fit a shared-memory chunk (tiled path)");
     SearchArgs a{};
-    a.t = h->t.as<double>(); a.dval = h->dval.as<double>(); a.wval = h->wval.as<double>(); a.N = h->N;
+    const size_t cur_off = (size_t)h->cur * (size_t)h->N;
+    a.t = h->t.as<double>() + (h->shared_t ? 0 : cur_off);
+    a.dval = h->dval.as<double>() + cur_off; a.wval = h->wval.as<double>() + cur_off; a.N = h->N;
     a.tq = h->tq.as<double>(); a.rec = h->d_rec.as<WidthRec>(); a.nU = h->nU; a.M = h->M; a.pad = h->pad;
     a.periods = h->periods.as<double>(); a.ulo = h->ulo.as<int>(); a.uhi = h->uhi.as<int>();
     a.order = h->order.as<int>(); a.P = P; a.depth_min = h->prm.transit_depth_min; a.w0 = h->w0;
@@ -1593,7 +1610,7 @@ int tlsb_destroy(tlsb_handle *h)
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo,
                       &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch, &h->t0_trials, &h->t0_model,
-                      &h->t0_resid})
+                      &h->t0_resid, &h->asc_order, &h->brec, &h->bchi, &h->bSR, &h->bpr, &h->bpw, &h->bscal, &h->bamax})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1601,38 +1618,87 @@ int tlsb_destroy(tlsb_handle *h)
     return 0;
 }
 
+static int set_curves(tlsb_handle *h, const double *t, const double *y, const double *dy, int64_t n64,
+                      int64_t n_curves, bool shared_t)
+{
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = (int)n64;
+    const size_t total = (size_t)n * (size_t)n_curves, bytes = sizeof(double) * total;
+    int rc;
+    if ((rc = upload(h->t, t, shared_t ? sizeof(double) * (size_t)n : bytes))) return rc;
+    if ((rc = upload(h->y, y, bytes))) return rc;
+    if ((rc = upload(h->dy, dy, bytes))) return rc;
+    if (h->dval.ensure(bytes) || h->wval.ensure(bytes)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    tlsb_prepare_kernel<<<(unsigned)((total + 255) / 256), 256>>>(h->y.as<double>(), h->dy.as<double>(),
+                                                                 h->dval.as<double>(), h->wval.as<double>(), total);
+    CUDA_TRY(cudaGetLastError());
+    h->c_span.assign((size_t)n_curves, 0.0);
+    h->c_w0.assign((size_t)n_curves, 0.0);
+    h->c_uniform.assign((size_t)n_curves, 0);
+    for (int64_t c = 0; c < n_curves; ++c) {
+        const double *tc = shared_t ? t : t + (size_t)c * n, *dc = dy + (size_t)c * n;
+        if (!shared_t || c == 0) {
+            double tmin = tc[0], tmax = tc[0];  // core.py:148: max(t) - min(t)
+            for (int k = 1; k < n; ++k) {
+                tmin = std::min(tmin, tc[k]);
+                tmax = std::max(tmax, tc[k]);
+            }
+            h->c_span[c] = tmax - tmin;
+        } else
+            h->c_span[c] = h->c_span[0];
+        bool uniform = true;
+        for (int k = 1; k < n && uniform; ++k) uniform = dc[k] == dc[0];
+        h->c_uniform[c] = uniform ? 1 : 0;
+        h->c_w0[c] = 1.0 / (dc[0] * dc[0]);
+    }
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->n_curves = (int)n_curves;
+    h->shared_t = shared_t;
+    h->cur = 0;
+    h->uniform_w = h->c_uniform[0] != 0;
+    h->w0 = h->c_w0[0];
+    h->N = n;
+    h->span = h->c_span[0];
+    h->have_lc = true;
+    h->recs_stale = true;
+    h->host_plan_valid = false;
+    h->dev_plan_valid = false;
+    return 0;
+}
+
 int tlsb_set_lightcurve(tlsb_handle *h, const tlsb_lightcurve *lc)
 {
     if (!h || !lc || !lc->t || !lc->y || !lc->dy) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurve: NULL argument");
     if (lc->n < 3 || lc->n > (int64_t)1 << 28) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurve: need 3 <= n <= 2^28 samples");
-    CUDA_TRY(cudaSetDevice(h->device));
-    const int n = (int)lc->n;
-    const size_t bytes = sizeof(double) * (size_t)n;
-    int rc;
-    if ((rc = upload(h->t, lc->t, bytes))) return rc;
-    if ((rc = upload(h->y, lc->y, bytes))) return rc;
-    if ((rc = upload(h->dy, lc->dy, bytes))) return rc;
-    if (h->dval.ensure(bytes) || h->wval.ensure(bytes)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
-    tlsb_prepare_kernel<<<(n + 255) / 256, 256>>>(h->y.as<double>(), h->dy.as<double>(),
-                                                  h->dval.as<double>(), h->wval.as<double>(), n);
-    CUDA_TRY(cudaGetLastError());
-    double tmin = lc->t[0], tmax = lc->t[0];  // core.py:148: max(t) - min(t)
-    bool uniform = true;
-    for (int k = 1; k < n; ++k) {
-        tmin = std::min(tmin, lc->t[k]);
-        tmax = std::max(tmax, lc->t[k]);
-        uniform = uniform && lc->dy[k] == lc->dy[0];
+    return set_curves(h, lc->t, lc->y, lc->dy, lc->n, 1, true);
+}
+
+int tlsb_set_lightcurves(tlsb_handle *h, const double *t, const double *y, const double *dy, int64_t n,
+                         int64_t n_curves, int32_t shared_t)
+{
+    if (!h || !t || !y || !dy) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurves: NULL argument");
+    if (n < 3 || n > (int64_t)1 << 28) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurves: need 3 <= n <= 2^28 samples");
+    if (n_curves < 1 || n_curves > 65535 || n * n_curves > (int64_t)1 << 31)
+        return fail(TLSB_ERR_ARG, "tlsb_set_lightcurves: need 1 <= n_curves <= 65535 and n * n_curves <= 2^31");
+    return set_curves(h, t, y, dy, n, n_curves, shared_t != 0);
+}
+
+int tlsb_select_lightcurve(tlsb_handle *h, int64_t index)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_select_lightcurve: NULL handle");
+    if (!h->have_lc) return fail(TLSB_ERR_STATE, "tlsb_select_lightcurve: no light curves set");
+    if (index < 0 || index >= h->n_curves) return fail(TLSB_ERR_ARG, "tlsb_select_lightcurve: index out of range");
+    h->cur = (int)index;
+    h->uniform_w = h->c_uniform[(size_t)index] != 0;
+    h->w0 = h->c_w0[(size_t)index];
+    if (h->span != h->c_span[(size_t)index]) {
+        h->span = h->c_span[(size_t)index];
+        h->host_plan_valid = false;
     }
-    CUDA_TRY(cudaStreamSynchronize(nullptr));
-    h->uniform_w = uniform;
-    h->w0 = 1.0 / (lc->dy[0] * lc->dy[0]);
-    h->N = n;
-    h->span = tmax - tmin;
-    h->have_lc = true;
-    h->recs_stale = true;
-    h->host_plan_valid = false;
     return 0;
 }
+
+int64_t tlsb_lightcurve_count(const tlsb_handle *h) { return h && h->have_lc ? h->n_curves : 0; }
 
 int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_params *prm)
 {
@@ -1699,6 +1765,7 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     h->have_tp = true;
     h->recs_stale = true;
     h->host_plan_valid = false;
+    h->dev_plan_valid = false;
     return 0;
 }
 
@@ -1711,9 +1778,16 @@ int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods)
     h->h_periods.assign(periods, periods + n_periods);
     int rc;
     if ((rc = upload(h->periods, periods, sizeof(double) * (size_t)n_periods))) return rc;
+    // main.py:190-196: results are consumed in ascending-period order
+    h->h_asc_order.resize((size_t)n_periods);
+    std::iota(h->h_asc_order.begin(), h->h_asc_order.end(), 0);
+    std::stable_sort(h->h_asc_order.begin(), h->h_asc_order.end(),
+                     [&](int x, int y) { return periods[x] < periods[y]; });
+    if ((rc = upload(h->asc_order, h->h_asc_order.data(), sizeof(int) * (size_t)n_periods))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->have_periods = true;
     h->host_plan_valid = false;
+    h->dev_plan_valid = false;
     return 0;
 }
 
@@ -1934,7 +2008,8 @@ int run_t0_fit(tlsb_handle *h, cudaStream_t s, const double *model_in, int64_t d
     if (h->t0_resid.ensure(sizeof(double) * (size_t)n_trials)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
 
     T0Args a{};
-    a.t = h->t.as<double>(); a.y = h->y.as<double>(); a.N = N;
+    const size_t cur_off = (size_t)h->cur * (size_t)N;
+    a.t = h->t.as<double>() + (h->shared_t ? 0 : cur_off); a.y = h->y.as<double>() + cur_off; a.N = N;
     a.trials = h->t0_trials.as<double>(); a.n_trials = (int)n_trials;
     a.model = h->t0_model.as<double>(); a.dur = (int)dur; a.shift = (int)(dur / 2) + 1;  // stats.py:186
     a.period = period;
@@ -2025,3 +2100,89 @@ int tlsb_final_t0_fit_lc(const tlsb_lightcurve *lc, int32_t device, const double
 }
 
 }  // extern "C"
+
+// ---- batch pipeline: every resident light curve through plan/search, then spectra, one sync ----
+namespace {
+
+__global__ void tlsb_gather_rows_kernel(const double *__restrict__ records, size_t record_stride,
+                                        const int *__restrict__ order, double *__restrict__ out, int P)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t c = blockIdx.y;
+    if (k < P) out[c * P + k] = records[c * record_stride + order[k]];  // chi2 plane, ascending period
+}
+
+}  // namespace
+
+extern "C" int tlsb_search_batch(tlsb_handle *h, void *cuda_stream, int64_t median_window, double *chi2_out,
+                                 int64_t *row_out, double *depth_out, int64_t *t0_index_out, double *power_out,
+                                 double *SDE_raw_out, double *SDE_out, int64_t *best_period_index_out)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_search_batch: NULL handle");
+    if (!h->have_lc || !h->have_tp || !h->have_periods)
+        return fail(TLSB_ERR_STATE, "tlsb_search_batch: light curves, templates and periods must be set first");
+    if (!SDE_raw_out || !SDE_out) return fail(TLSB_ERR_ARG, "tlsb_search_batch: NULL argument");
+    if (median_window < 1 || median_window > 24000) return fail(TLSB_ERR_ARG, "tlsb_search_batch: median window must be in 1..24000");
+    if (h->P < 1) return fail(TLSB_ERR_ARG, "tlsb_search_batch: no periods");
+    if (h->M > h->N) return fail(TLSB_ERR_ARG, "widest template is longer than the light curve");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const size_t B = (size_t)h->n_curves, P = (size_t)h->P, stride = 3 * P + 1;
+    if (h->brec.ensure(B * stride * 8) || h->bchi.ensure(B * P * 8) || h->bSR.ensure(B * P * 8) ||
+        h->bpr.ensure(B * P * 8) || h->bpw.ensure(B * P * 8) || h->bscal.ensure(B * 32) || h->bamax.ensure(B * 8))
+        return fail(TLSB_ERR_ALLOC, "device allocation failed (batch buffers)");
+    double *rec = h->brec.as<double>();
+    std::vector<long long> status(B);
+    int64_t launches = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool exact = attempt == 1 || h->plan_mode == 1;
+        int rc;
+        for (size_t c = 0; c < B; ++c) {
+            if ((rc = tlsb_select_lightcurve(h, (int64_t)c))) return rc;
+            if ((rc = enqueue_search(h, s, rec + c * stride, exact))) return rc;
+            launches += h->launches;
+            // the device plan of this launch serves the following curves while span/periods/bank stay the same
+            if (!exact && h->plan_mode == 0) h->dev_plan_valid = true;
+        }
+        // one strided copy of the B status words
+        CUDA_TRY(cudaMemcpy2DAsync(status.data(), 8, rec + 3 * P, stride * 8, 8, B, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        bool unsure = false;
+        for (size_t c = 0; c < B; ++c) unsure = unsure || status[c] != 0;
+        if (!unsure || exact) break;
+        h->fallbacks += 1;  // some T14 limit was too close to an integer for the device pow(): exact host plan
+        h->dev_plan_valid = false;
+    }
+    h->dev_plan_valid = false;  // do not carry the shortcut outside the batch
+    dim3 grid((unsigned)((P + 255) / 256), (unsigned)B);
+    tlsb_gather_rows_kernel<<<grid, 256, 0, s>>>(rec, stride, h->asc_order.as<int>(), h->bchi.as<double>(), (int)P);
+    CUDA_TRY(cudaGetLastError());
+    int rc = tlsb::spectra_device(h->bchi.as<double>(), (int64_t)P, (int64_t)B, median_window, h->bSR.as<double>(),
+                                  h->bpr.as<double>(), h->bpw.as<double>(), h->bscal.as<double>(),
+                                  h->bamax.as<long long>(), s);
+    if (rc) return rc;
+    launches += 1 + (P > 2 * (size_t)median_window ? 3 : 2);
+    h->launches = launches;
+    std::vector<double> scal(B * 4);
+    std::vector<long long> amax(B), packed;
+    CUDA_TRY(cudaMemcpyAsync(scal.data(), h->bscal.p, B * 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(amax.data(), h->bamax.p, B * 8, cudaMemcpyDeviceToHost, s));
+    if (chi2_out) CUDA_TRY(cudaMemcpy2DAsync(chi2_out, P * 8, rec, stride * 8, P * 8, B, cudaMemcpyDeviceToHost, s));
+    if (depth_out) CUDA_TRY(cudaMemcpy2DAsync(depth_out, P * 8, rec + P, stride * 8, P * 8, B, cudaMemcpyDeviceToHost, s));
+    if (row_out || t0_index_out) {
+        packed.resize(B * P);
+        CUDA_TRY(cudaMemcpy2DAsync(packed.data(), P * 8, rec + 2 * P, stride * 8, P * 8, B, cudaMemcpyDeviceToHost, s));
+    }
+    if (power_out) CUDA_TRY(cudaMemcpyAsync(power_out, h->bpw.p, B * P * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (size_t k = 0; k < packed.size(); ++k) {
+        if (row_out) row_out[k] = (int64_t)(uint32_t)(packed[k] & 0xffffffffLL);
+        if (t0_index_out) t0_index_out[k] = (int64_t)(int32_t)(packed[k] >> 32);
+    }
+    for (size_t c = 0; c < B; ++c) {
+        SDE_raw_out[c] = scal[4 * c + 0];
+        SDE_out[c] = scal[4 * c + 1];
+        if (best_period_index_out) best_period_index_out[c] = h->h_asc_order[(size_t)amax[c]];
+    }
+    return 0;
+}

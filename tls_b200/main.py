@@ -89,6 +89,18 @@ class transitleastsquares(object):
             devices=devices,
         )
 
+    def _spectra(self, chi2):
+        """stats.py:105-132 on the GPU (``tlsb_spectra``)."""
+        return stats.spectra(chi2, self.oversampling_factor, device=getattr(self, "_t0_device", None))
+
+    def _final_T0_fit(self, signal, depth, period):
+        """stats.py:135-204 on the GPU (``tlsb_final_t0_fit_lc``)."""
+        return stats.final_T0_fit(
+            signal=signal, depth=depth, t=self.t, y=self.y, dy=self.dy, period=period,
+            T0_fit_margin=self.T0_fit_margin, show_progress_bar=self.show_progress_bar,
+            verbose=self.verbose, device=getattr(self, "_t0_device", None),
+        )
+
     def power(self, **kwargs):
         """Compute the periodogram for a set of user-defined parameters (main.py:51)."""
         inputs = self.prepare(**kwargs)
@@ -153,16 +165,11 @@ class transitleastsquares(object):
             duration = nan
             in_count = after_count = before_count = nan
         else:
-            SR, power_raw, power, SDE_raw, SDE = stats.spectra(
-                chi2, self.oversampling_factor, device=getattr(self, "_t0_device", None))
+            SR, power_raw, power, SDE_raw, SDE = self._spectra(chi2)
             top = np.argmax(power)
             period = test_statistic_periods[top]
             depth = depths[top]
-            T0 = stats.final_T0_fit(
-                signal=lc_arr[best_row], depth=depth, t=t, y=y, dy=dy, period=period,
-                T0_fit_margin=self.T0_fit_margin, show_progress_bar=self.show_progress_bar,
-                verbose=self.verbose, device=getattr(self, "_t0_device", None),
-            )
+            T0 = self._final_T0_fit(lc_arr[best_row], depth, period)
             transit_times = stats.all_transit_times(T0, t, period)
             transit_duration = stats.calculate_transit_duration_in_days(t, period, transit_times, duration)
 

@@ -21,6 +21,7 @@ EXPORTS = (
     "tlsb_plan_fallback_count", "tlsb_last_layout",
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
     "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra",
+    "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
 )
 
 _c_i64 = ctypes.c_int64
@@ -94,6 +95,11 @@ def lib():
     L.tlsb_last_chunk.argtypes = [_c_vp]
     L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
     L.tlsb_spectra.argtypes = [ctypes.c_int32, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
+    L.tlsb_set_lightcurves.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_int32]
+    L.tlsb_select_lightcurve.argtypes = [_c_vp, _c_i64]
+    L.tlsb_lightcurve_count.restype = _c_i64
+    L.tlsb_lightcurve_count.argtypes = [_c_vp]
+    L.tlsb_search_batch.argtypes = [_c_vp, _c_vp, _c_i64] + [_c_vp] * 8
     L.tlsb_last_t0_fit_ms.restype = ctypes.c_double
     L.tlsb_last_t0_fit_ms.argtypes = [_c_vp]
     _LIB = L
@@ -227,6 +233,43 @@ class Searcher(object):
         t, y, dy = _f64(t), _f64(y), _f64(dy)
         lc = LightCurve(_ptr(t), _ptr(y), _ptr(dy), len(t))
         _check(lib().tlsb_set_lightcurve(self._h, ctypes.byref(lc)), "tlsb_set_lightcurve")
+
+    def set_templates(self, templates, params):
+        pk = _Packed(np.zeros(1), np.zeros(1), np.ones(1), templates, params)
+        _check(lib().tlsb_set_templates(self._h, ctypes.byref(pk.tp), ctypes.byref(pk.prm)), "tlsb_set_templates")
+
+    def set_lightcurves(self, t, ys, dys):
+        """Several curves of the same length: ``t`` is ``[n]`` (shared) or ``[curves, n]``."""
+        ys, dys, t = _f64(ys), _f64(dys), _f64(t)
+        if ys.ndim != 2 or dys.shape != ys.shape:
+            raise ValueError("ys and dys must be [curves, n] arrays of the same shape")
+        shared = t.ndim == 1
+        if (t.shape[-1] != ys.shape[1]) or (not shared and t.shape != ys.shape):
+            raise ValueError("t must be [n] or [curves, n]")
+        _check(lib().tlsb_set_lightcurves(self._h, _ptr(t), _ptr(ys), _ptr(dys), ys.shape[1], ys.shape[0],
+                                          1 if shared else 0), "tlsb_set_lightcurves")
+
+    def select(self, index):
+        _check(lib().tlsb_select_lightcurve(self._h, int(index)), "tlsb_select_lightcurve")
+
+    @property
+    def n_curves(self):
+        return int(lib().tlsb_lightcurve_count(self._h))
+
+    def search_batch(self, median_window, stream=None, want_power=True, want_records=True):
+        """``tlsb_search_batch`` -> dict(chi2, row, depth, t0_index, power, SDE_raw, SDE, best_index)."""
+        B, P = self.n_curves, self.n_periods
+        out = dict(SDE_raw=np.empty(B), SDE=np.empty(B), best_index=np.empty(B, np.int64))
+        if want_records:
+            out.update(chi2=np.empty((B, P)), row=np.empty((B, P), np.int64), depth=np.empty((B, P)),
+                       t0_index=np.empty((B, P), np.int64))
+        if want_power:
+            out["power"] = np.empty((B, P))
+        opt = lambda k: _ptr(out[k]) if k in out else None  # noqa: E731
+        _check(lib().tlsb_search_batch(self._h, _c_vp(stream or 0), int(median_window), opt("chi2"), opt("row"),
+                                       opt("depth"), opt("t0_index"), opt("power"), _ptr(out["SDE_raw"]),
+                                       _ptr(out["SDE"]), _ptr(out["best_index"])), "tlsb_search_batch")
+        return out
 
     def set_periods(self, periods):
         periods = _f64(periods)
