@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg1", help="cfg1 (default, the config the metric is quoted on), "
                     "tutorial01, cfg1_500ppm, cfg3, cfg2")
-    ap.add_argument("--max-periods", type=int, default=0, help="cap the periods per rank (0 = whole grid)")
+    ap.add_argument("--max-periods", type=int, default=0, help="cap the periods per rank to an evenly spread subset of the grid (0 = whole grid)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -216,8 +216,8 @@ def run_reference(args):
     oversampling = 3 * args.gpus
     inp = build_inputs(args.workload, oversampling)
     periods = inp.periods
-    if args.max_periods:
-        periods = periods[: args.max_periods * args.gpus]
+    if args.max_periods and args.max_periods * args.gpus < len(periods):
+        periods = periods[np.linspace(0, len(periods) - 1, args.max_periods * args.gpus).astype(int)]
     from oracle import oracle
 
     cores = os.cpu_count() or 1
@@ -274,8 +274,8 @@ def run_b200(args):
     oversampling = 3 * n_gpus
     inp = build_inputs(args.workload, oversampling)
     all_periods = inp.periods
-    if args.max_periods:
-        all_periods = all_periods[: args.max_periods * n_gpus]
+    if args.max_periods and args.max_periods * n_gpus < len(all_periods):  # evenly spread over the grid
+        all_periods = all_periods[np.linspace(0, len(all_periods) - 1, args.max_periods * n_gpus).astype(int)]
     job = ShardedSearch(inp.t, inp.y, inp.dy, inp.templates, inp.params, all_periods,
                         rank=rank, world=world, device=local, dist=dist)
     P_rank, P_total = job.n_local, len(all_periods)

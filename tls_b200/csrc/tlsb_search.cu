@@ -311,43 +311,143 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
                                                  const double *__restrict__ src1, const double *__restrict__ src2,
                                                  double *dst1, double *dst2, int *scan_scratch)
 {
+    constexpr int kU = 4;  // independent load chains per thread (the streaming layouts sort in L2/HBM)
     const int tid = threadIdx.x;
     for (int b = tid; b <= NB; b += kT) H[b] = 0;
     __syncthreads();
     double *ph_unsorted = dst1;  // [N], free until the ranking step writes the sorted values
-    for (int k = tid; k < N; k += kT) {
-        const double tk = __ldcs(t + k);  // streamed: keep L1 for the templates
-        const double ph = fold_phase(kEpoch ? tk - T0 : tk, r);
-        ph_unsorted[k] = ph;
-        atomicAdd(&H[bucket_of(ph, NB) + 1], 1);
+    for (int k0 = tid; k0 < N; k0 += kT * kU) {
+        double tv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) tv[u] = (k0 + u * kT < N) ? __ldcs(t + k0 + u * kT) : 0.0;  // streamed
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int k = k0 + u * kT;
+            if (k < N) {
+                const double ph = fold_phase(kEpoch ? tv[u] - T0 : tv[u], r);
+                ph_unsorted[k] = ph;
+                atomicAdd(&H[bucket_of(ph, NB) + 1], 1);
+            }
+        }
     }
     __syncthreads();
     // inclusive scan of H[0..NB] (H[0] = 0): H[b] = number of keys in buckets < b
     block_inclusive_scan<kT, int>(H, NB + 1, scan_scratch);
-    for (int k = tid; k < N; k += kT) {
-        const double ph = ph_unsorted[k];
-        const int pos = atomicAdd(&H[bucket_of(ph, NB)], 1);  // any order inside the bucket
-        skey[pos] = ph;
-        sid[pos] = (idx_t)k;
+    for (int k0 = tid; k0 < N; k0 += kT * kU) {
+        double ph[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) ph[u] = (k0 + u * kT < N) ? ph_unsorted[k0 + u * kT] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int k = k0 + u * kT;
+            if (k < N) {
+                const int pos = atomicAdd(&H[bucket_of(ph[u], NB)], 1);  // any order inside the bucket
+                skey[pos] = ph[u];
+                sid[pos] = (idx_t)k;
+            }
+        }
     }
     __syncthreads();  // now H[b] = end of bucket b; the unsorted phases are dead
-    for (int q = tid; q < N; q += kT) {
-        const double key = skey[q];
-        const int id = (int)sid[q];
-        const double v1 = __ldcs(src1 + id);  // issued early: the gather overlaps the ranking loop
-        double v2 = 0.0;
-        if (kTwo) v2 = __ldcs(src2 + id);
-        const int b = bucket_of(key, NB);
-        const int lo = b ? H[b - 1] : 0, hi = H[b];
-        int rank = lo;
-        for (int s = lo; s < hi; ++s) {
-            const double ks = skey[s];
-            const int is = (int)sid[s];
-            rank += (ks < key) || (ks == key && is < id);  // (phase, index): the stable order
+    for (int q0 = tid; q0 < N; q0 += kT * kU) {
+        double key[kU], v1[kU], v2[kU];
+        int id[kU], lo[kU], hi[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int q = q0 + u * kT;
+            key[u] = q < N ? skey[q] : 0.0;
+            id[u] = q < N ? (int)sid[q] : 0;
         }
-        dst1[rank] = v1;
-        if (kTwo) dst2[rank] = v2;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {  // gathers issued early: they overlap the ranking loops
+            v1[u] = __ldcs(src1 + id[u]);
+            v2[u] = kTwo ? __ldcs(src2 + id[u]) : 0.0;
+            const int bk = bucket_of(key[u], NB);
+            lo[u] = bk ? H[bk - 1] : 0;
+            hi[u] = H[bk];
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (q0 + u * kT < N) {
+                int rank = lo[u];
+                for (int s = lo[u]; s < hi[u]; ++s) {
+                    const double ks = skey[s];
+                    const int is = (int)sid[s];
+                    rank += (ks < key[u]) || (ks == key[u] && is < id[u]);  // (phase, index): the stable order
+                }
+                dst1[rank] = v1[u];
+                if (kTwo) dst2[rank] = v2[u];
+            }
+        }
     }
+}
+
+// After the sort: cs1[0..N) holds the sorted d = 1 - y (cs1 = cs + 1).  Wrap the first M samples to
+// the end (core.py:126-132), then ONE pass turns d into its inclusive cumulative sum in place
+// (helpers.py:70-73), writes wd = w * d and returns this thread's share of T = sum_{k<N} w d^2.
+template <int kT, bool kUniformW>
+__device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, double *wd, double w0, int N, int NM,
+                                                   int NMP, double *warp_tot /* [kT/32 + 1] shared */)
+{
+    constexpr int kW = kT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int k = N + tid; k < NMP; k += kT) {
+        if (k < NM) {
+            cs1[k] = cs1[k - N];
+            if (!kUniformW) w[k] = w[k - N];
+        } else {  // slack read (never used) by the unguarded tap groups
+            wd[k] = 0.0;
+            if (!kUniformW) w[k] = 0.0;
+        }
+    }
+    __syncthreads();
+    double tpart = 0.0, carry = 0.0;
+    for (int base = 0; base < NM; base += kT * kScanItems) {
+        const int first = base + tid * kScanItems;
+        double v[kScanItems];
+        double run = 0.0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const int e = first + k;
+            double d = 0.0;
+            if (e < NM) {
+                d = cs1[e];
+                const double x = (kUniformW ? w0 : w[e]) * d;
+                wd[e] = x;
+                if (e < N) tpart = fma(x, d, tpart);
+            }
+            run += d;
+            v[k] = run;
+        }
+        double incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(kFull, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const double wv = (lane < kW) ? warp_tot[lane] : 0.0;
+            double wi = wv;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double o = __shfl_up_sync(kFull, wi, off);
+                if (lane >= off) wi += o;
+            }
+            if (lane < kW) warp_tot[lane] = wi - wv;
+            if (lane == kW - 1) warp_tot[kW] = wi;
+        }
+        __syncthreads();
+        double excl = __shfl_up_sync(kFull, incl, 1);
+        if (lane == 0) excl = 0.0;
+        const double offset = carry + warp_tot[wid] + excl;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+            if (first + k < NM) cs1[first + k] = v[k] + offset;
+        carry += warp_tot[kW];
+        __syncthreads();
+    }
+    return tpart;
 }
 
 struct Best {
@@ -490,8 +590,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         H = reinterpret_cast<int *>(queue + a.qcap);
         tail = smem_raw + (size_t)a.qcap * 8 + (((size_t)(NB + 1) * 4 + 15) & ~(size_t)15);
     }
-    double *skey = cs;
-    double *dsorted = wd;
+    double *skey = wd;  // the sort keys borrow the wd area; the sorted d go straight to cs[1..N]
     WidthRec *rec = reinterpret_cast<WidthRec *>(tail);                       // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
     int *red_i = reinterpret_cast<int *>(red_d + 2 * kW + 2);                 // [2*kW]
@@ -530,34 +629,17 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         }
 
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
-        fold_sort_gather<kT, idx_t, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, dsorted, w,
+        fold_sort_gather<kT, idx_t, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w,
                                                        reinterpret_cast<int *>(red_d));
-        __syncthreads();  // keys are dead: cs may overwrite them
-        // wrap the first M samples to the end (core.py:126-132)
-        for (int k = tid; k < NM; k += kT) cs[k + 1] = dsorted[k < N ? k : k - N];
         if (tid == 0) cs[0] = 0.0;
-        __syncthreads();  // the sorted d are dead: wd may overwrite them
-        double tpart = 0.0;
-        for (int k = tid; k < NMP; k += kT) {
-            if (k < NM) {
-                const double d = cs[k + 1];
-                const double wv = kUniformW ? a.w0 : w[k < N ? k : k - N];
-                const double x = wv * d;
-                if (!kUniformW && k >= N) w[k] = wv;
-                wd[k] = x;
-                if (k < N) tpart = fma(x, d, tpart);  // T = sum w d^2 over the unpatched curve
-            } else {  // slack read (never used) by the unguarded tap groups
-                wd[k] = 0.0;
-                if (!kUniformW) w[k] = 0.0;
-            }
-        }
+        __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
+        double tpart = wrap_weight_scan<kT, kUniformW>(cs + 1, w, wd, a.w0, N, NM, NMP, red_d);
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
         if (lane == 0) red_d[kW + 1 + wid] = tpart;
         __syncthreads();
-        block_inclusive_scan<kT, double>(cs + 1, NM, red_d);
         double T = 0.0;
-        for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];  // fixed order: deterministic
+        for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];  // T = sum w d^2 over the unpatched curve; fixed order
 
         // ---- B. gate + survivor compaction + tap loop ----------------------------------------
         // B1: warp `wid` gates tiles wid, wid+kW, ... of the sweep (wide widths first) from two
@@ -803,8 +885,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     double *w = cs + cs_elems;
     double *wd = kUniformW ? w : w + nmp_even;
     unsigned *sid = reinterpret_cast<unsigned *>(wd + nmp_even);
-    double *skey = cs;
-    double *dsorted = wd;
+    double *skey = wd;  // the sort keys borrow the wd area; the sorted d go straight to cs[1..N]
 
     // ---- shared: queue | chunk of cs | [chunk of w] | chunk of wd | records, tables, scratch ----
     int2 *queue = reinterpret_cast<int2 *>(smem_raw);
@@ -854,31 +935,15 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         }
 
         // ---- A. fold + stable sort + gather, wrap, w*d, T, cumulative sums (global scratch) ----
-        fold_sort_gather<kT, unsigned, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, dsorted, w,
+        fold_sort_gather<kT, unsigned, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w,
                                                           reinterpret_cast<int *>(red_d));
-        __syncthreads();
-        for (int k = tid; k < NM; k += kT) cs[k + 1] = dsorted[k < N ? k : k - N];
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();
-        double tpart = 0.0;
-        for (int k = tid; k < (int)nmp_even; k += kT) {
-            if (k < NM) {
-                const double d = cs[k + 1];
-                const double wv = kUniformW ? a.w0 : w[k < N ? k : k - N];
-                const double x = wv * d;
-                if (!kUniformW && k >= N) w[k] = wv;
-                wd[k] = x;
-                if (k < N) tpart = fma(x, d, tpart);
-            } else {
-                wd[k] = 0.0;
-                if (!kUniformW) w[k] = 0.0;
-            }
-        }
+        double tpart = wrap_weight_scan<kT, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d);
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
         if (lane == 0) red_d[kW + 1 + wid] = tpart;
         __syncthreads();
-        block_inclusive_scan<kT, double>(cs + 1, NM, red_d);
         double T = 0.0;
         for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];
         fence_proxy_async();  // this thread's global writes -> visible to the bulk copies below
