@@ -305,13 +305,13 @@ __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] sh
 // rank inside the bucket by (phase, index) = numpy's stable mergesort order; src1 (and src2) are
 // gathered to their sorted slots in dst1 (dst2).  dst1 doubles as the store of the unsorted
 // phases until the ranking step; skey/sid/H are scratch.  Ends WITHOUT a barrier.
-template <int kT, typename idx_t, bool kTwo, bool kEpoch>
+template <int kT, typename idx_t, bool kTwo, bool kEpoch, int kU = 4>
 __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, double T0, double r, int N, int NB,
                                                  int *H, double *skey, idx_t *sid,
                                                  const double *__restrict__ src1, const double *__restrict__ src2,
                                                  double *dst1, double *dst2, int *scan_scratch)
 {
-    constexpr int kU = 4;  // independent load chains per thread (the streaming layouts sort in L2/HBM)
+    // kU independent load chains per thread (the streaming layouts sort in L2/HBM)
     const int tid = threadIdx.x;
     for (int b = tid; b <= NB; b += kT) H[b] = 0;
     __syncthreads();
@@ -365,17 +365,33 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
             lo[u] = bk ? H[bk - 1] : 0;
             hi[u] = H[bk];
         }
+        // the kU ranking loops run in lockstep so that their loads are in flight together
+        int rank[kU], longest = 0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            rank[u] = lo[u];
+            if (q0 + u * kT >= N) hi[u] = lo[u];
+            longest = max(longest, hi[u] - lo[u]);
+        }
+        for (int s = 0; s < longest; ++s) {
+            double ks[kU];
+            int is[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int at = lo[u] + s < hi[u] ? lo[u] + s : lo[u];  // a harmless re-read once this chain is done
+                ks[u] = skey[at];
+                is[u] = (int)sid[at];
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (lo[u] + s < hi[u])
+                    rank[u] += (ks[u] < key[u]) || (ks[u] == key[u] && is[u] < id[u]);  // (phase, index): the stable order
+        }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             if (q0 + u * kT < N) {
-                int rank = lo[u];
-                for (int s = lo[u]; s < hi[u]; ++s) {
-                    const double ks = skey[s];
-                    const int is = (int)sid[s];
-                    rank += (ks < key[u]) || (ks == key[u] && is < id[u]);  // (phase, index): the stable order
-                }
-                dst1[rank] = v1[u];
-                if (kTwo) dst2[rank] = v2[u];
+                dst1[rank[u]] = v1[u];
+                if (kTwo) dst2[rank[u]] = v2[u];
             }
         }
     }
@@ -405,13 +421,20 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
         const int first = base + tid * kScanItems;
         double v[kScanItems];
         double run = 0.0;
+        double dv[kScanItems], wv[kScanItems];
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {  // every load in flight before the arithmetic
+            const int e = first + k < NM ? first + k : NM - 1;
+            dv[k] = cs1[e];
+            wv[k] = kUniformW ? w0 : w[e];
+        }
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
             const int e = first + k;
             double d = 0.0;
             if (e < NM) {
-                d = cs1[e];
-                const double x = (kUniformW ? w0 : w[e]) * d;
+                d = dv[k];
+                const double x = wv[k] * d;
                 wd[e] = x;
                 if (e < N) tpart = fma(x, d, tpart);
             }
@@ -935,8 +958,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         }
 
         // ---- A. fold + stable sort + gather, wrap, w*d, T, cumulative sums (global scratch) ----
-        fold_sort_gather<kT, unsigned, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w,
-                                                          reinterpret_cast<int *>(red_d));
+        fold_sort_gather<kT, unsigned, !kUniformW, false, 8>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1,
+                                                             w, reinterpret_cast<int *>(red_d));
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();
         double tpart = wrap_weight_scan<kT, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d);
