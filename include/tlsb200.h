@@ -133,6 +133,12 @@ int32_t tlsb_last_path_resident(const tlsb_handle *h);
 int32_t tlsb_last_path(const tlsb_handle *h);
 /* Chunk capacity [doubles per staged array] of the most recent tiled search (0 otherwise). */
 int32_t tlsb_last_chunk(const tlsb_handle *h);
+/* Tiled path: the fold is sorted on chip, one phase segment at a time (segment_capacity keys per
+ * segment, n_segments segments; both 0 when the sort runs in global scratch).  A period whose
+ * phases cluster so strongly that a segment overflows is sorted in global scratch instead;
+ * global_sort_periods counts those of the most recent search (synchronises).  Any pointer may be NULL. */
+int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_segments,
+                        int64_t *global_sort_periods);
 /* Force a layout (tests, experiments): path 0 = automatic (default), 1..3 as above; a search
  * fails with TLSB_ERR_ARG if the forced layout cannot hold the inputs.  chunk_doubles > 0 caps
  * the tiled path's chunk capacity so that small inputs exercise several chunks. */

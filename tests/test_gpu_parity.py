@@ -135,7 +135,7 @@ def _search_with_path(native, g, path, chunk=0):
     s.set_path(path, chunk)
     s.search_async()
     out = s.results()
-    info = s.layout
+    info = dict(s.layout, **s.sort_info)
     s.close()
     return out, info
 
@@ -152,6 +152,10 @@ def test_tiled_path_matches_reference_golden(name):
     n = len(g["y"])
     out, info = _search_with_path(native, g, "tiled", chunk=max(256, n // 3))
     assert info["path"] == "tiled"
+    # the fold is sorted on chip in several phase segments; only clustered phases may fall back
+    assert info["n_segments"] >= 2 and info["segment_capacity"] < n
+    if name in ("small", "cfg1_50ppm", "cfg3", "k2_epic201367065"):
+        assert info["global_sort_periods"] <= len(g["periods"]) // 10
     assert_search_parity(out[:3], g, rtol=RTOL, label=name + " tiled")
     auto, _ = _search_with_path(native, g, "auto")
     np.testing.assert_array_equal(out[1], auto[1])
@@ -191,3 +195,40 @@ def test_forced_resident_path_refuses_what_does_not_fit():
     with pytest.raises(RuntimeError, match="resident"):
         s.search_async()
     s.close()
+
+
+def test_on_chip_sort_equals_global_sort(monkeypatch):
+    """Tiled path with the segmented on-chip sort vs the same path sorting in global scratch."""
+    native = _native()
+    g = load_search_golden("cfg3")
+    g = dict(g, periods=g["periods"][::7])
+    on, info_on = _search_with_path(native, g, "tiled")
+    assert info_on["n_segments"] >= 2
+    monkeypatch.setenv("TLSB_ONCHIP_SORT", "0")
+    off, info_off = _search_with_path(native, g, "tiled")
+    assert info_off["n_segments"] == 0
+    np.testing.assert_array_equal(on[1], off[1])
+    np.testing.assert_array_equal(on[3], off[3])
+    np.testing.assert_allclose(on[0], off[0], rtol=1e-12)
+
+
+def test_clustered_phases_fall_back_to_the_global_sort():
+    """Three samples per day, trial period one day: every sample sits on one of three phases, a
+    segment of the on-chip sort overflows and that period is sorted in global scratch instead -
+    with the same results as the resident path."""
+    native = _native()
+    g = load_search_golden("small")
+    n = len(g["y"])
+    rng = np.random.RandomState(8)
+    k = np.arange(n)
+    t = (k % 3) / 3.0 + k // 3 + rng.uniform(0, 1e-7, n)
+    y = 1.0 + rng.normal(0, 2e-4, n)
+    g = dict(g, t=t, y=y, dy=np.full(n, np.std(y)), periods=np.array([1.0, 2.0, 3.3, 0.5, 7.7]))
+    tiled, info = _search_with_path(native, g, "tiled", chunk=max(256, n // 3))
+    assert info["n_segments"] >= 2
+    assert 1 <= info["global_sort_periods"] <= 3, info
+    auto, info2 = _search_with_path(native, g, "auto")
+    assert info2["path"] == "resident"
+    np.testing.assert_array_equal(tiled[1], auto[1])
+    np.testing.assert_array_equal(tiled[3], auto[3])
+    np.testing.assert_allclose(tiled[0], auto[0], rtol=1e-12)

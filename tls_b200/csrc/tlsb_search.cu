@@ -56,6 +56,7 @@ constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per
 constexpr int kTile = 32 * kBlock * kSub;  // candidates one warp gates at a time
 constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
+constexpr int kMaxSegments = 64;     // phase segments of the on-chip sort of the tiled path
 constexpr int kPlanThreads = 1024;
 constexpr int kPlanBins = 1024;
 constexpr unsigned kFull = 0xffffffffu;
@@ -148,6 +149,8 @@ struct SearchArgs {
     size_t scratch_per_cta;
     int NB;               // number of phase buckets
     int chunk;            // tiled path: doubles per staged array (cs / w / wd) in shared memory
+    int seg_cap;          // tiled path, on-chip sort: elements per phase segment (0: sort in global scratch)
+    int n_seg;            // number of phase segments (<= kMaxSegments)
 };
 
 // tls_constants.py:20-25,78 and grid.py:9-32 (T14); same operation order on host and device
@@ -400,24 +403,29 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
 // After the sort: cs1[0..N) holds the sorted d = 1 - y (cs1 = cs + 1).  Wrap the first M samples to
 // the end (core.py:126-132), then ONE pass turns d into its inclusive cumulative sum in place
 // (helpers.py:70-73), writes wd = w * d and returns this thread's share of T = sum_{k<N} w d^2.
+// With begin > 0 the pass resumes at position `begin` with the running sum `carry` (the samples
+// there already hold their d; nothing is wrapped).
 template <int kT, bool kUniformW>
 __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, double *wd, double w0, int N, int NM,
-                                                   int NMP, double *warp_tot /* [kT/32 + 1] shared */)
+                                                   int NMP, double *warp_tot /* [kT/32 + 1] shared */,
+                                                   int begin = 0, double carry = 0.0)
 {
     constexpr int kW = kT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int k = N + tid; k < NMP; k += kT) {
         if (k < NM) {
-            cs1[k] = cs1[k - N];
-            if (!kUniformW) w[k] = w[k - N];
+            if (begin == 0) {
+                cs1[k] = cs1[k - N];
+                if (!kUniformW) w[k] = w[k - N];
+            }
         } else {  // slack read (never used) by the unguarded tap groups
             wd[k] = 0.0;
             if (!kUniformW) w[k] = 0.0;
         }
     }
     __syncthreads();
-    double tpart = 0.0, carry = 0.0;
-    for (int base = 0; base < NM; base += kT * kScanItems) {
+    double tpart = 0.0;
+    for (int base = begin; base < NM; base += kT * kScanItems) {
         const int first = base + tid * kScanItems;
         double v[kScanItems];
         double run = 0.0;
@@ -889,6 +897,165 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // what a candidate block of width record wr may read behind its start offset
 __host__ __device__ inline int window_need(int W, int X) { return W + kPadGroups * kBlock * X + 2; }
 
+// Phase A of the tiled path ON CHIP.  The light curve does not fit shared memory, but a slice of
+// it does: the phase axis is cut into n_seg equal segments; ONE pass over t folds every sample
+// and appends (phase, index) to its segment's list in global scratch (warp-aggregated smem
+// counters); then each segment is sorted entirely in shared memory - histogram over fine phase
+// buckets with the arrival index of every key kept (so the scatter needs no second round of
+// atomics), block scan, rank inside the bucket by (phase, index) - its d = 1-y (and w) gathered
+// to their sorted slots, and the segment emitted in phase order: wd = w*d, T, the cumulative sum
+// continued from the previous segment, and the first M samples stashed behind position N for the
+// wrap (core.py:126-132).  Returns false (nothing consumed) if a segment overflows its capacity -
+// strongly clustered phases - and the caller then sorts in global scratch instead.
+template <int kT, bool kUniformW>
+__device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsigned char *area, int *cnt,
+                                             double *gkey, unsigned *gid, double *cs1, double *w, double *wd,
+                                             int nmp_even, double *red_d, double &tpart_out)
+{
+    constexpr int kU = 4;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = a.N, M = a.M, NM = N + M, S = a.seg_cap, ns = a.n_seg;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    double *val_s = reinterpret_cast<double *>(area);            // [S] sorted d of the segment
+    double *wv_s = val_s + S;                                    // [S] sorted w (unequal weights only)
+    double *skey_s = kUniformW ? wv_s : wv_s + S;                // [S] keys, bucket order
+    int *H = reinterpret_cast<int *>(skey_s + S);                // [S + 2] fine-bucket histogram
+    unsigned *sid_s = reinterpret_cast<unsigned *>(H + S + 2);   // [S] sample ids, bucket order
+    unsigned short *arr = reinterpret_cast<unsigned short *>(sid_s + S);  // [S] arrival index inside the bucket
+    const double dns = (double)ns, dS = (double)S;
+
+    for (int j = tid; j <= ns; j += kT) cnt[j] = 0;
+    __syncthreads();
+    // ---- partition: one pass over t ------------------------------------------------------------
+    for (int kb = wid * 32; kb < N; kb += kT * kU) {  // warp-uniform bounds: every lane reaches the match
+        double tv[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) tv[u] = (kb + u * kT + lane < N) ? __ldcs(a.t + kb + u * kT + lane) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int k = kb + u * kT + lane;
+            int sg = -1;
+            double ph = 0.0;
+            if (k < N) {
+                ph = fold_phase(tv[u], r);
+                sg = min(ns - 1, __double2int_rz(__dmul_rn(ph, dns)));
+            }
+            const unsigned peers = __match_any_sync(kFull, sg);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader && sg >= 0) base = atomicAdd(&cnt[sg], __popc(peers));
+            base = __shfl_sync(kFull, base, leader);
+            if (sg >= 0) {
+                const int slot = base + __popc(peers & lt_mask);
+                if (slot < S) {
+                    gkey[(size_t)sg * S + slot] = ph;
+                    gid[(size_t)sg * S + slot] = (unsigned)k;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int worst = 0;
+    for (int j = 0; j < ns; ++j) worst = max(worst, cnt[j]);
+    if (worst > S) return false;
+
+    auto fine = [&](double ph, int j) {  // monotone in ph inside segment j
+        // explicit roundings: the three passes must map a key to the same bucket (no FMA contraction)
+        const double x = __dsub_rn(__dmul_rn(ph, dns), (double)j);
+        const int fb = __double2int_rz(__dmul_rn(x, dS));
+        return fb < 0 ? 0 : (fb < S - 1 ? fb : S - 1);
+    };
+    double tpart = 0.0, carry = 0.0;
+    int off = 0;
+    for (int j = 0; j < ns; ++j) {
+        const int nj = cnt[j];
+        if (nj == 0) continue;
+        const double *lk = gkey + (size_t)j * S;
+        const unsigned *li = gid + (size_t)j * S;
+        for (int b = tid; b <= S; b += kT) H[b] = 0;
+        __syncthreads();
+        for (int q0 = tid; q0 < nj; q0 += kT * kU) {  // histogram; keep each key's arrival index
+            double ph[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) ph[u] = (q0 + u * kT < nj) ? lk[q0 + u * kT] : 0.0;
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (q0 + u * kT < nj) arr[q0 + u * kT] = (unsigned short)atomicAdd(&H[fine(ph[u], j) + 1], 1);
+        }
+        __syncthreads();
+        block_inclusive_scan<kT, int>(H, S + 1, reinterpret_cast<int *>(red_d));  // H[b] = keys in buckets < b
+        for (int q0 = tid; q0 < nj; q0 += kT * kU) {  // scatter to bucket order, no atomics
+            double ph[kU];
+            unsigned id[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                ph[u] = (q0 + u * kT < nj) ? lk[q0 + u * kT] : 0.0;
+                id[u] = (q0 + u * kT < nj) ? li[q0 + u * kT] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (q0 + u * kT < nj) {
+                    const int pos = H[fine(ph[u], j)] + (int)arr[q0 + u * kT];
+                    skey_s[pos] = ph[u];
+                    sid_s[pos] = id[u];
+                }
+            }
+        }
+        __syncthreads();
+        for (int q0 = tid; q0 < nj; q0 += kT * kU) {  // rank inside the bucket, gather to sorted slots
+            double key[kU], v1[kU], v2[kU];
+            unsigned id[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int q = q0 + u * kT < nj ? q0 + u * kT : 0;
+                key[u] = skey_s[q];
+                id[u] = sid_s[q];
+                v1[u] = __ldcs(a.dval + id[u]);
+                v2[u] = kUniformW ? 0.0 : __ldcs(a.wval + id[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (q0 + u * kT < nj) {
+                    const int fb = fine(key[u], j);
+                    const int lo = H[fb], hi = H[fb + 1];
+                    int rank = lo;
+                    for (int s2 = lo; s2 < hi; ++s2) {
+                        const double ks = skey_s[s2];
+                        const unsigned is = sid_s[s2];
+                        rank += (ks < key[u]) || (ks == key[u] && is < id[u]);  // (phase, index): the stable order
+                    }
+                    val_s[rank] = v1[u];
+                    if (!kUniformW) wv_s[rank] = v2[u];
+                }
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < nj; q += kT) {  // emit: wd, T, w, and the samples the wrap repeats
+            const int pos = off + q;
+            const double d = val_s[q];
+            const double wv = kUniformW ? a.w0 : wv_s[q];
+            const double x = wv * d;
+            wd[pos] = x;
+            tpart = fma(x, d, tpart);
+            if (!kUniformW) w[pos] = wv;
+            if (pos < M) {
+                cs1[N + pos] = d;
+                if (!kUniformW) w[N + pos] = wv;
+            }
+        }
+        __syncthreads();
+        block_inclusive_scan<kT, double>(val_s, nj, red_d);
+        for (int q = tid; q < nj; q += kT) cs1[off + q] = carry + val_s[q];
+        carry += val_s[nj - 1];
+        off += nj;
+        __syncthreads();
+    }
+    // positions N .. NM-1 hold the wrapped d: continue the cumulative sum, weight them, zero the slack
+    wrap_weight_scan<kT, kUniformW>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry);
+    tpart_out = tpart;
+    return true;
+}
+
 template <int kT, bool kUniformW>
 __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_kernel(const __grid_constant__ SearchArgs a)
 {
@@ -924,6 +1091,10 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     int *ch_lo = s_next + 8;       // [nU] first candidate of the chunk, per width
     int *ch_hi = ch_lo + nU;       // [nU] one past the last
     int *ch_tiles = ch_hi + nU;    // [nU]
+    int *seg_cnt = ch_tiles + nU;  // [kMaxSegments + 1] on-chip sort: keys per phase segment
+    // segment lists of the on-chip sort, behind the arrays above
+    double *gkey = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(sid) + (((size_t)N * 4 + 15) & ~(size_t)15));
+    unsigned *gid = reinterpret_cast<unsigned *>(gkey + (size_t)a.n_seg * a.seg_cap);
 
     for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
         reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
@@ -958,11 +1129,19 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         }
 
         // ---- A. fold + stable sort + gather, wrap, w*d, T, cumulative sums (global scratch) ----
-        fold_sort_gather<kT, unsigned, !kUniformW, false, 8>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1,
-                                                             w, reinterpret_cast<int *>(red_d));
+        double tpart = 0.0;
         if (tid == 0) cs[0] = 0.0;
-        __syncthreads();
-        double tpart = wrap_weight_scan<kT, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d);
+        bool on_chip = false;
+        if (a.seg_cap > 0)
+            on_chip = sort_on_chip<kT, kUniformW>(a, r, reinterpret_cast<unsigned char *>(cs_s), seg_cnt, gkey, gid,
+                                                  cs + 1, w, wd, (int)nmp_even, red_d, tpart);
+        if (!on_chip) {  // clustered phases (or no room for segments): sort in the global scratch
+            if (tid == 0 && a.seg_cap > 0) atomicAdd(a.counter + 4, 1);
+            fold_sort_gather<kT, unsigned, !kUniformW, false, 8>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval,
+                                                                 cs + 1, w, reinterpret_cast<int *>(red_d));
+            __syncthreads();
+            tpart = wrap_weight_scan<kT, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d);
+        }
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
         if (lane == 0) red_d[kW + 1 + wid] = tpart;
@@ -1332,6 +1511,8 @@ struct Layout {
     bool resident = false;
     bool tiled = false;    // not resident: phase B from shared-memory chunks staged by bulk async copies
     int chunk = 0;         // doubles per staged array
+    int seg_cap = 0;       // on-chip sort of the tiled path: segment capacity (0 = off) and count
+    int n_seg = 0;
     int threads = 256;     // 256 (two CTAs per SM) or 512 (one)
     int ctas_per_sm = 2;
     int qcap = 4096;
@@ -1520,7 +1701,7 @@ Layout choose_layout(const tlsb_handle *h)
         for (const auto &t : tries) {
             if (forced > 0 && forced != t[0]) continue;
             const size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);
-            const size_t fixed = (size_t)t[2] * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128;
+            const size_t fixed = (size_t)t[2] * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 + (size_t)(kMaxSegments + 2) * 4;
             if (per_cta <= fixed) continue;
             long long C = (long long)(((per_cta - fixed) / (8 * (size_t)narr)) & ~(size_t)1);
             if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~1LL);
@@ -1535,8 +1716,20 @@ Layout choose_layout(const tlsb_handle *h)
             best.qcap = t[2];
             best.chunk = (int)C;
             best.NB = (int)std::min<long long>(N, (long long)narr * C * 2 - 2);
-            best.smem = (size_t)t[2] * 8 + (size_t)narr * (size_t)C * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128;
-            best.scratch_per_cta = (cs + (size_t)(narr - 1) * nmp_even * 8 + (size_t)N * 4 + 255) & ~(size_t)255;
+            best.smem = (size_t)t[2] * 8 + (size_t)narr * (size_t)C * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 +
+                        (size_t)(kMaxSegments + 2) * 4;
+            best.scratch_per_cta = cs + (size_t)(narr - 1) * nmp_even * 8 + align16((size_t)N * 4);
+            // on-chip sort: segments of S keys sorted in the chunk area; 1.5x head room over N / n_seg
+            const char *oc = std::getenv("TLSB_ONCHIP_SORT");  // "0" disables (experiments)
+            const size_t area = (size_t)narr * (size_t)C * 8;
+            const long long S = (long long)(((area - 64) / (h->uniform_w ? 26 : 34)) & ~(size_t)1);
+            const long long ns = S > 0 ? (3LL * N + 2 * S - 1) / (2 * S) : 0;
+            if (!(oc && std::atoi(oc) == 0) && S >= 64 && S <= 65534 && ns >= 1 && ns <= kMaxSegments) {
+                best.seg_cap = (int)S;
+                best.n_seg = (int)ns;
+                best.scratch_per_cta += (size_t)ns * (size_t)S * 12 + 16;
+            }
+            best.scratch_per_cta = (best.scratch_per_cta + 255) & ~(size_t)255;
             return best;
         }
     }
@@ -1616,6 +1809,8 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     a.qcap = lay.qcap;
     a.NB = lay.NB;
     a.chunk = lay.chunk;
+    a.seg_cap = lay.seg_cap;
+    a.n_seg = lay.n_seg;
     const int grid = std::min(P, h->num_sms * lay.ctas_per_sm);
     if (!lay.resident) {
         if (lay.NB < 1) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
@@ -1623,6 +1818,7 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
         if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
         a.scratch = h->scratch.as<unsigned char>();
     }
+    CUDA_TRY(cudaMemsetAsync(h->counter.as<int>() + 4, 0, 4, s));  // periods whose on-chip sort overflowed
     CUDA_TRY(cudaEventRecord(h->ev0, s));
     const bool uni = h->uniform_w;
     if (lay.resident && lay.threads == 256) {
@@ -1944,6 +2140,20 @@ int64_t tlsb_last_launch_count(const tlsb_handle *h) { return h ? h->launches : 
 int32_t tlsb_last_path_resident(const tlsb_handle *h) { return h && h->layout.resident ? 1 : 0; }
 int32_t tlsb_last_path(const tlsb_handle *h) { return !h ? 0 : h->layout.resident ? 1 : h->layout.tiled ? 2 : 3; }
 int32_t tlsb_last_chunk(const tlsb_handle *h) { return h ? h->layout.chunk : 0; }
+
+int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_segments, int64_t *global_sort_periods)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_last_sort_info: NULL handle");
+    if (segment_capacity) *segment_capacity = h->layout.seg_cap;
+    if (n_segments) *n_segments = h->layout.n_seg;
+    if (global_sort_periods) {
+        CUDA_TRY(cudaSetDevice(h->device));
+        int v = 0;
+        CUDA_TRY(cudaMemcpy(&v, h->counter.as<int>() + 4, 4, cudaMemcpyDeviceToHost));  // synchronises
+        *global_sort_periods = v;
+    }
+    return 0;
+}
 int64_t tlsb_plan_fallback_count(const tlsb_handle *h) { return h ? h->fallbacks : 0; }
 
 int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,

@@ -20,7 +20,7 @@ EXPORTS = (
     "tlsb_last_error", "tlsb_version", "tlsb_device_count", "tlsb_set_plan_mode",
     "tlsb_plan_fallback_count", "tlsb_last_layout",
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
-    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra",
+    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info",
     "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
 )
 
@@ -94,6 +94,7 @@ def lib():
     L.tlsb_last_chunk.restype = ctypes.c_int32
     L.tlsb_last_chunk.argtypes = [_c_vp]
     L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
+    L.tlsb_last_sort_info.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_spectra.argtypes = [ctypes.c_int32, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_set_lightcurves.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_int32]
     L.tlsb_select_lightcurve.argtypes = [_c_vp, _c_i64]
@@ -322,6 +323,14 @@ class Searcher(object):
     @property
     def chunk(self):
         return int(lib().tlsb_last_chunk(self._h))
+
+    @property
+    def sort_info(self):
+        """Tiled path: dict(segment_capacity, n_segments, global_sort_periods) of the last search."""
+        cap, ns, fb = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        _check(lib().tlsb_last_sort_info(self._h, ctypes.byref(cap), ctypes.byref(ns), ctypes.byref(fb)),
+               "tlsb_last_sort_info")
+        return dict(segment_capacity=cap.value, n_segments=ns.value, global_sort_periods=fb.value)
 
     @property
     def plan_fallbacks(self):
