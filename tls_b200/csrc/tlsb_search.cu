@@ -56,6 +56,7 @@ constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per
 constexpr int kTile = 32 * kBlock * kSub;  // candidates one warp gates at a time
 constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
+constexpr int kSegPerThread = 16;   // keys of one segment a thread keeps in registers (S <= 16 * threads)
 constexpr int kMaxSegments = 64;     // phase segments of the on-chip sort of the tiled path
 constexpr int kPlanThreads = 1024;
 constexpr int kPlanBins = 1024;
@@ -921,7 +922,6 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     double *skey_s = kUniformW ? wv_s : wv_s + S;                // [S] keys, bucket order
     int *H = reinterpret_cast<int *>(skey_s + S);                // [S + 2] fine-bucket histogram
     unsigned *sid_s = reinterpret_cast<unsigned *>(H + S + 2);   // [S] sample ids, bucket order
-    unsigned short *arr = reinterpret_cast<unsigned short *>(sid_s + S);  // [S] arrival index inside the bucket
     const double dns = (double)ns, dS = (double)S;
 
     for (int j = tid; j <= ns; j += kT) cnt[j] = 0;
@@ -974,58 +974,73 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         const unsigned *li = gid + (size_t)j * S;
         for (int b = tid; b <= S; b += kT) H[b] = 0;
         __syncthreads();
-        for (int q0 = tid; q0 < nj; q0 += kT * kU) {  // histogram; keep each key's arrival index
-            double ph[kU];
+        // histogram: every key of this thread stays in registers together with its bucket and its
+        // arrival index inside the bucket, so the scatter below needs neither a reload nor atomics
+        double ph[kSegPerThread];
+        unsigned id[kSegPerThread], where[kSegPerThread];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) ph[u] = (q0 + u * kT < nj) ? lk[q0 + u * kT] : 0.0;
+        for (int i = 0; i < kSegPerThread; ++i) {
+            const int q = tid + i * kT;
+            ph[i] = q < nj ? lk[q] : 0.0;
+            id[i] = q < nj ? li[q] : 0u;
+        }
 #pragma unroll
-            for (int u = 0; u < kU; ++u)
-                if (q0 + u * kT < nj) arr[q0 + u * kT] = (unsigned short)atomicAdd(&H[fine(ph[u], j) + 1], 1);
+        for (int i = 0; i < kSegPerThread; ++i) {
+            if (tid + i * kT < nj) {
+                const int fb = fine(ph[i], j);
+                where[i] = ((unsigned)atomicAdd(&H[fb + 1], 1) << 16) | (unsigned)fb;
+            }
         }
         __syncthreads();
         block_inclusive_scan<kT, int>(H, S + 1, reinterpret_cast<int *>(red_d));  // H[b] = keys in buckets < b
-        for (int q0 = tid; q0 < nj; q0 += kT * kU) {  // scatter to bucket order, no atomics
-            double ph[kU];
-            unsigned id[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                ph[u] = (q0 + u * kT < nj) ? lk[q0 + u * kT] : 0.0;
-                id[u] = (q0 + u * kT < nj) ? li[q0 + u * kT] : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (q0 + u * kT < nj) {
-                    const int pos = H[fine(ph[u], j)] + (int)arr[q0 + u * kT];
-                    skey_s[pos] = ph[u];
-                    sid_s[pos] = id[u];
-                }
+        for (int i = 0; i < kSegPerThread; ++i) {
+            if (tid + i * kT < nj) {
+                const int pos = H[where[i] & 0xffffu] + (int)(where[i] >> 16);
+                skey_s[pos] = ph[i];
+                sid_s[pos] = id[i];
             }
         }
         __syncthreads();
         for (int q0 = tid; q0 < nj; q0 += kT * kU) {  // rank inside the bucket, gather to sorted slots
             double key[kU], v1[kU], v2[kU];
-            unsigned id[kU];
+            unsigned sidq[kU];
+            int lo[kU], hi[kU], rank[kU], longest = 0;
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 const int q = q0 + u * kT < nj ? q0 + u * kT : 0;
                 key[u] = skey_s[q];
-                id[u] = sid_s[q];
-                v1[u] = __ldcs(a.dval + id[u]);
-                v2[u] = kUniformW ? 0.0 : __ldcs(a.wval + id[u]);
+                sidq[u] = sid_s[q];
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                v1[u] = __ldcs(a.dval + sidq[u]);
+                v2[u] = kUniformW ? 0.0 : __ldcs(a.wval + sidq[u]);
+                const int fb = fine(key[u], j);
+                lo[u] = H[fb];
+                hi[u] = q0 + u * kT < nj ? H[fb + 1] : lo[u];
+                rank[u] = lo[u];
+                longest = max(longest, hi[u] - lo[u]);
+            }
+            for (int s2 = 0; s2 < longest; ++s2) {  // the kU ranking loops in lockstep
+                double ks[kU];
+                unsigned is[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int at = lo[u] + s2 < hi[u] ? lo[u] + s2 : lo[u];
+                    ks[u] = skey_s[at];
+                    is[u] = sid_s[at];
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (lo[u] + s2 < hi[u])
+                        rank[u] += (ks[u] < key[u]) || (ks[u] == key[u] && is[u] < sidq[u]);  // (phase, index)
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 if (q0 + u * kT < nj) {
-                    const int fb = fine(key[u], j);
-                    const int lo = H[fb], hi = H[fb + 1];
-                    int rank = lo;
-                    for (int s2 = lo; s2 < hi; ++s2) {
-                        const double ks = skey_s[s2];
-                        const unsigned is = sid_s[s2];
-                        rank += (ks < key[u]) || (ks == key[u] && is < id[u]);  // (phase, index): the stable order
-                    }
-                    val_s[rank] = v1[u];
-                    if (!kUniformW) wv_s[rank] = v2[u];
+                    val_s[rank[u]] = v1[u];
+                    if (!kUniformW) wv_s[rank[u]] = v2[u];
                 }
             }
         }
@@ -1722,7 +1737,8 @@ Layout choose_layout(const tlsb_handle *h)
             // on-chip sort: segments of S keys sorted in the chunk area; 1.5x head room over N / n_seg
             const char *oc = std::getenv("TLSB_ONCHIP_SORT");  // "0" disables (experiments)
             const size_t area = (size_t)narr * (size_t)C * 8;
-            const long long S = (long long)(((area - 64) / (h->uniform_w ? 26 : 34)) & ~(size_t)1);
+            long long S = (long long)(((area - 64) / (h->uniform_w ? 24 : 32)) & ~(size_t)1);
+            S = std::min<long long>(S, (long long)kSegPerThread * t[0]);
             const long long ns = S > 0 ? (3LL * N + 2 * S - 1) / (2 * S) : 0;
             if (!(oc && std::atoi(oc) == 0) && S >= 64 && S <= 65534 && ns >= 1 && ns <= kMaxSegments) {
                 best.seg_cap = (int)S;
