@@ -133,6 +133,9 @@ int32_t tlsb_last_path_resident(const tlsb_handle *h);
 int32_t tlsb_last_path(const tlsb_handle *h);
 /* Chunk capacity [doubles per staged array] of the most recent tiled search (0 otherwise). */
 int32_t tlsb_last_chunk(const tlsb_handle *h);
+/* T0 candidates one lane carried through the tap loop in the most recent search (7 with equal
+ * weights, 5 with per-point weights or when 7 would cost too many offsets per chunk). */
+int32_t tlsb_last_block(const tlsb_handle *h);
 /* Tiled path: the fold is sorted on chip, one phase segment at a time (segment_capacity keys per
  * segment, n_segments segments; both 0 when the sort runs in global scratch).  A period whose
  * phases cluster so strongly that a segment overflows is sorted in global scratch instead;

@@ -50,10 +50,12 @@
 
 namespace {
 
-constexpr int kBlock = 5;             // R: consecutive T0 candidates one lane carries through the tap loop
-                                      // (odd: neighbouring lanes sit R*stride doubles apart in shared memory)
+// R = kB (template parameter of the kernels): consecutive T0 candidates one lane carries through the
+// tap loop.  Odd (neighbouring lanes sit R*stride doubles apart in shared memory): 7 when all weights
+// are equal (one correlation: the register window fits), 5 with unequal weights (two correlations).
+constexpr int kBlockMax = 7;          // host-side slack (template padding, array slack) is sized for the largest R
 constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per queue reservation
-constexpr int kTile = 32 * kBlock * kSub;  // candidates one warp gates at a time
+__host__ __device__ constexpr int tile_size(int kb) { return 32 * kb * kSub; }  // candidates one warp gates at a time
 constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr int kSegPerThread = 16;   // keys of one segment a thread keeps in registers (S <= 16 * threads)
@@ -503,7 +505,7 @@ __device__ __forceinline__ bool better(double c, int u, int i, const Best &b)
 // pipeline): templates are zero padded in tq and the patched arrays have slack behind them,
 // so ramp-in/ramp-out and the one-group overshoot need no predicates.
 // kUniformW: all weights equal (dy=None) -> only B = sum q_j (w d)_{i+j} is accumulated.
-template <bool kUnit, bool kUniformW>
+template <int kBlock, bool kUnit, bool kUniformW>
 __device__ __forceinline__ void tap_block(const WidthRec &wr, const double *__restrict__ tq,
                                           const double *__restrict__ w, const double *__restrict__ wd,
                                           int c0, double (&A)[kBlock], double (&B)[kBlock])
@@ -582,10 +584,11 @@ __device__ __noinline__ double untouched_tail(const double *w, const double *wd,
     return rest;
 }
 
-template <int kT, bool kResident, bool kUniformW>
+template <int kT, bool kResident, bool kUniformW, int kBlock>
 __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
 {
     constexpr int kW = kT / 32;
+    constexpr int kTile = tile_size(kBlock);
     using idx_t = typename std::conditional<kResident, unsigned short, unsigned int>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -766,9 +769,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                     const int i0 = e.x * wr.X;
                     double A[kBlock], B[kBlock];
                     if (wr.X == 1)
-                        tap_block<true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
+                        tap_block<kBlock, true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
                     else
-                        tap_block<false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
+                        tap_block<kBlock, false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
 #pragma unroll
                     for (int rr = 0; rr < kBlock; ++rr) {
                         if (mask & (1 << rr)) {
@@ -896,7 +899,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // what a candidate block of width record wr may read behind its start offset
-__host__ __device__ inline int window_need(int W, int X) { return W + kPadGroups * kBlock * X + 2; }
+__host__ __device__ inline int window_need(int W, int X, int kb) { return W + kPadGroups * kb * X + 2; }
 
 // Phase A of the tiled path ON CHIP.  The light curve does not fit shared memory, but a slice of
 // it does: the phase axis is cut into n_seg equal segments; ONE pass over t folds every sample
@@ -1071,10 +1074,11 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     return true;
 }
 
-template <int kT, bool kUniformW>
+template <int kT, bool kUniformW, int kBlock>
 __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_kernel(const __grid_constant__ SearchArgs a)
 {
     constexpr int kW = kT / 32;
+    constexpr int kTile = tile_size(kBlock);
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1171,7 +1175,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         best.D = 0.0;
         best.u = -1;
         best.i = -1;
-        const int TP = (C - window_need(rec[uhi - 1].W, rec[uhi - 1].X)) & ~1;
+        const int TP = (C - window_need(rec[uhi - 1].W, rec[uhi - 1].X, kBlock)) & ~1;
         const int i_last = NM - rec[ulo].W;  // the narrowest admissible width has the most offsets
         for (int a0 = 0; a0 <= i_last; a0 += TP) {
             fence_proxy_async();
@@ -1294,9 +1298,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                         const int i0 = e.x * wr.X;
                         double A[kBlock], B[kBlock];
                         if (wr.X == 1)
-                            tap_block<true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
+                            tap_block<kBlock, true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
                         else
-                            tap_block<false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
+                            tap_block<kBlock, false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
 #pragma unroll
                         for (int rr = 0; rr < kBlock; ++rr) {
                             if (mask & (1 << rr)) {
@@ -1526,6 +1530,7 @@ struct Layout {
     bool resident = false;
     bool tiled = false;    // not resident: phase B from shared-memory chunks staged by bulk async copies
     int chunk = 0;         // doubles per staged array
+    int kb = 5;            // candidates per lane (block size R)
     int seg_cap = 0;       // on-chip sort of the tiled path: segment capacity (0 = off) and count
     int n_seg = 0;
     int threads = 256;     // 256 (two CTAs per SM) or 512 (one)
@@ -1566,6 +1571,7 @@ struct tlsb_handle {
     DevBuf tq, d_rec;
     bool have_tp = false;
     bool recs_stale = true;       // ncand/tiles/cum depend on N + M
+    int rec_kb = 0;               // ... and on the block size R the tiles were counted for
     // periods
     int P = 0;
     std::vector<double> h_periods;
@@ -1598,9 +1604,10 @@ int upload(DevBuf &buf, const void *src, size_t bytes, cudaStream_t s = nullptr)
     return 0;
 }
 
-// candidates and scheduler tiles per width (depend on N + M), wide -> narrow prefix
-int refresh_records(tlsb_handle *h)
+// candidates and scheduler tiles per width (depend on N + M and on the block size R), wide -> narrow prefix
+int refresh_records(tlsb_handle *h, int kb, cudaStream_t s)
 {
+    const int kTile = tile_size(kb);
     int cum = 0;
     for (int u = h->nU - 1; u >= 0; --u) {
         WidthRec &wr = h->recs[u];
@@ -1610,9 +1617,10 @@ int refresh_records(tlsb_handle *h)
         cum += wr.tiles;
     }
     int rc;
-    if ((rc = upload(h->d_rec, h->recs.data(), sizeof(WidthRec) * (size_t)h->nU))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if ((rc = upload(h->d_rec, h->recs.data(), sizeof(WidthRec) * (size_t)h->nU, s))) return rc;  // ordered behind earlier launches on s
+    CUDA_TRY(cudaStreamSynchronize(s));
     h->recs_stale = false;
+    h->rec_kb = kb;
     h->host_plan_valid = false;
     h->dev_plan_valid = false;
     return 0;
@@ -1678,6 +1686,10 @@ Layout choose_layout(const tlsb_handle *h)
 {
     Layout best;
     const int N = h->N;
+    // block size R: 7 candidates per lane when all weights are equal, 5 with two correlations (registers)
+    const char *kbe = std::getenv("TLSB_BLOCK");  // experiments: force 5
+    const int kb_pref = (h->uniform_w && !(kbe && std::atoi(kbe) == 5)) ? 7 : 5;
+    best.kb = kb_pref;
     if (N < 65536 && h->path_mode <= 1) {
         const int tries[2][2] = {{256, 2}, {512, 1}};
         const int qcaps[3] = {4096, 3584, 3072};
@@ -1707,8 +1719,11 @@ Layout choose_layout(const tlsb_handle *h)
     const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
     const size_t nmp_even = (NMP + 1) & ~(size_t)1;
     const int narr = h->uniform_w ? 2 : 3;
-    int need_max = 0;
-    for (const WidthRec &wr : h->recs) need_max = std::max(need_max, window_need(wr.W, wr.X));
+    int need_max = 0, need5 = 0;
+    for (const WidthRec &wr : h->recs) {
+        need_max = std::max(need_max, window_need(wr.W, wr.X, kb_pref));
+        need5 = std::max(need5, window_need(wr.W, wr.X, 5));
+    }
     const char *force = std::getenv("TLSB_TILED");  // "0": never, "256"/"512": force that CTA size (experiments)
     const int forced = force ? std::atoi(force) : -1;
     if (forced != 0 && h->path_mode != 3) {
@@ -1720,12 +1735,19 @@ Layout choose_layout(const tlsb_handle *h)
             if (per_cta <= fixed) continue;
             long long C = (long long)(((per_cta - fixed) / (8 * (size_t)narr)) & ~(size_t)1);
             if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~1LL);
-            const long long TP = C - need_max;
+            if (C <= need5) continue;
+            long long TP = C - need_max;
+            int kb = kb_pref;
+            if (kb == 7 && 5 * TP < 4 * (C - need5)) {  // the longer overshoot would cost > 20 % of the offsets per chunk
+                kb = 5;
+                TP = C - need5;
+            }
             if (h->chunk_cap > 0 && TP < 2) continue;
             // two CTAs per SM only when a chunk still starts a few thousand offsets; one big CTA otherwise
             if (h->chunk_cap <= 0 && TP < (t[1] == 2 && forced < 0 ? 2048 : 256)) continue;
             best.resident = false;
             best.tiled = true;
+            best.kb = kb;
             best.threads = t[0];
             best.ctas_per_sm = t[1];
             best.qcap = t[2];
@@ -1777,7 +1799,8 @@ cudaError_t launch_search(K kernel, const SearchArgs &a, int grid, int threads, 
 int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact_plan)
 {
     int rc;
-    if (h->recs_stale && (rc = refresh_records(h))) return rc;
+    const Layout lay = choose_layout(h);
+    if ((h->recs_stale || h->rec_kb != lay.kb) && (rc = refresh_records(h, lay.kb, s))) return rc;
     const int P = h->P;
     double *rec_words = reinterpret_cast<double *>(records_dev);
     long long *status = reinterpret_cast<long long *>(rec_words + 3 * (size_t)P);
@@ -1807,7 +1830,6 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
         h->dev_plan_span = h->span;
     }
 
-    const Layout lay = choose_layout(h);
     h->layout = lay;
     if (h->path_mode == 1 && !lay.resident) return fail(TLSB_ERR_ARG, "tlsb_set_path: the folded curve does not fit shared memory (resident path)");
     if (h->path_mode == 2 && !lay.tiled) return fail(TLSB_ERR_ARG, "tlsb_set_path: the widest window does not fit a shared-memory chunk (tiled path)");
@@ -1837,22 +1859,35 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     CUDA_TRY(cudaMemsetAsync(h->counter.as<int>() + 4, 0, 4, s));  // periods whose on-chip sort overflowed
     CUDA_TRY(cudaEventRecord(h->ev0, s));
     const bool uni = h->uniform_w;
-    if (lay.resident && lay.threads == 256) {
-        if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<256, true, true>, a, grid, 256, lay.smem, s));
-        else CUDA_TRY(launch_search(tlsb_search_kernel<256, true, false>, a, grid, 256, lay.smem, s));
-    } else if (lay.resident) {
-        if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<512, true, true>, a, grid, 512, lay.smem, s));
-        else CUDA_TRY(launch_search(tlsb_search_kernel<512, true, false>, a, grid, 512, lay.smem, s));
-    } else if (lay.tiled && lay.threads == 256) {
-        if (uni) CUDA_TRY(launch_search(tlsb_search_tiled_kernel<256, true>, a, grid, 256, lay.smem, s));
-        else CUDA_TRY(launch_search(tlsb_search_tiled_kernel<256, false>, a, grid, 256, lay.smem, s));
+    cudaError_t le = cudaSuccess;
+#define TLSB_GO(K) le = launch_search(K, a, grid, lay.threads, lay.smem, s)
+    if (lay.resident) {
+        if (lay.threads == 256) {
+            if (uni && lay.kb == 7) TLSB_GO((tlsb_search_kernel<256, true, true, 7>));
+            else if (uni) TLSB_GO((tlsb_search_kernel<256, true, true, 5>));
+            else TLSB_GO((tlsb_search_kernel<256, true, false, 5>));
+        } else {
+            if (uni && lay.kb == 7) TLSB_GO((tlsb_search_kernel<512, true, true, 7>));
+            else if (uni) TLSB_GO((tlsb_search_kernel<512, true, true, 5>));
+            else TLSB_GO((tlsb_search_kernel<512, true, false, 5>));
+        }
     } else if (lay.tiled) {
-        if (uni) CUDA_TRY(launch_search(tlsb_search_tiled_kernel<512, true>, a, grid, 512, lay.smem, s));
-        else CUDA_TRY(launch_search(tlsb_search_tiled_kernel<512, false>, a, grid, 512, lay.smem, s));
+        if (lay.threads == 256) {
+            if (uni && lay.kb == 7) TLSB_GO((tlsb_search_tiled_kernel<256, true, 7>));
+            else if (uni) TLSB_GO((tlsb_search_tiled_kernel<256, true, 5>));
+            else TLSB_GO((tlsb_search_tiled_kernel<256, false, 5>));
+        } else {
+            if (uni && lay.kb == 7) TLSB_GO((tlsb_search_tiled_kernel<512, true, 7>));
+            else if (uni) TLSB_GO((tlsb_search_tiled_kernel<512, true, 5>));
+            else TLSB_GO((tlsb_search_tiled_kernel<512, false, 5>));
+        }
     } else {
-        if (uni) CUDA_TRY(launch_search(tlsb_search_kernel<256, false, true>, a, grid, 256, lay.smem, s));
-        else CUDA_TRY(launch_search(tlsb_search_kernel<256, false, false>, a, grid, 256, lay.smem, s));
+        if (uni && lay.kb == 7) TLSB_GO((tlsb_search_kernel<256, false, true, 7>));
+        else if (uni) TLSB_GO((tlsb_search_kernel<256, false, true, 5>));
+        else TLSB_GO((tlsb_search_kernel<256, false, false, 5>));
     }
+#undef TLSB_GO
+    CUDA_TRY(le);
     CUDA_TRY(cudaEventRecord(h->ev1, s));
     h->launches += 1;
     h->timed = true;
@@ -2050,7 +2085,7 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
             sq2 = std::fma(q, q, sq2);
         }
         wr.sq2 = sq2;
-        for (int j = 0; j < xth * kPadGroups * kBlock; ++j) tq.push_back(0.0);  // ramp-out + pipeline overshoot
+        for (int j = 0; j < xth * kPadGroups * kBlockMax; ++j) tq.push_back(0.0);  // ramp-out + pipeline overshoot
     }
     int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
@@ -2058,7 +2093,7 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     if ((rc = upload(h->tq, tq.data(), tq.size() * 8))) return rc;
     CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->recs.swap(recs);
-    h->pad = kPadGroups * kBlock * xmax;
+    h->pad = kPadGroups * kBlockMax * xmax;
     h->nU = nU;
     h->M = M;
     h->prm = *prm;
@@ -2156,6 +2191,7 @@ int64_t tlsb_last_launch_count(const tlsb_handle *h) { return h ? h->launches : 
 int32_t tlsb_last_path_resident(const tlsb_handle *h) { return h && h->layout.resident ? 1 : 0; }
 int32_t tlsb_last_path(const tlsb_handle *h) { return !h ? 0 : h->layout.resident ? 1 : h->layout.tiled ? 2 : 3; }
 int32_t tlsb_last_chunk(const tlsb_handle *h) { return h ? h->layout.chunk : 0; }
+int32_t tlsb_last_block(const tlsb_handle *h) { return h ? h->layout.kb : 0; }
 
 int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_segments, int64_t *global_sort_periods)
 {

@@ -20,7 +20,7 @@ EXPORTS = (
     "tlsb_last_error", "tlsb_version", "tlsb_device_count", "tlsb_set_plan_mode",
     "tlsb_plan_fallback_count", "tlsb_last_layout",
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
-    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info",
+    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info", "tlsb_last_block",
     "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
 )
 
@@ -91,6 +91,8 @@ def lib():
                                        _c_vp, _c_i64, _c_vp, _c_vp]
     L.tlsb_last_path.restype = ctypes.c_int32
     L.tlsb_last_path.argtypes = [_c_vp]
+    L.tlsb_last_block.restype = ctypes.c_int32
+    L.tlsb_last_block.argtypes = [_c_vp]
     L.tlsb_last_chunk.restype = ctypes.c_int32
     L.tlsb_last_chunk.argtypes = [_c_vp]
     L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
@@ -343,7 +345,8 @@ class Searcher(object):
         _check(lib().tlsb_last_layout(self._h, ctypes.byref(th), ctypes.byref(cp), ctypes.byref(qc), ctypes.byref(sm)),
                "tlsb_last_layout")
         return dict(threads=th.value, ctas_per_sm=cp.value, queue_capacity=qc.value, smem_bytes=sm.value,
-                    resident=self.resident, path=self.path, chunk=self.chunk)
+                    resident=self.resident, path=self.path, chunk=self.chunk,
+                    block=int(lib().tlsb_last_block(self._h)))
 
     @property
     def launch_count(self):
