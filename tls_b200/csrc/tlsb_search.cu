@@ -772,6 +772,10 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                         tap_block<kBlock, true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
                     else
                         tap_block<kBlock, false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
+                    // the block's own minimum first (same width, ascending offsets: strict '<' keeps the
+                    // earliest), then ONE lexicographic comparison against the lane's running best
+                    double blk_chi = INFINITY, blk_D = 0.0;
+                    int blk_i = -1;
 #pragma unroll
                     for (int rr = 0; rr < kBlock; ++rr) {
                         if (mask & (1 << rr)) {
@@ -781,9 +785,10 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                             const double Aq = kUniformW ? a.w0 * wr.sq2 : A[rr];
                             double chi = T + D * (D * Aq - 2.0 * B[rr]);
                             if (wr.L < wr.W) chi -= untouched_tail<kUniformW>(w, wd, a.w0, i + wr.L, i + wr.W);
-                            if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
+                            if (chi < blk_chi) { blk_chi = chi; blk_D = D; blk_i = i; }
                         }
                     }
+                    if (blk_i >= 0 && better(blk_chi, u, blk_i, best)) { best.chi2 = blk_chi; best.D = blk_D; best.u = u; best.i = blk_i; }
                 }
             }
             if (!more) break;
@@ -1301,6 +1306,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                             tap_block<kBlock, true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
                         else
                             tap_block<kBlock, false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
+                        double blk_chi = INFINITY, blk_D = 0.0;
+                        int blk_i = -1;
 #pragma unroll
                         for (int rr = 0; rr < kBlock; ++rr) {
                             if (mask & (1 << rr)) {
@@ -1310,9 +1317,10 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                                 const double Aq = kUniformW ? a.w0 * wr.sq2 : A[rr];
                                 double chi = T + D * (D * Aq - 2.0 * B[rr]);
                                 if (wr.L < wr.W) chi -= untouched_tail<kUniformW>(wb, wdb, a.w0, i + wr.L, i + wr.W);
-                                if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
+                                if (chi < blk_chi) { blk_chi = chi; blk_D = D; blk_i = i; }
                             }
                         }
+                        if (blk_i >= 0 && better(blk_chi, u, blk_i, best)) { best.chi2 = blk_chi; best.D = blk_D; best.u = u; best.i = blk_i; }
                     }
                 }
                 if (!more) break;
