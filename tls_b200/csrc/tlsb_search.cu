@@ -1572,6 +1572,9 @@ struct tlsb_handle {
     double dev_plan_span = 0.0;
     DevBuf asc_order, brec, bchi, bSR, bpr, bpw, bscal, bamax;  // batch pipeline
     std::vector<int> h_asc_order;
+    bool asc_valid = false;        // asc_order matches the current periods (made on demand by the batch call)
+    bool defer_sync = false;       // one-shot call: the caller's buffers outlive the whole call, setters need not wait
+    std::vector<double> h_tq;      // host copy of tq (keeps the upload source alive without a synchronisation)
     // templates
     tlsb_params prm{};
     int nU = 0, M = 0, pad = 0;
@@ -1626,7 +1629,7 @@ int refresh_records(tlsb_handle *h, int kb, cudaStream_t s)
     }
     int rc;
     if ((rc = upload(h->d_rec, h->recs.data(), sizeof(WidthRec) * (size_t)h->nU, s))) return rc;  // ordered behind earlier launches on s
-    CUDA_TRY(cudaStreamSynchronize(s));
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(s));  // h->recs itself stays alive and is only rewritten here
     h->recs_stale = false;
     h->rec_kb = kb;
     h->host_plan_valid = false;
@@ -1994,7 +1997,7 @@ static int set_curves(tlsb_handle *h, const double *t, const double *y, const do
         h->c_uniform[c] = uniform ? 1 : 0;
         h->c_w0[c] = 1.0 / (dc[0] * dc[0]);
     }
-    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->n_curves = (int)n_curves;
     h->shared_t = shared_t;
     h->cur = 0;
@@ -2098,8 +2101,9 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
     int rc;
-    if ((rc = upload(h->tq, tq.data(), tq.size() * 8))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->h_tq.swap(tq);  // stays alive behind the asynchronous upload
+    if ((rc = upload(h->tq, h->h_tq.data(), h->h_tq.size() * 8))) return rc;
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->recs.swap(recs);
     h->pad = kPadGroups * kBlockMax * xmax;
     h->nU = nU;
@@ -2121,13 +2125,8 @@ int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods)
     h->h_periods.assign(periods, periods + n_periods);
     int rc;
     if ((rc = upload(h->periods, periods, sizeof(double) * (size_t)n_periods))) return rc;
-    // main.py:190-196: results are consumed in ascending-period order
-    h->h_asc_order.resize((size_t)n_periods);
-    std::iota(h->h_asc_order.begin(), h->h_asc_order.end(), 0);
-    std::stable_sort(h->h_asc_order.begin(), h->h_asc_order.end(),
-                     [&](int x, int y) { return periods[x] < periods[y]; });
-    if ((rc = upload(h->asc_order, h->h_asc_order.data(), sizeof(int) * (size_t)n_periods))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->asc_valid = false;
     h->have_periods = true;
     h->host_plan_valid = false;
     h->dev_plan_valid = false;
@@ -2274,11 +2273,14 @@ static int search_on_device(int device, const tlsb_lightcurve *lc, const double 
     }
     tlsb_handle *h = pool_take(device);
     int rc = h ? 0 : tlsb_create(&h, device);
+    if (!rc) h->defer_sync = true;  // every input buffer outlives this call: one synchronisation, at the end
     if (!rc) rc = tlsb_set_lightcurve(h, lc);
     if (!rc) rc = tlsb_set_templates(h, tp, prm);
     if (!rc) rc = tlsb_set_periods(h, periods, nP);
     if (!rc) rc = tlsb_search_async(h, nullptr, nullptr);
     if (!rc) rc = tlsb_get_results(h, nullptr, chi2, row, depth, t0);
+    if (h) h->defer_sync = false;
+    if (rc && h) cudaStreamSynchronize(nullptr);
     if (rc && err) *err = g_error;
     if (rc)
         tlsb_destroy(h);  // do not recycle a handle that failed
@@ -2489,6 +2491,15 @@ extern "C" int tlsb_search_batch(tlsb_handle *h, void *cuda_stream, int64_t medi
     if (h->brec.ensure(B * stride * 8) || h->bchi.ensure(B * P * 8) || h->bSR.ensure(B * P * 8) ||
         h->bpr.ensure(B * P * 8) || h->bpw.ensure(B * P * 8) || h->bscal.ensure(B * 32) || h->bamax.ensure(B * 8))
         return fail(TLSB_ERR_ALLOC, "device allocation failed (batch buffers)");
+    if (!h->asc_valid) {  // main.py:190-196: the spectra consume chi2 in ascending-period order
+        const std::vector<double> &per = h->h_periods;
+        h->h_asc_order.resize(P);
+        std::iota(h->h_asc_order.begin(), h->h_asc_order.end(), 0);
+        std::stable_sort(h->h_asc_order.begin(), h->h_asc_order.end(), [&](int x, int y) { return per[x] < per[y]; });
+        int rc0 = upload(h->asc_order, h->h_asc_order.data(), sizeof(int) * P, s);
+        if (rc0) return rc0;
+        h->asc_valid = true;
+    }
     double *rec = h->brec.as<double>();
     std::vector<long long> status(B);
     int64_t launches = 0;
