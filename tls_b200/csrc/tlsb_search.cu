@@ -118,6 +118,7 @@ struct PlanArgs {
     double R_star_min, R_star_max, M_star_min, M_star_max;
     double eps;                                         // kPlanEps (or huge: test mode)
     int *ulo, *uhi, *order, *bin_of;                    // [P]
+    int *gbins;                                         // [kPlanBins + 2] cost histogram, uncertain periods, finished CTAs (zero between launches)
     long long *status;                                  // records word 3P: number of uncertain periods
 };
 
@@ -168,22 +169,23 @@ __host__ __device__ inline double t14_fraction(double R_s, double M_s, double P,
     return frac > 0.12 ? 0.12 : frac;
 }
 
-// One CTA: admissible width range per period (core.py:143-156) and the processing order.
+// Admissible width range per period (core.py:143-156) and the processing order.  The T14 limits
+// (two fp64 pow() per period) are spread over many CTAs; every CTA adds its periods to a global
+// histogram of cost bins, and the LAST CTA to finish scans the bins and scatters the periods
+// into the processing order (most expensive first), then clears the bins for the next launch.
 // The device pow() may differ from the host libm in the last bits; a period whose limits sit
 // within eps of an integer is counted in *status and the host then redoes the plan exactly.
 __global__ void __launch_bounds__(kPlanThreads) tlsb_plan_kernel(const PlanArgs a)
 {
     __shared__ int bins[kPlanBins];
     __shared__ int warp_tot[32];
-    __shared__ int uncertain;
+    __shared__ int last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int b = tid; b < kPlanBins; b += kPlanThreads) bins[b] = 0;
-    if (tid == 0) uncertain = 0;
-    __syncthreads();
     const int nU = a.nU;
     const int total_tiles = nU > 0 ? a.rec[0].cum + a.rec[0].tiles : 0;
     const double Nd = (double)a.N;
-    for (int p = tid; p < a.P; p += kPlanThreads) {
+    int unsure_count = 0;
+    for (int p = blockIdx.x * kPlanThreads + tid; p < a.P; p += gridDim.x * kPlanThreads) {
         const double period = a.periods[p];
         const double dmax = t14_fraction(a.R_star_max, a.M_star_max, period, false);
         const double dmin = t14_fraction(a.R_star_min, a.M_star_min, period, true);
@@ -212,12 +214,18 @@ __global__ void __launch_bounds__(kPlanThreads) tlsb_plan_kernel(const PlanArgs 
         int bin = (int)(((long long)cost * kPlanBins) / (total_tiles + 1));
         bin = kPlanBins - 1 - (bin < kPlanBins ? bin : kPlanBins - 1);  // expensive periods first
         a.bin_of[p] = bin;
-        atomicAdd(&bins[bin], 1);
-        if (unsure) atomicAdd(&uncertain, 1);
+        atomicAdd(&a.gbins[bin], 1);
+        unsure_count += unsure ? 1 : 0;
     }
+    if (unsure_count) atomicAdd(&a.gbins[kPlanBins], unsure_count);
+    __threadfence();
     __syncthreads();
+    if (tid == 0) last = atomicAdd(&a.gbins[kPlanBins + 1], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
     // exclusive scan of the 1024 bins (one per thread)
-    const int mine = bins[tid];
+    const int mine = *(volatile int *)&a.gbins[tid];
     int incl = mine;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -239,8 +247,13 @@ __global__ void __launch_bounds__(kPlanThreads) tlsb_plan_kernel(const PlanArgs 
     __syncthreads();
     bins[tid] = warp_tot[wid] + incl - mine;
     __syncthreads();
-    for (int p = tid; p < a.P; p += kPlanThreads) a.order[atomicAdd(&bins[a.bin_of[p]], 1)] = p;
-    if (tid == 0) *a.status = (long long)uncertain;
+    for (int p = tid; p < a.P; p += kPlanThreads) a.order[atomicAdd(&bins[__ldcg(a.bin_of + p)], 1)] = p;
+    if (tid == 0) {
+        *a.status = (long long)*(volatile int *)&a.gbins[kPlanBins];
+        a.gbins[kPlanBins] = 0;
+        a.gbins[kPlanBins + 1] = 0;
+    }
+    a.gbins[tid] = 0;  // self-cleaning: the next launch needs no memset
 }
 
 __device__ __forceinline__ double fold_phase(double t, double r)
@@ -1593,7 +1606,7 @@ struct tlsb_handle {
     int plan_mode = 0;            // 0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)
     bool host_plan_valid = false;
     // outputs / scheduling / scratch
-    DevBuf out, counter, scratch;
+    DevBuf out, counter, scratch, plan_bins;
     // final_T0_fit
     DevBuf t0_trials, t0_model, t0_resid;
     bool t0_resident = false;
@@ -1833,7 +1846,9 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
         pa.eps = h->plan_mode == 2 ? 1e300 : kPlanEps;
         pa.ulo = h->ulo.as<int>(); pa.uhi = h->uhi.as<int>(); pa.order = h->order.as<int>();
         pa.bin_of = h->bin_of.as<int>(); pa.status = status;
-        tlsb_plan_kernel<<<1, kPlanThreads, 0, s>>>(pa);
+        pa.gbins = h->plan_bins.as<int>();
+        const int plan_grid = std::max(1, std::min(h->num_sms, (P + kPlanThreads - 1) / kPlanThreads));
+        tlsb_plan_kernel<<<plan_grid, kPlanThreads, 0, s>>>(pa);
         CUDA_TRY(cudaGetLastError());
         h->host_plan_valid = false;
         h->launches += 1;
@@ -1946,6 +1961,8 @@ int tlsb_create(tlsb_handle **out, int32_t device)
     CUDA_TRY(cudaEventCreate(&h->ev1));
     if (h->counter.ensure(32)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
     CUDA_TRY(cudaMemset(h->counter.p, 0, 32));  // [0,1] search kernel, [2,3] T0-fit kernel
+    if (h->plan_bins.ensure((kPlanBins + 2) * 4)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    CUDA_TRY(cudaMemset(h->plan_bins.p, 0, (kPlanBins + 2) * 4));
     *out = h;
     return 0;
 }
@@ -1956,7 +1973,7 @@ int tlsb_destroy(tlsb_handle *h)
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo,
                       &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch, &h->t0_trials, &h->t0_model,
-                      &h->t0_resid, &h->asc_order, &h->brec, &h->bchi, &h->bSR, &h->bpr, &h->bpw, &h->bscal, &h->bamax})
+                      &h->t0_resid, &h->plan_bins, &h->asc_order, &h->brec, &h->bchi, &h->bSR, &h->bpr, &h->bpw, &h->bscal, &h->bamax})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
