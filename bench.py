@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--max-periods", type=int, default=0, help="cap the periods per rank to an evenly spread subset of the grid (0 = whole grid)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the extra records (cfg2 whole grid through the tiled kernel, .power() wall clock)")
     return ap.parse_args()
 
 
@@ -374,7 +376,8 @@ def run_b200(args):
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roofline = {
             "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-            "traffic": None, "peak_source": peak_src, "kernel": "tlsb_search_kernel",
+            "traffic": None, "peak_source": peak_src,
+            "kernel": "tlsb_search_tiled_kernel" if job.searcher.path == "tiled" else "tlsb_search_kernel",
             "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
             "algorithmic_bytes_per_period": alg_bytes / P_rank, "mean_admissible_widths": mean_widths,
             "kernel_share_of_step": k_ms * args.steps / float(sum(step_ms)),
@@ -396,6 +399,10 @@ def run_b200(args):
                    "sample": "%d of %d periods (evenly spread) of the same workload, C restatement of "
                              "core.search_period under oracle/, OpenMP over periods" % (n, P_rank)}
 
+    secondary = None
+    if rank == 0 and n_gpus == 1 and not args.no_secondary and not args.max_periods:
+        secondary = secondary_records(args, peak_gbs, local)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
@@ -407,11 +414,68 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "parity": parity,
         }
+        if secondary:
+            line["secondary"] = secondary
         _emit(json.dumps(line))
     job.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def secondary_records(args, peak_gbs, device):
+    """Extra context beside the headline (never part of `value`): the Kepler-long configuration
+    (cfg2, whole default grid, tiled kernel) and the wall clock of the drop-in ``.power()``."""
+    import warnings
+
+    import torch
+
+    from tls_b200 import native, transitleastsquares, workloads
+
+    out = {}
+    try:
+        if args.workload != "cfg2":
+            inp = build_inputs("cfg2", 3)
+            s = native.Searcher(device=device)
+            s.set_inputs(inp.t, inp.y, inp.dy, inp.templates, inp.params)
+            s.set_periods(inp.periods)
+            stream = torch.cuda.current_stream()
+            ms = []
+            for k in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                s.search_async(stream=stream.cuda_stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if k >= 2:
+                    ms.append(e0.elapsed_time(e1))
+            alg, _, _ = algorithmic_bytes(inp, inp.periods[:: max(1, len(inp.periods) // 2000)])
+            alg *= len(inp.periods) / len(inp.periods[:: max(1, len(inp.periods) // 2000)])
+            step = float(np.mean(ms))
+            out["cfg2"] = {
+                "workload": "cfg2: Kepler-long 4 yr @ 30 min, 50 ppm, whole default grid", "n_points": int(len(inp.y)),
+                "periods": int(len(inp.periods)), "value": len(inp.periods) / (step * 1e-3), "unit": UNIT,
+                "ms_per_step": step, "steps": len(ms), "layout": s.layout, "sort": s.sort_info,
+                "roofline_frac": alg / (step * 1e-3) / 1e9 / peak_gbs, "l2": "inputs larger than L2 per step (scratch 2.5 MB per CTA)",
+            }
+            s.close()
+    except Exception as exc:  # context only: never fail the headline
+        out["cfg2"] = {"error": str(exc)[:200]}
+    try:
+        t, y, dy, kw = workloads.lightcurve(args.workload)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = transitleastsquares(t, y, dy, verbose=False)
+            best = 1e9
+            for _ in range(3):
+                t0 = time.perf_counter()
+                res = model.power(show_progress_bar=False, verbose=False, device=device, **kw)
+                best = min(best, time.perf_counter() - t0)
+        out["power"] = {"call": "transitleastsquares(t, y).power() end to end (grids, bank, search, spectra, T0 fit, statistics)",
+                        "workload": args.workload, "wall_s": best, "SDE": float(res.SDE), "period": float(res.period)}
+    except Exception as exc:
+        out["power"] = {"error": str(exc)[:200]}
+    return out
 
 
 def main():
