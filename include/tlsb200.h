@@ -108,14 +108,23 @@ int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods);
  * then ONE status word (int64).  status != 0 means the device-side T14 limits
  * (grid.py:9-32, core.py:143-156) of that many periods fell within 1e-9 (relative) of an
  * integer, where the device pow() cannot be trusted to round like the host libm: the
- * consumer must then call tlsb_set_plan_mode(h, 1) and search again (tlsb_get_results does
- * this by itself for the handle's own buffer). */
+ * consumer must then call tlsb_resolve_plan (tlsb_get_results does this by itself for the
+ * handle's own buffer). */
 int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev);
 /* 0 = plan on the device (default); 1 = exact plan on the host (libm pow, bit-identical to
- * the reference's T14); 2 = device plan that flags every period (exercises the fallback). */
+ * the reference's T14); 2 = device plan that flags every period (exercises the repair path);
+ * 3 = as 2 and the device plan is deliberately wrong for every 7th period (tests). */
 int tlsb_set_plan_mode(tlsb_handle *h, int32_t mode);
-/* How many times tlsb_get_results had to redo a search with the exact host plan. */
+/* After a search on `cuda_stream` whose status word (see tlsb_search_async) is non-zero: recompute the
+ * flagged periods' admissible widths on the host (core.py:143-156 with libm, bit-identical to the
+ * reference), search again ONLY the periods whose range differs from the device's, and clear the
+ * status word.  records_dev as given to tlsb_search_async (NULL = the handle's buffer).
+ * Synchronises.  tlsb_get_results and tlsb_search_batch do this themselves. */
+int tlsb_resolve_plan(tlsb_handle *h, void *cuda_stream, void *records_dev);
+/* How many searches had to be redone completely with the exact host plan (more flagged periods
+ * than the plan kernel lists), and how many single periods were re-searched by the repair path. */
 int64_t tlsb_plan_fallback_count(const tlsb_handle *h);
+int64_t tlsb_plan_repair_count(const tlsb_handle *h);
 /* Wait for the stream and copy the handle's own result buffer to the host. */
 int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_t *row_out,
                      double *depth_out, int64_t *t0_index_out);

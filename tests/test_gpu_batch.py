@@ -86,10 +86,11 @@ def test_batch_with_per_curve_time_axes_and_records():
     s.search_async()
     chi2b = s.results()[0]
     np.testing.assert_array_equal(chi2b, out["chi2"][1])
-    s.set_plan_mode(2)  # every period flagged: the batch redoes itself with the exact host plan
+    s.set_plan_mode(3)  # every period flagged, every 7th device range wrong: the batch repairs those periods
     out2 = s.search_batch(stats.median_window(3), want_power=False)
     np.testing.assert_array_equal(out2["chi2"], out["chi2"])
-    assert s.plan_fallbacks >= 1
+    np.testing.assert_array_equal(out2["row"], out["row"])
+    assert s.plan_repairs >= len(g["periods"]) // 8
     s.close()
 
 

@@ -50,24 +50,55 @@ def test_handle_api_equals_one_shot_and_is_repeatable():
 
 
 @pytest.mark.parametrize("name", ["small", "no_admissible", "cfg1_hetero"])
-def test_device_plan_equals_exact_host_plan_and_fallback(name):
-    """T14 limits on the device (plan kernel) vs the exact host plan (libm pow), and the
-    automatic fallback when the device flags a limit as too close to an integer."""
+def test_device_plan_equals_exact_host_plan_and_repair(name):
+    """T14 limits on the device (plan kernel) vs the exact host plan (libm pow), and the repair of
+    periods the device flags as too close to an integer: mode 2 flags every period (nothing differs,
+    nothing is searched again), mode 3 also makes every 7th device range wrong (those periods are
+    searched again with the exact range)."""
     native = _native()
     g = load_search_golden(name)
     s = native.Searcher()
     s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
     s.set_periods(g["periods"])
     out = {}
-    for mode in (0, 1, 2):
+    repairs = {}
+    for mode in (0, 1, 2, 3):
         s.set_plan_mode(mode)
         s.search_async()
         out[mode] = s.results()
-    assert s.plan_fallbacks == 1  # only mode 2 (every period flagged) had to redo the search
-    for mode in (1, 2):
+        repairs[mode] = s.plan_repairs
+    assert repairs[0] == repairs[1] == repairs[2] == 0
+    if name != "no_admissible":
+        assert repairs[3] >= len(g["periods"]) // 8   # every 7th period with an admissible width
+    assert s.plan_fallbacks == (1 if len(g["periods"]) > 4096 else 0)  # more flags than the kernel lists: whole exact plan
+    for mode in (1, 2, 3):
         for a, b in zip(out[0], out[mode]):
             np.testing.assert_array_equal(a, b)
     assert_search_parity(out[0][:3], g, rtol=RTOL, label=name)
+    s.close()
+
+
+def test_resolve_plan_on_a_caller_owned_record_buffer():
+    """The asynchronous API: a sabotaged device plan, then tlsb_resolve_plan on the caller's buffer."""
+    import torch
+
+    native = _native()
+    g = load_search_golden("small")
+    P = len(g["periods"])
+    s = native.Searcher()
+    s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
+    s.set_periods(g["periods"])
+    rec = torch.zeros(3 * P + 1, dtype=torch.int64, device="cuda")
+    s.set_plan_mode(3)
+    s.search_async(records_ptr=rec.data_ptr())
+    torch.cuda.synchronize()
+    assert int(rec[3 * P].item()) == P            # every period flagged
+    wrong = native.unpack_records(rec.cpu().numpy(), P)
+    s.resolve_plan(records_ptr=rec.data_ptr())
+    assert int(rec[3 * P].item()) == 0
+    fixed = native.unpack_records(rec.cpu().numpy(), P)
+    assert not np.array_equal(wrong[0], fixed[0])  # the sabotage did change some results ...
+    assert_search_parity(fixed[:3], g, rtol=RTOL, label="resolved")   # ... and the repair restored them
     s.close()
 
 

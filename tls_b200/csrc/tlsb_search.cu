@@ -62,6 +62,7 @@ constexpr int kSegPerThread = 16;   // keys of one segment a thread keeps in reg
 constexpr int kMaxSegments = 64;     // phase segments of the on-chip sort of the tiled path
 constexpr int kPlanThreads = 1024;
 constexpr int kPlanBins = 1024;
+constexpr int kUnsureCap = 4096;     // uncertain periods the plan kernel lists (more: the whole plan is redone on the host)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kSignalDepth = 0.5;  // tls_constants.py:71
 constexpr double kPlanEps = 1e-9;     // relative distance to an integer below which the device plan is "uncertain"
@@ -119,6 +120,8 @@ struct PlanArgs {
     double eps;                                         // kPlanEps (or huge: test mode)
     int *ulo, *uhi, *order, *bin_of;                    // [P]
     int *gbins;                                         // [kPlanBins + 2] cost histogram, uncertain periods, finished CTAs (zero between launches)
+    int *unsure_list;                                   // [kUnsureCap] the first uncertain periods
+    int sabotage;                                       // tests: drop the widest admissible width of every 7th period
     long long *status;                                  // records word 3P: number of uncertain periods
 };
 
@@ -184,7 +187,6 @@ __global__ void __launch_bounds__(kPlanThreads) tlsb_plan_kernel(const PlanArgs 
     const int nU = a.nU;
     const int total_tiles = nU > 0 ? a.rec[0].cum + a.rec[0].tiles : 0;
     const double Nd = (double)a.N;
-    int unsure_count = 0;
     for (int p = blockIdx.x * kPlanThreads + tid; p < a.P; p += gridDim.x * kPlanThreads) {
         const double period = a.periods[p];
         const double dmax = t14_fraction(a.R_star_max, a.M_star_max, period, false);
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(kPlanThreads) tlsb_plan_kernel(const PlanArgs 
             if ((double)a.rec[hi + half].W <= wmax_f) { hi += half + 1; n -= half + 1; } else n = half;
         }
         if (!(wmax_f >= wmin_f) || hi < lo) hi = lo;  // NaN / empty
+        if (a.sabotage && p % 7 == 3 && hi > lo) hi -= 1;
         a.ulo[p] = lo;
         a.uhi[p] = hi;
         const int cost = hi > lo ? a.rec[lo].cum + a.rec[lo].tiles - a.rec[hi - 1].cum : 0;
@@ -215,9 +218,11 @@ __global__ void __launch_bounds__(kPlanThreads) tlsb_plan_kernel(const PlanArgs 
         bin = kPlanBins - 1 - (bin < kPlanBins ? bin : kPlanBins - 1);  // expensive periods first
         a.bin_of[p] = bin;
         atomicAdd(&a.gbins[bin], 1);
-        unsure_count += unsure ? 1 : 0;
+        if (unsure) {
+            const int at = atomicAdd(&a.gbins[kPlanBins], 1);
+            if (at < kUnsureCap) a.unsure_list[at] = p;
+        }
     }
-    if (unsure_count) atomicAdd(&a.gbins[kPlanBins], unsure_count);
     __threadfence();
     __syncthreads();
     if (tid == 0) last = atomicAdd(&a.gbins[kPlanBins + 1], 1) == (int)gridDim.x - 1;
@@ -1606,14 +1611,15 @@ struct tlsb_handle {
     int plan_mode = 0;            // 0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)
     bool host_plan_valid = false;
     // outputs / scheduling / scratch
-    DevBuf out, counter, scratch, plan_bins;
+    DevBuf out, counter, scratch, plan_bins, unsure;
     // final_T0_fit
     DevBuf t0_trials, t0_model, t0_resid;
     bool t0_resident = false;
     double t0_ms = 0.0;
     // bookkeeping
     int64_t launches = 0;
-    int64_t fallbacks = 0;
+    int64_t fallbacks = 0;        // searches redone completely with the exact host plan
+    int64_t repairs = 0;          // periods re-searched because their exact limits differed from the device's
     Layout layout;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -1653,26 +1659,28 @@ int refresh_records(tlsb_handle *h, int kb, cudaStream_t s)
 // The exact plan on the host (libm pow, bit-identical to the reference's T14): admissible
 // unique-width range per period (core.py:143-156) + processing order.  Used when the device
 // plan reports a limit too close to an integer to trust its pow(), and by plan_mode 1.
+void exact_range(const tlsb_handle *h, double period, int *lo, int *hi)
+{
+    const double dmax = t14_fraction(h->prm.R_star_max, h->prm.M_star_max, period, false);
+    const double dmin = t14_fraction(h->prm.R_star_min, h->prm.M_star_min, period, true);
+    const double naive = h->span / period;
+    const double corr = (naive + 1) / naive;
+    const double wmin_f = std::floor(dmin * (double)h->N);
+    const double wmax_f = std::ceil(dmax * (double)h->N * corr);
+    int a = 0;
+    while (a < h->nU && (double)h->recs[a].W < wmin_f) ++a;
+    int b = h->nU;
+    while (b > a && (double)h->recs[b - 1].W > wmax_f) --b;
+    if (!(wmax_f >= wmin_f)) b = a;  // NaN / empty
+    *lo = a;
+    *hi = b;
+}
+
 int host_plan(tlsb_handle *h)
 {
-    const int P = h->P, N = h->N;
+    const int P = h->P;
     std::vector<int> lo(P), hi(P), order(P);
-    for (int p = 0; p < P; ++p) {
-        const double period = h->h_periods[p];
-        const double dmax = t14_fraction(h->prm.R_star_max, h->prm.M_star_max, period, false);
-        const double dmin = t14_fraction(h->prm.R_star_min, h->prm.M_star_min, period, true);
-        const double naive = h->span / period;
-        const double corr = (naive + 1) / naive;
-        const double wmin_f = std::floor(dmin * (double)N);
-        const double wmax_f = std::ceil(dmax * (double)N * corr);
-        int a = 0;
-        while (a < h->nU && (double)h->recs[a].W < wmin_f) ++a;
-        int b = h->nU;
-        while (b > a && (double)h->recs[b - 1].W > wmax_f) --b;
-        if (!(wmax_f >= wmin_f)) b = a;  // NaN / empty
-        lo[p] = a;
-        hi[p] = b;
-    }
+    for (int p = 0; p < P; ++p) exact_range(h, h->h_periods[p], &lo[p], &hi[p]);
     std::iota(order.begin(), order.end(), 0);
     // most expensive first: cost ~ number of candidate tiles in the admissible range
     auto cost = [&](int p) {
@@ -1820,7 +1828,10 @@ cudaError_t launch_search(K kernel, const SearchArgs &a, int grid, int threads, 
 }
 
 // plan (unless the exact host plan is in force) + search, asynchronous on `s`
-int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact_plan)
+// `only` / `n_only`: search just these periods (device array of indices) with the plan that is already
+// on the device - used to repair the few periods whose device-side limits were uncertain.
+int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact_plan, const int *only = nullptr,
+                   int n_only = 0)
 {
     int rc;
     const Layout lay = choose_layout(h);
@@ -1832,7 +1843,9 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
         h->order.ensure(sizeof(int) * (size_t)P) || h->bin_of.ensure(sizeof(int) * (size_t)P))
         return fail(TLSB_ERR_ALLOC, "device allocation failed");
     h->launches = 0;
-    if (exact_plan) {
+    if (only) {
+        // keep ulo/uhi as they are
+    } else if (exact_plan) {
         if (!h->host_plan_valid && (rc = host_plan(h))) return rc;
         CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));
     } else if (h->dev_plan_valid && h->dev_plan_span == h->span && h->plan_mode == 0) {
@@ -1843,10 +1856,12 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
         pa.N = h->N; pa.span = h->span;
         pa.R_star_min = h->prm.R_star_min; pa.R_star_max = h->prm.R_star_max;
         pa.M_star_min = h->prm.M_star_min; pa.M_star_max = h->prm.M_star_max;
-        pa.eps = h->plan_mode == 2 ? 1e300 : kPlanEps;
+        pa.eps = h->plan_mode >= 2 ? 1e300 : kPlanEps;
+        pa.sabotage = h->plan_mode == 3 ? 1 : 0;
         pa.ulo = h->ulo.as<int>(); pa.uhi = h->uhi.as<int>(); pa.order = h->order.as<int>();
         pa.bin_of = h->bin_of.as<int>(); pa.status = status;
         pa.gbins = h->plan_bins.as<int>();
+        pa.unsure_list = h->unsure.as<int>();
         const int plan_grid = std::max(1, std::min(h->num_sms, (P + kPlanThreads - 1) / kPlanThreads));
         tlsb_plan_kernel<<<plan_grid, kPlanThreads, 0, s>>>(pa);
         CUDA_TRY(cudaGetLastError());
@@ -1865,7 +1880,8 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     a.dval = h->dval.as<double>() + cur_off; a.wval = h->wval.as<double>() + cur_off; a.N = h->N;
     a.tq = h->tq.as<double>(); a.rec = h->d_rec.as<WidthRec>(); a.nU = h->nU; a.M = h->M; a.pad = h->pad;
     a.periods = h->periods.as<double>(); a.ulo = h->ulo.as<int>(); a.uhi = h->uhi.as<int>();
-    a.order = h->order.as<int>(); a.P = P; a.depth_min = h->prm.transit_depth_min; a.w0 = h->w0;
+    a.order = only ? only : h->order.as<int>(); a.P = only ? n_only : P;
+    a.depth_min = h->prm.transit_depth_min; a.w0 = h->w0;
     a.out_chi2 = rec_words;
     a.out_depth = rec_words + P;
     a.out_packed = reinterpret_cast<long long *>(rec_words + 2 * (size_t)P);
@@ -1875,7 +1891,7 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     a.chunk = lay.chunk;
     a.seg_cap = lay.seg_cap;
     a.n_seg = lay.n_seg;
-    const int grid = std::min(P, h->num_sms * lay.ctas_per_sm);
+    const int grid = std::min(only ? n_only : P, h->num_sms * lay.ctas_per_sm);
     if (!lay.resident) {
         if (lay.NB < 1) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
         a.scratch_per_cta = lay.scratch_per_cta;
@@ -1917,6 +1933,59 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     CUDA_TRY(cudaEventRecord(h->ev1, s));
     h->launches += 1;
     h->timed = true;
+    return 0;
+}
+
+
+// The plan kernel flagged `count` periods whose T14 limits sit too close to an integer for the
+// device pow() to be trusted.  Recompute just those on the host (libm, bit-identical to the
+// reference), patch the device plan where it differs, and list the periods that changed.
+// Returns 1 if there are more flagged periods than the kernel could list (caller: whole exact plan).
+int find_changed_periods(tlsb_handle *h, cudaStream_t s, long long count, std::vector<int> *changed)
+{
+    changed->clear();
+    if (count > kUnsureCap) return 1;
+    const int n = (int)count;
+    std::vector<int> list((size_t)n), lo((size_t)h->P), hi((size_t)h->P);
+    CUDA_TRY(cudaMemcpyAsync(list.data(), h->unsure.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(lo.data(), h->ulo.p, sizeof(int) * (size_t)h->P, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hi.data(), h->uhi.p, sizeof(int) * (size_t)h->P, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int k = 0; k < n; ++k) {
+        const int p = list[(size_t)k];
+        int a, b;
+        exact_range(h, h->h_periods[(size_t)p], &a, &b);
+        if (a != lo[(size_t)p] || b != hi[(size_t)p]) {
+            CUDA_TRY(cudaMemcpyAsync(h->ulo.as<int>() + p, &a, sizeof(int), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(h->uhi.as<int>() + p, &b, sizeof(int), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s));  // a, b live on this stack frame
+            changed->push_back(p);
+        }
+    }
+    if (!changed->empty())  // the list buffer doubles as the processing order of the repair launch
+        CUDA_TRY(cudaMemcpyAsync(h->unsure.p, changed->data(), sizeof(int) * changed->size(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Repair the records of the current curve after a search whose status word was `count` != 0.
+int resolve_records(tlsb_handle *h, cudaStream_t s, void *records_dev, long long count)
+{
+    std::vector<int> changed;
+    int rc = find_changed_periods(h, s, count, &changed);
+    if (rc < 0) return rc;
+    long long *status = reinterpret_cast<long long *>(reinterpret_cast<double *>(records_dev) + 3 * (size_t)h->P);
+    if (rc == 1) {  // too many to list: the whole plan on the host, everything again
+        h->fallbacks += 1;
+        return enqueue_search(h, s, records_dev, true);
+    }
+    if (!changed.empty()) {
+        h->repairs += (int64_t)changed.size();
+        const int64_t before = h->launches;
+        if ((rc = enqueue_search(h, s, records_dev, false, h->unsure.as<int>(), (int)changed.size()))) return rc;
+        h->launches += before;
+    }
+    CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));
     return 0;
 }
 
@@ -1963,6 +2032,7 @@ int tlsb_create(tlsb_handle **out, int32_t device)
     CUDA_TRY(cudaMemset(h->counter.p, 0, 32));  // [0,1] search kernel, [2,3] T0-fit kernel
     if (h->plan_bins.ensure((kPlanBins + 2) * 4)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
     CUDA_TRY(cudaMemset(h->plan_bins.p, 0, (kPlanBins + 2) * 4));
+    if (h->unsure.ensure(kUnsureCap * 4)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
     *out = h;
     return 0;
 }
@@ -1973,7 +2043,7 @@ int tlsb_destroy(tlsb_handle *h)
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo,
                       &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch, &h->t0_trials, &h->t0_model,
-                      &h->t0_resid, &h->plan_bins, &h->asc_order, &h->brec, &h->bchi, &h->bSR, &h->bpr, &h->bpw, &h->bscal, &h->bamax})
+                      &h->t0_resid, &h->plan_bins, &h->unsure, &h->asc_order, &h->brec, &h->bchi, &h->bSR, &h->bpr, &h->bpw, &h->bscal, &h->bamax})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -2152,7 +2222,7 @@ int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods)
 
 int tlsb_set_plan_mode(tlsb_handle *h, int32_t mode)
 {
-    if (!h || mode < 0 || mode > 2) return fail(TLSB_ERR_ARG, "tlsb_set_plan_mode: mode must be 0, 1 or 2");
+    if (!h || mode < 0 || mode > 3) return fail(TLSB_ERR_ARG, "tlsb_set_plan_mode: mode must be 0..3");
     h->plan_mode = mode;
     return 0;
 }
@@ -2199,10 +2269,12 @@ int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_
         CUDA_TRY(cudaMemcpyAsync(packed.data(), h->out.as<double>() + 2 * P, (P + 1) * 8, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         if (packed[P] == 0 || attempt == 1) break;
-        // the device plan was not sure about some period's limits: redo with the exact host plan
-        h->fallbacks += 1;
-        int rc = enqueue_search(h, s, h->out.p, true);
+        // the device plan was not sure about some periods' limits: settle those on the host and search
+        // again only the ones whose admissible widths really differ
+        const int64_t before = h->repairs + h->fallbacks;
+        int rc = resolve_records(h, s, h->out.p, packed[P]);
         if (rc) return rc;
+        if (h->repairs + h->fallbacks == before) break;  // every flagged limit was right: results stand
     }
     for (size_t p = 0; p < P; ++p) {
         row_out[p] = (int64_t)(uint32_t)(packed[p] & 0xffffffffLL);
@@ -2231,6 +2303,23 @@ int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_se
     return 0;
 }
 int64_t tlsb_plan_fallback_count(const tlsb_handle *h) { return h ? h->fallbacks : 0; }
+int64_t tlsb_plan_repair_count(const tlsb_handle *h) { return h ? h->repairs : 0; }
+
+int tlsb_resolve_plan(tlsb_handle *h, void *cuda_stream, void *records_dev)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_resolve_plan: NULL handle");
+    if (!h->have_lc || !h->have_tp || !h->have_periods || h->P == 0)
+        return fail(TLSB_ERR_STATE, "tlsb_resolve_plan: nothing has been searched");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (!records_dev) records_dev = h->out.p;
+    if (!records_dev) return fail(TLSB_ERR_STATE, "tlsb_resolve_plan: no record buffer");
+    long long count = 0;
+    CUDA_TRY(cudaMemcpyAsync(&count, reinterpret_cast<double *>(records_dev) + 3 * (size_t)h->P, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (count == 0) return 0;
+    return resolve_records(h, s, records_dev, count);
+}
 
 int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,
                      int64_t *smem_bytes)
@@ -2522,22 +2611,43 @@ extern "C" int tlsb_search_batch(tlsb_handle *h, void *cuda_stream, int64_t medi
     int64_t launches = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool exact = attempt == 1 || h->plan_mode == 1;
-        int rc;
+        int rc, n_plans = 0;
         for (size_t c = 0; c < B; ++c) {
             if ((rc = tlsb_select_lightcurve(h, (int64_t)c))) return rc;
             if ((rc = enqueue_search(h, s, rec + c * stride, exact))) return rc;
             launches += h->launches;
+            n_plans += h->launches == 2 ? 1 : 0;
             // the device plan of this launch serves the following curves while span/periods/bank stay the same
             if (!exact && h->plan_mode == 0) h->dev_plan_valid = true;
         }
         // one strided copy of the B status words
         CUDA_TRY(cudaMemcpy2DAsync(status.data(), 8, rec + 3 * P, stride * 8, 8, B, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
-        bool unsure = false;
-        for (size_t c = 0; c < B; ++c) unsure = unsure || status[c] != 0;
-        if (!unsure || exact) break;
-        h->fallbacks += 1;  // some T14 limit was too close to an integer for the device pow(): exact host plan
+        long long flagged = 0;
+        for (size_t c = 0; c < B; ++c) flagged = std::max(flagged, status[c]);
+        if (flagged == 0 || exact) break;
+        // Some T14 limit was too close to an integer for the device pow().  One shared plan: settle the
+        // flagged periods on the host and search again only those whose admissible widths differ, for
+        // every curve.  Several plans in the batch (different spans): the exact host plan, everything again.
         h->dev_plan_valid = false;
+        bool same_span = true;  // every plan of this batch is the same plan
+        for (size_t c = 1; c < B; ++c) same_span = same_span && h->c_span[c] == h->c_span[0];
+        if ((n_plans == 1 || same_span) && status[0] == flagged) {
+            std::vector<int> changed;
+            rc = find_changed_periods(h, s, flagged, &changed);
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                for (size_t c = 0; c < B && !changed.empty(); ++c) {
+                    if ((rc = tlsb_select_lightcurve(h, (int64_t)c))) return rc;
+                    if ((rc = enqueue_search(h, s, rec + c * stride, false, h->unsure.as<int>(), (int)changed.size()))) return rc;
+                    launches += h->launches;
+                }
+                h->repairs += (int64_t)changed.size();
+                CUDA_TRY(cudaStreamSynchronize(s));
+                break;
+            }
+        }
+        h->fallbacks += 1;
     }
     h->dev_plan_valid = false;  // do not carry the shortcut outside the batch
     dim3 grid((unsigned)((P + 255) / 256), (unsigned)B);

@@ -144,16 +144,16 @@ class ShardedSearch(object):
         return unpack_gathered(g, n, self.world)
 
     def _redo_exact(self, fetch):
-        """The device plan flagged a T14 limit too close to an integer: search again with the
-        exact host plan (include/tlsb200.h: tlsb_set_plan_mode)."""
+        """The device plan flagged T14 limits too close to an integer: every rank settles its own
+        flagged periods on the host and re-searches only those that changed
+        (include/tlsb200.h: tlsb_resolve_plan); then the records are gathered again."""
         import torch
 
-        self.searcher.set_plan_mode(1)
-        try:
-            self.step(torch.cuda.current_stream(self.records.device))
-            return fetch()
-        finally:
-            self.searcher.set_plan_mode(0)
+        stream = torch.cuda.current_stream(self.records.device)
+        self.searcher.resolve_plan(stream=stream.cuda_stream, records_ptr=self.records.data_ptr())
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered, self.records)
+        return fetch()
 
     def gather_host(self, local_out):
         """All-gather host-side results (the e2e path: results already copied back)."""

@@ -20,7 +20,7 @@ EXPORTS = (
     "tlsb_last_error", "tlsb_version", "tlsb_device_count", "tlsb_set_plan_mode",
     "tlsb_plan_fallback_count", "tlsb_last_layout",
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
-    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info", "tlsb_last_block",
+    "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info", "tlsb_last_block", "tlsb_resolve_plan", "tlsb_plan_repair_count",
     "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
 )
 
@@ -72,6 +72,9 @@ def lib():
     L.tlsb_last_search_kernel_ms.argtypes = [_c_vp]
     L.tlsb_last_path_resident.restype = ctypes.c_int32
     L.tlsb_last_path_resident.argtypes = [_c_vp]
+    L.tlsb_plan_repair_count.restype = _c_i64
+    L.tlsb_plan_repair_count.argtypes = [_c_vp]
+    L.tlsb_resolve_plan.argtypes = [_c_vp, _c_vp, _c_vp]
     L.tlsb_plan_fallback_count.restype = _c_i64
     L.tlsb_plan_fallback_count.argtypes = [_c_vp]
     L.tlsb_set_plan_mode.argtypes = [_c_vp, ctypes.c_int32]
@@ -306,8 +309,16 @@ class Searcher(object):
     def t0_fit_ms(self):
         return float(lib().tlsb_last_t0_fit_ms(self._h))
 
+    def resolve_plan(self, stream=None, records_ptr=None):
+        """``tlsb_resolve_plan``: settle the periods the device plan flagged, re-search those that changed."""
+        _check(lib().tlsb_resolve_plan(self._h, _c_vp(stream or 0), _c_vp(records_ptr or 0)), "tlsb_resolve_plan")
+
+    @property
+    def plan_repairs(self):
+        return int(lib().tlsb_plan_repair_count(self._h))
+
     def set_plan_mode(self, mode):
-        """0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)."""
+        """0 device plan, 1 exact host plan, 2 device plan flagging every period, 3 = 2 + wrong ranges (tests)."""
         _check(lib().tlsb_set_plan_mode(self._h, int(mode)), "tlsb_set_plan_mode")
 
     PATHS = {0: "auto", 1: "resident", 2: "tiled", 3: "streaming"}
