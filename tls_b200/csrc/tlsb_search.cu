@@ -1762,7 +1762,9 @@ Layout choose_layout(const tlsb_handle *h)
         const int tries[2][3] = {{256, 2, 3072}, {512, 1, 4096}};  // threads, CTAs per SM, queue entries
         for (const auto &t : tries) {
             if (forced > 0 && forced != t[0]) continue;
-            const size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);
+            size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);
+            if (const char *cap = std::getenv("TLSB_SMEM_KB"))  // experiments: leave part of the SM's 256 KB to L1
+                per_cta = std::min(per_cta, (size_t)std::atoi(cap) * 1024 / (size_t)t[1]);
             const size_t fixed = (size_t)t[2] * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 + (size_t)(kMaxSegments + 2) * 4;
             if (per_cta <= fixed) continue;
             long long C = (long long)(((per_cta - fixed) / (8 * (size_t)narr)) & ~(size_t)1);
@@ -1775,8 +1777,9 @@ Layout choose_layout(const tlsb_handle *h)
                 TP = C - need5;
             }
             if (h->chunk_cap > 0 && TP < 2) continue;
-            // two CTAs per SM only when a chunk still starts a few thousand offsets; one big CTA otherwise
-            if (h->chunk_cap <= 0 && TP < (t[1] == 2 && forced < 0 ? 2048 : 256)) continue;
+            // two CTAs per SM only when most of a chunk is start offsets (halo below ~40 %); one big CTA otherwise
+            if (h->chunk_cap <= 0 && t[1] == 2 && forced < 0 && (TP < 2048 || 5 * TP < 3 * C)) continue;
+            if (h->chunk_cap <= 0 && TP < 256) continue;
             best.resident = false;
             best.tiled = true;
             best.kb = kb;
