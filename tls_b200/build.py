@@ -32,11 +32,13 @@ def is_stale():
     return any(os.path.getmtime(p) > built for p in SRC + HEADERS + [os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False):
-    """Compile if the library is missing or older than its sources; returns the path."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile if the library is missing or older than its sources; returns the path.
+    `defines` / `out` build an experimental variant next to the product library (scripts/gpu_variants.sh)."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRC
+    out = out or LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-o", out] + SRC
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports a gcc wrapper that nvcc must not pick up
     env.pop("CXX", None)
@@ -45,7 +47,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

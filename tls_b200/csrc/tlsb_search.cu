@@ -58,6 +58,7 @@ constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per
 __host__ __device__ constexpr int tile_size(int kb) { return 32 * kb * kSub; }  // candidates one warp gates at a time
 constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
+constexpr int kResScanItems = 19;     // ... of the resident kernel: one tile covers 19 * 256 = 4864 samples (cfg-1: one tile, 3 barriers)
 constexpr int kSegPerThread = 16;   // keys of one segment a thread keeps in registers (S <= 16 * threads)
 constexpr int kMaxSegments = 64;     // phase segments of the on-chip sort of the tiled path
 constexpr int kPlanThreads = 1024;
@@ -276,7 +277,7 @@ __device__ __forceinline__ int bucket_of(double phase, int NB)
 }
 
 // In-place block-wide inclusive scan of data[0..n) (all threads must call).
-template <int kT, typename T>
+template <int kT, typename T, int kScanItems = ::kScanItems>
 __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] shared */)
 {
     constexpr int kW = kT / 32;
@@ -321,6 +322,65 @@ __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] sh
             if (first + k < n) data[first + k] = v[k] + offset;
         carry += warp_tot[kW];
         __syncthreads();
+    }
+}
+
+// Second half of the sort: skey/sid hold the keys grouped by bucket (any order inside a bucket); rank every key
+// inside its bucket by (phase, index) = numpy's stable mergesort order, and gather src1 (src2) to the sorted
+// slots of dst1 (dst2).  Bucket b spans [H[b-1], H[b]) with kShift = 0 (H[-1] = 0), [H[b], H[b+1]) with
+// kShift = 1.  Ends WITHOUT a barrier.
+template <int kT, typename idx_t, bool kTwo, int kU, int kShift>
+__device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const double *skey, const idx_t *sid,
+                                            const double *__restrict__ src1, const double *__restrict__ src2,
+                                            double *dst1, double *dst2)
+{
+    const int tid = threadIdx.x;
+    for (int q0 = tid; q0 < N; q0 += kT * kU) {
+        double key[kU], v1[kU], v2[kU];
+        int id[kU], lo[kU], hi[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int q = q0 + u * kT;
+            key[u] = q < N ? skey[q] : 0.0;
+            id[u] = q < N ? (int)sid[q] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {  // gathers issued early: they overlap the ranking loops
+            v1[u] = __ldcs(src1 + id[u]);
+            v2[u] = kTwo ? __ldcs(src2 + id[u]) : 0.0;
+            const int bk = bucket_of(key[u], NB);
+            lo[u] = (bk + kShift) ? H[bk - 1 + kShift] : 0;
+            hi[u] = H[bk + kShift];
+        }
+        // the kU ranking loops run in lockstep so that their loads are in flight together
+        int rank[kU], longest = 0;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            rank[u] = lo[u];
+            if (q0 + u * kT >= N) hi[u] = lo[u];
+            longest = max(longest, hi[u] - lo[u]);
+        }
+        for (int s = 0; s < longest; ++s) {
+            double ks[kU];
+            int is[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int at = lo[u] + s < hi[u] ? lo[u] + s : lo[u];  // a harmless re-read once this chain is done
+                ks[u] = skey[at];
+                is[u] = (int)sid[at];
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (lo[u] + s < hi[u])
+                    rank[u] += (ks[u] < key[u]) || (ks[u] == key[u] && is[u] < id[u]);  // (phase, index): the stable order
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (q0 + u * kT < N) {
+                dst1[rank[u]] = v1[u];
+                if (kTwo) dst2[rank[u]] = v2[u];
+            }
+        }
     }
 }
 
@@ -372,53 +432,7 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
         }
     }
     __syncthreads();  // now H[b] = end of bucket b; the unsorted phases are dead
-    for (int q0 = tid; q0 < N; q0 += kT * kU) {
-        double key[kU], v1[kU], v2[kU];
-        int id[kU], lo[kU], hi[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            const int q = q0 + u * kT;
-            key[u] = q < N ? skey[q] : 0.0;
-            id[u] = q < N ? (int)sid[q] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {  // gathers issued early: they overlap the ranking loops
-            v1[u] = __ldcs(src1 + id[u]);
-            v2[u] = kTwo ? __ldcs(src2 + id[u]) : 0.0;
-            const int bk = bucket_of(key[u], NB);
-            lo[u] = bk ? H[bk - 1] : 0;
-            hi[u] = H[bk];
-        }
-        // the kU ranking loops run in lockstep so that their loads are in flight together
-        int rank[kU], longest = 0;
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            rank[u] = lo[u];
-            if (q0 + u * kT >= N) hi[u] = lo[u];
-            longest = max(longest, hi[u] - lo[u]);
-        }
-        for (int s = 0; s < longest; ++s) {
-            double ks[kU];
-            int is[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int at = lo[u] + s < hi[u] ? lo[u] + s : lo[u];  // a harmless re-read once this chain is done
-                ks[u] = skey[at];
-                is[u] = (int)sid[at];
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u)
-                if (lo[u] + s < hi[u])
-                    rank[u] += (ks[u] < key[u]) || (ks[u] == key[u] && is[u] < id[u]);  // (phase, index): the stable order
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-            if (q0 + u * kT < N) {
-                dst1[rank[u]] = v1[u];
-                if (kTwo) dst2[rank[u]] = v2[u];
-            }
-        }
-    }
+    rank_gather<kT, idx_t, kTwo, kU, 0>(N, NB, H, skey, sid, src1, src2, dst1, dst2);
 }
 
 // After the sort: cs1[0..N) holds the sorted d = 1 - y (cs1 = cs + 1).  Wrap the first M samples to
@@ -426,7 +440,7 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
 // (helpers.py:70-73), writes wd = w * d and returns this thread's share of T = sum_{k<N} w d^2.
 // With begin > 0 the pass resumes at position `begin` with the running sum `carry` (the samples
 // there already hold their d; nothing is wrapped).
-template <int kT, bool kUniformW>
+template <int kT, bool kUniformW, int kScanItems = ::kScanItems>
 __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, double *wd, double w0, int N, int NM,
                                                    int NMP, double *warp_tot /* [kT/32 + 1] shared */,
                                                    int begin = 0, double carry = 0.0)
@@ -602,6 +616,39 @@ __device__ __noinline__ double untouched_tail(const double *w, const double *wd,
     return rest;
 }
 
+
+// After the tap loop: chi2 of the block's surviving candidates (bit `rr` of mask), the block's own minimum first
+// (same width, ascending offsets: strict '<' keeps the earliest), then ONE lexicographic comparison against the
+// lane's running best.  The cumulative sums of all kBlock candidates are loaded up front, unconditionally (the
+// arrays have slack behind them), so that the loads are in flight together instead of one per taken branch.
+template <int kBlock, bool kUniformW>
+__device__ __forceinline__ void block_min(const WidthRec &wr, const double *cs, const double *w, const double *wd,
+                                          double w0, double T, int i0, int mask, int u, const double (&A)[kBlock],
+                                          const double (&B)[kBlock], Best &best)
+{
+    double lo[kBlock], hi[kBlock];
+    const double *__restrict__ p = cs + i0;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        lo[rr] = p[rr * wr.X];
+        hi[rr] = p[rr * wr.X + wr.W];
+    }
+    double blk_chi = INFINITY, blk_D = 0.0;
+    int blk_i = -1;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        const int i = i0 + rr * wr.X;
+        const double mean = (hi[rr] - lo[rr]) * wr.invW;
+        const double D = mean * wr.os;
+        const double Aq = kUniformW ? w0 * wr.sq2 : A[rr];
+        double chi = T + D * (D * Aq - 2.0 * B[rr]);
+        const bool on = (mask >> rr) & 1;
+        if (wr.L < wr.W && on) chi -= untouched_tail<kUniformW>(w, wd, w0, i + wr.L, i + wr.W);
+        if (on && chi < blk_chi) { blk_chi = chi; blk_D = D; blk_i = i; }
+    }
+    if (blk_i >= 0 && better(blk_chi, u, blk_i, best)) { best.chi2 = blk_chi; best.D = blk_D; best.u = u; best.i = blk_i; }
+}
+
 template <int kT, bool kResident, bool kUniformW, int kBlock>
 __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
 {
@@ -686,7 +733,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                                                        reinterpret_cast<int *>(red_d));
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
-        double tpart = wrap_weight_scan<kT, kUniformW>(cs + 1, w, wd, a.w0, N, NM, NMP, red_d);
+        double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems)>(cs + 1, w, wd, a.w0, N, NM,
+                                                                                                 NMP, red_d);
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
         if (lane == 0) red_d[kW + 1 + wid] = tpart;
@@ -790,23 +838,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                         tap_block<kBlock, true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
                     else
                         tap_block<kBlock, false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
-                    // the block's own minimum first (same width, ascending offsets: strict '<' keeps the
-                    // earliest), then ONE lexicographic comparison against the lane's running best
-                    double blk_chi = INFINITY, blk_D = 0.0;
-                    int blk_i = -1;
-#pragma unroll
-                    for (int rr = 0; rr < kBlock; ++rr) {
-                        if (mask & (1 << rr)) {
-                            const int i = i0 + rr * wr.X;
-                            const double mean = (cs[i + wr.W] - cs[i]) * wr.invW;
-                            const double D = mean * wr.os;
-                            const double Aq = kUniformW ? a.w0 * wr.sq2 : A[rr];
-                            double chi = T + D * (D * Aq - 2.0 * B[rr]);
-                            if (wr.L < wr.W) chi -= untouched_tail<kUniformW>(w, wd, a.w0, i + wr.L, i + wr.W);
-                            if (chi < blk_chi) { blk_chi = chi; blk_D = D; blk_i = i; }
-                        }
-                    }
-                    if (blk_i >= 0 && better(blk_chi, u, blk_i, best)) { best.chi2 = blk_chi; best.D = blk_D; best.u = u; best.i = blk_i; }
+                    block_min<kBlock, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
                 }
             }
             if (!more) break;
@@ -1324,21 +1356,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                             tap_block<kBlock, true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
                         else
                             tap_block<kBlock, false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
-                        double blk_chi = INFINITY, blk_D = 0.0;
-                        int blk_i = -1;
-#pragma unroll
-                        for (int rr = 0; rr < kBlock; ++rr) {
-                            if (mask & (1 << rr)) {
-                                const int i = i0 + rr * wr.X;
-                                const double mean = (csb[i + wr.W] - csb[i]) * wr.invW;
-                                const double D = mean * wr.os;
-                                const double Aq = kUniformW ? a.w0 * wr.sq2 : A[rr];
-                                double chi = T + D * (D * Aq - 2.0 * B[rr]);
-                                if (wr.L < wr.W) chi -= untouched_tail<kUniformW>(wb, wdb, a.w0, i + wr.L, i + wr.W);
-                                if (chi < blk_chi) { blk_chi = chi; blk_D = D; blk_i = i; }
-                            }
-                        }
-                        if (blk_i >= 0 && better(blk_chi, u, blk_i, best)) { best.chi2 = blk_chi; best.D = blk_D; best.u = u; best.i = blk_i; }
+                        block_min<kBlock, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
                     }
                 }
                 if (!more) break;

@@ -55,8 +55,8 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if _build.is_stale():
+    path = os.environ.get("TLSB200_LIB") or _build.LIB  # TLSB200_LIB: an experimental build (scripts/gpu_variants.sh)
+    if path == _build.LIB and _build.is_stale():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this machine: use the shipped .so if there is one
