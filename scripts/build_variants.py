@@ -18,6 +18,6 @@ for spec in sys.argv[1:]:
         print(name, "FAILED\n", proc.stderr[-2000:]); continue
     lines = proc.stderr.splitlines()
     for i, l in enumerate(lines):
-        if "Compiling entry function" in l and re.search(r"search_kernelILi256ELb1ELb1ELi7|search_tiled_kernelILi512ELb1ELi5|search_kernelILi256ELb1ELb0ELi5", l):
+        if "Compiling entry function" in l and re.search(r"search_kernelILi256ELb1ELb1ELi[79]|search_tiled_kernelILi512ELb1ELi[579]|search_kernelILi256ELb1ELb0ELi5", l):
             kn = re.search(r"tlsb_\w+?kernelI\w+?EEE", l).group(0)
             print("%-10s %-46s %s | %s" % (name, kn, lines[i + 2].strip(), lines[i + 3].strip()[:60]))

@@ -60,6 +60,6 @@ VALID_PARAMETERS = (
 ).split()
 
 # keywords that only exist in this implementation (device selection)
-EXTRA_PARAMETERS = ("device", "devices")
+EXTRA_PARAMETERS = ("device", "devices", "dist")
 
 resources_dir = path.join(path.dirname(__file__), "data")

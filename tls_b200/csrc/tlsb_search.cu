@@ -617,27 +617,58 @@ __device__ __noinline__ double untouched_tail(const double *w, const double *wd,
 }
 
 
+// B1 for one block: bit rr of the result is set when candidate c0 + rr of a width passes the gate
+// mean_i > transit_depth_min (core.py:58), mean from two cumulative-sum reads (helpers.py:70-73).
+// kUnit: stride 1 (most widths) - the 2 * kBlock loads get immediate offsets.
+template <int kBlock, bool kUnit>
+__device__ __forceinline__ int gate_block(const double *cs, int c0, int c_end, int W, int X, double invW,
+                                          double depth_min)
+{
+    const int Xs = kUnit ? 1 : X;
+    int mask = 0;
+    if (c0 + kBlock <= c_end) {  // straight line: all loads in flight, then the compares
+        const double *__restrict__ lo = cs + (size_t)c0 * Xs;
+        const double *__restrict__ hi = lo + W;
+        double mean[kBlock];
+#pragma unroll
+        for (int rr = 0; rr < kBlock; ++rr) mean[rr] = (hi[rr * Xs] - lo[rr * Xs]) * invW;
+#pragma unroll
+        for (int rr = 0; rr < kBlock; ++rr) mask |= (mean[rr] > depth_min ? 1 : 0) << rr;
+    } else {  // the last, partial block of this width (or nothing)
+        for (int rr = 0; rr < kBlock; ++rr) {
+            const int c = c0 + rr;
+            if (c < c_end) {
+                const int i = c * Xs;
+                if ((cs[i + W] - cs[i]) * invW > depth_min) mask |= 1 << rr;
+            }
+        }
+    }
+    return mask;
+}
+
 // After the tap loop: chi2 of the block's surviving candidates (bit `rr` of mask), the block's own minimum first
 // (same width, ascending offsets: strict '<' keeps the earliest), then ONE lexicographic comparison against the
 // lane's running best.  The cumulative sums of all kBlock candidates are loaded up front, unconditionally (the
 // arrays have slack behind them), so that the loads are in flight together instead of one per taken branch.
-template <int kBlock, bool kUniformW>
+template <int kBlock, bool kUnit, bool kUniformW>
 __device__ __forceinline__ void block_min(const WidthRec &wr, const double *cs, const double *w, const double *wd,
                                           double w0, double T, int i0, int mask, int u, const double (&A)[kBlock],
                                           const double (&B)[kBlock], Best &best)
 {
     double lo[kBlock], hi[kBlock];
+    const int X = kUnit ? 1 : wr.X;
     const double *__restrict__ p = cs + i0;
+    const double *__restrict__ ph = p + wr.W;
 #pragma unroll
     for (int rr = 0; rr < kBlock; ++rr) {
-        lo[rr] = p[rr * wr.X];
-        hi[rr] = p[rr * wr.X + wr.W];
+        lo[rr] = p[rr * X];
+        hi[rr] = ph[rr * X];
     }
     double blk_chi = INFINITY, blk_D = 0.0;
     int blk_i = -1;
 #pragma unroll
     for (int rr = 0; rr < kBlock; ++rr) {
-        const int i = i0 + rr * wr.X;
+        const int i = i0 + rr * X;
         const double mean = (hi[rr] - lo[rr]) * wr.invW;
         const double D = mean * wr.os;
         const double Aq = kUniformW ? w0 * wr.sq2 : A[rr];
@@ -780,29 +811,18 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                 int masks[kSub];
                 unsigned votes[kSub];
                 int total = 0;
+                if (X == 1) {
+#pragma unroll
+                    for (int sb = 0; sb < kSub; ++sb)
+                        masks[sb] = gate_block<kBlock, true>(cs, c_tile + sb * 32 * kBlock, ncand, W, 1, invW, depth_min);
+                } else {
+#pragma unroll
+                    for (int sb = 0; sb < kSub; ++sb)
+                        masks[sb] = gate_block<kBlock, false>(cs, c_tile + sb * 32 * kBlock, ncand, W, X, invW, depth_min);
+                }
 #pragma unroll
                 for (int sb = 0; sb < kSub; ++sb) {
-                    const int c0 = c_tile + sb * 32 * kBlock;
-                    int mask = 0;
-                    if (c0 + kBlock <= ncand) {  // straight line: ten loads in flight, then the compares
-                        const double *__restrict__ lo = cs + (size_t)c0 * X;
-                        const double *__restrict__ hi = lo + W;
-                        double mean[kBlock];
-#pragma unroll
-                        for (int rr = 0; rr < kBlock; ++rr) mean[rr] = (hi[rr * X] - lo[rr * X]) * invW;
-#pragma unroll
-                        for (int rr = 0; rr < kBlock; ++rr) mask |= (mean[rr] > depth_min ? 1 : 0) << rr;  // core.py:58
-                    } else {  // the last, partial block of this width (or nothing)
-                        for (int rr = 0; rr < kBlock; ++rr) {
-                            const int c = c0 + rr;
-                            if (c < ncand) {
-                                const int i = c * X;
-                                if ((cs[i + W] - cs[i]) * invW > depth_min) mask |= 1 << rr;
-                            }
-                        }
-                    }
-                    masks[sb] = mask;
-                    votes[sb] = __ballot_sync(kFull, mask != 0);
+                    votes[sb] = __ballot_sync(kFull, masks[sb] != 0);
                     total += __popc(votes[sb]);
                 }
                 if (total) {
@@ -834,11 +854,13 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
                     const WidthRec wr = rec[u];
                     const int i0 = e.x * wr.X;
                     double A[kBlock], B[kBlock];
-                    if (wr.X == 1)
+                    if (wr.X == 1) {
                         tap_block<kBlock, true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
-                    else
+                        block_min<kBlock, true, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
+                    } else {
                         tap_block<kBlock, false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
-                    block_min<kBlock, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
+                        block_min<kBlock, false, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
+                    }
                 }
             }
             if (!more) break;
@@ -1298,29 +1320,18 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                     int masks[kSub];
                     unsigned votes[kSub];
                     int total = 0;
+                    if (X == 1) {
+#pragma unroll
+                        for (int sb = 0; sb < kSub; ++sb)
+                            masks[sb] = gate_block<kBlock, true>(csb, c_tile + sb * 32 * kBlock, c_end, W, 1, invW, depth_min);
+                    } else {
+#pragma unroll
+                        for (int sb = 0; sb < kSub; ++sb)
+                            masks[sb] = gate_block<kBlock, false>(csb, c_tile + sb * 32 * kBlock, c_end, W, X, invW, depth_min);
+                    }
 #pragma unroll
                     for (int sb = 0; sb < kSub; ++sb) {
-                        const int c0 = c_tile + sb * 32 * kBlock;
-                        int mask = 0;
-                        if (c0 + kBlock <= c_end) {
-                            const double *__restrict__ lo = csb + (size_t)c0 * X;
-                            const double *__restrict__ hi = lo + W;
-                            double mean[kBlock];
-#pragma unroll
-                            for (int rr = 0; rr < kBlock; ++rr) mean[rr] = (hi[rr * X] - lo[rr * X]) * invW;
-#pragma unroll
-                            for (int rr = 0; rr < kBlock; ++rr) mask |= (mean[rr] > depth_min ? 1 : 0) << rr;  // core.py:58
-                        } else {
-                            for (int rr = 0; rr < kBlock; ++rr) {
-                                const int c = c0 + rr;
-                                if (c < c_end) {
-                                    const int i = c * X;
-                                    if ((csb[i + W] - csb[i]) * invW > depth_min) mask |= 1 << rr;
-                                }
-                            }
-                        }
-                        masks[sb] = mask;
-                        votes[sb] = __ballot_sync(kFull, mask != 0);
+                        votes[sb] = __ballot_sync(kFull, masks[sb] != 0);
                         total += __popc(votes[sb]);
                     }
                     if (total) {
@@ -1352,11 +1363,13 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                         const WidthRec wr = rec[u];
                         const int i0 = e.x * wr.X;
                         double A[kBlock], B[kBlock];
-                        if (wr.X == 1)
+                        if (wr.X == 1) {
                             tap_block<kBlock, true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
-                        else
+                            block_min<kBlock, true, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
+                        } else {
                             tap_block<kBlock, false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
-                        block_min<kBlock, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
+                            block_min<kBlock, false, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
+                        }
                     }
                 }
                 if (!more) break;

@@ -80,10 +80,19 @@ class transitleastsquares(object):
         return SearchInputs(self.t, self.y, self.dy, periods, lc_arr, overview, durations, params)
 
     # ------------------------------------------------------------------ the hot path
-    def _search(self, inputs, devices):
-        """main.py:121-196 replaced by one call into the CUDA library."""
+    def _search(self, inputs, devices, dist=None):
+        """main.py:121-196 replaced by one call into the CUDA library.  With ``dist`` (an initialised
+        ``torch.distributed`` module, one process per GPU) the periods are dealt to the ranks and
+        the per-period records all-gathered once (tls_b200/distributed.py); every rank gets the
+        whole result and carries on with identical post-processing."""
         from . import native
 
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            from .distributed import search_periods_distributed
+
+            device = None if devices is None else int(np.atleast_1d(devices)[0])
+            return search_periods_distributed(inputs.t, inputs.y, inputs.dy, inputs.periods, inputs.templates,
+                                              inputs.params, dist, device=device)
         return native.search_periods(
             inputs.t, inputs.y, inputs.dy, inputs.periods, inputs.templates, inputs.params,
             devices=devices,
@@ -119,7 +128,12 @@ class transitleastsquares(object):
             )
             print("Using the B200 search kernels (use_threads=%d is accepted and ignored)" % self.use_threads)
 
-        chi2_by_input, rows_by_input, depths_by_input = self._search(inputs, devices)
+        dist = kwargs.get("dist", None)
+        if dist is not None and devices is None:
+            import torch
+
+            devices = torch.cuda.current_device()  # one process per GPU: this rank's device
+        chi2_by_input, rows_by_input, depths_by_input = self._search(inputs, devices, dist)
         self._t0_device = None if devices is None else int(np.atleast_1d(devices)[0])
 
         # main.py:190-196: ascending period order
