@@ -154,7 +154,7 @@ class _OracleBacked(transitleastsquares):
 
         return oracle.final_T0_fit_numpy(signal, depth, self.t, self.y, self.dy, period, self.T0_fit_margin)[0]
 
-    def _search(self, inputs, devices):
+    def _search(self, inputs, devices, dist=None):
         from oracle import oracle
 
         return oracle.search_periods_c(inputs.t, inputs.y, inputs.dy, inputs.periods, inputs.templates, inputs.params)
