@@ -223,6 +223,9 @@ const char *tlsb_last_error(void);
 const char *tlsb_version(void);
 int32_t tlsb_device_count(void);
 
+/* The calling thread's current CUDA device (what a negative `device` argument resolves to), or -1. */
+int32_t tlsb_current_device(void);
+
 #ifdef __cplusplus
 }
 #endif

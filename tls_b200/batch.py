@@ -103,7 +103,7 @@ def batch_power(t, ys, dys=None, device=None, dist=None, return_power=False, **k
     summary = np.full((B, len(SUMMARY_FIELDS)), np.nan)
     power = np.zeros((B, len(inputs.periods))) if return_power else None
     if len(mine):
-        s = native.Searcher(device=-1 if device is None else device)
+        s = native.Searcher.acquire(device=-1 if device is None else device)
         try:
             s.set_templates(inputs.templates, inputs.params)
             s.set_periods(inputs.periods)
@@ -130,7 +130,7 @@ def batch_power(t, ys, dys=None, device=None, dist=None, return_power=False, **k
                         power[c] = out["power"][k]
                 summary[c] = [row[f] for f in SUMMARY_FIELDS]
         finally:
-            s.close()
+            s.release()
     if world > 1:
         summary = _all_gather_rows(summary, mine, B, dist, device)
         if return_power:

@@ -2040,6 +2040,16 @@ int32_t tlsb_device_count(void)
     return n;
 }
 
+int32_t tlsb_current_device(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return d;
+}
+
 int tlsb_create(tlsb_handle **out, int32_t device)
 {
     if (!out) return fail(TLSB_ERR_ARG, "tlsb_create: out is NULL");

@@ -98,7 +98,7 @@ class ShardedSearch(object):
         self.local_periods = np.ascontiguousarray(self.all_periods[self.index])
         self.n_local = len(self.local_periods)
         self.capacity = shard_capacity(len(self.all_periods), world)
-        self.searcher = native.Searcher(device=device)
+        self.searcher = native.Searcher.acquire(device=device)
         self.searcher.set_inputs(t, y, dy, templates, params)
         self.searcher.set_periods(self.local_periods)
         self.records = torch.zeros(record_words(self.capacity), dtype=torch.int64, device="cuda:%d" % device)
@@ -166,7 +166,7 @@ class ShardedSearch(object):
         return unpack_gathered(out.cpu().numpy(), len(self.all_periods), self.world)
 
     def close(self):
-        self.searcher.close()
+        self.searcher.release()
 
 
 def search_periods_distributed(t, y, dy, periods, templates, params, dist, device=None):

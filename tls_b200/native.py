@@ -22,6 +22,7 @@ EXPORTS = (
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
     "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info", "tlsb_last_block", "tlsb_resolve_plan", "tlsb_plan_repair_count",
     "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
+    "tlsb_current_device",
 )
 
 _c_i64 = ctypes.c_int64
@@ -66,6 +67,7 @@ def lib():
     L.tlsb_last_error.restype = ctypes.c_char_p
     L.tlsb_version.restype = ctypes.c_char_p
     L.tlsb_device_count.restype = ctypes.c_int32
+    L.tlsb_current_device.restype = ctypes.c_int32
     L.tlsb_last_launch_count.restype = _c_i64
     L.tlsb_last_launch_count.argtypes = [_c_vp]
     L.tlsb_last_search_kernel_ms.restype = ctypes.c_double
@@ -228,6 +230,43 @@ class Searcher(object):
             self.close()
         except Exception:
             pass
+
+    # Creating and (above all) destroying a handle costs tens to hundreds of milliseconds of
+    # cudaMalloc / cudaFree - more than a whole cfg-1 search - so the drivers that open a handle
+    # per call (batch_power, ShardedSearch) borrow one from a per-device pool instead.  Every
+    # setter replaces the state it owns, so a recycled handle carries nothing over.
+    _POOL = {}
+
+    @classmethod
+    def acquire(cls, device=-1):
+        device = int(device)
+        if device < 0:
+            device = int(lib().tlsb_current_device())
+        idle = cls._POOL.get(device)
+        if idle:
+            s = idle.pop()
+            s.set_path("auto")
+            s.set_plan_mode(0)
+            return s
+        s = cls(device=device)
+        s._pool_key = device
+        return s
+
+    def release(self):
+        """Back to the pool (or destroyed when it was not acquired from it)."""
+        key = getattr(self, "_pool_key", None)
+        if key is None or not self._h:
+            self.close()
+            return
+        self._keep = None
+        Searcher._POOL.setdefault(key, []).append(self)
+
+    @classmethod
+    def drain_pool(cls):
+        for idle in cls._POOL.values():
+            for s in idle:
+                s.close()
+        cls._POOL.clear()
 
     def set_inputs(self, t, y, dy, templates, params):
         pk = _Packed(t, y, dy, templates, params)
