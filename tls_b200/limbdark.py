@@ -26,6 +26,8 @@ Host-side, once per search (~10 ms); not part of the GPU hot path.
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 __all__ = ["TransitParams", "TransitModel", "separation", "occulted_flux", "LAWS"]
@@ -91,8 +93,12 @@ LAWS = (
 )
 
 
+@functools.lru_cache(maxsize=16)
 def _gl(n):
+    """Gauss-Legendre nodes and weights (an eigenvalue problem: computed once per order)."""
     x, w = np.polynomial.legendre.leggauss(n)
+    x.setflags(write=False)
+    w.setflags(write=False)
     return x, w
 
 

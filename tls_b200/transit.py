@@ -28,9 +28,26 @@ def _lerp_resample(x_new, x, y):
     return (1 - theta) * y[idx] + theta * y[idx + 1]
 
 
+_REFERENCE_CACHE = {}
+
+
 def reference_transit(samples, per, rp, a, inc, ecc, w, u, limb_dark):
     """In-transit part of a model transit, resampled to ``samples`` points and
-    rescaled to 0 at mid-transit and 1 at the edges (transit.py:8-42)."""
+    rescaled to 0 at mid-transit and 1 at the edges (transit.py:8-42).  The reference rebuilds
+    it on every call (three times per ``power()``); here the few most recent shapes are kept."""
+    key = (int(samples), float(per), float(rp), float(a), float(inc), float(ecc), float(w),
+           tuple(float(x) for x in np.atleast_1d(u)), str(limb_dark))
+    hit = _REFERENCE_CACHE.get(key)
+    if hit is not None:
+        return hit.copy()
+    out = _reference_transit(samples, per, rp, a, inc, ecc, w, u, limb_dark)
+    if len(_REFERENCE_CACHE) >= 32:
+        _REFERENCE_CACHE.pop(next(iter(_REFERENCE_CACHE)))
+    _REFERENCE_CACHE[key] = out
+    return out.copy()
+
+
+def _reference_transit(samples, per, rp, a, inc, ecc, w, u, limb_dark):
     t = np.linspace(-0.5, 0.5, C.SUPERSAMPLE_SIZE)
     p = limbdark.TransitParams()
     p.t0, p.per, p.rp, p.a, p.inc, p.ecc, p.w = 0, per, rp, a, inc, ecc, w
