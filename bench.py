@@ -11,7 +11,9 @@ trial period of the grid) over one synthetic light curve:
   N > 1]); L2 is flushed between steps, outside the event brackets.
 * ``e2e``    — the same search through the reference-facing C-ABI call
   ``tlsb_search_periods`` with HOST buffers (pinned), host<->device copies inside the
-  timed region, wall clock bracketed by device synchronisation.
+  timed region, wall clock bracketed by device synchronisation.  With N > 1 the host buffers
+  go up through the handle setters of the same C ABI every step, the records are
+  all-gathered on the device and every rank copies the whole result back once.
 * multi-GPU  — weak scaling: every rank searches ``P`` periods of the same light curve; the
   job's grid is the reference's period grid oversampled N x (``oversampling_factor = 3 N``),
   dealt to the ranks round-robin (period k -> rank k mod N), one all-gather at the end of
@@ -338,14 +340,17 @@ def run_b200(args):
         tt = torch.from_numpy(np.ascontiguousarray(arr, np.float64).copy()).pin_memory()
         pin[name] = (tt, tt.numpy())
     h2d = 8 * (3 * len(inp.y) + P_rank) + sum(int(np.asarray(v).nbytes) for v in inp.templates.values())
-    d2h = 24 * P_rank
+    d2h = 24 * P_rank if dist is None else 8 * world * (3 * job.capacity + 1)
 
     def e2e_step():
-        out = native.search_periods(pin["t"][1], pin["y"][1], pin["dy"][1], pin["periods"][1], inp.templates,
-                                    inp.params, devices=[local])
-        if dist is not None:
-            job.gather_host(out)
-        return out
+        if dist is None:
+            return native.search_periods(pin["t"][1], pin["y"][1], pin["dy"][1], pin["periods"][1], inp.templates,
+                                         inp.params, devices=[local])
+        # N > 1: the same host buffers go up through the handle API (tlsb_set_lightcurve / _templates /
+        # _periods), the records are all-gathered on the device and come back in ONE copy
+        job.reload(pin["t"][1], pin["y"][1], pin["dy"][1], inp.templates, inp.params)
+        job.step(stream)
+        return job.results()
 
     for _ in range(max(3, args.warmup)):
         e2e_step()
@@ -410,7 +415,9 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, inp, n_gpus, P_rank, P_total, oversampling),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "call": "tlsb_search_periods (C ABI, host buffers)"},
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "call": "tlsb_search_periods (C ABI, host buffers)" if dist is None else
+                            "ShardedSearch.reload/step/results: C ABI setters with host buffers, device all-gather, one copy back"},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "parity": parity,
         }

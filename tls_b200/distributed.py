@@ -54,14 +54,13 @@ def unpack_gathered(gathered, n_periods, world):
     depth = np.empty(n_periods, np.float64)
     row = np.empty(n_periods, np.int64)
     t0 = np.empty(n_periods, np.int64)
-    for r in range(world):
-        idx = shard_indices(n_periods, r, world)
-        n = len(idx)
-        chi2[idx] = g[r, 0:n].view(np.float64)
-        depth[idx] = g[r, n:2 * n].view(np.float64)
+    for r in range(world):  # rank r holds periods r, r + world, ...: strided slices, no index arrays
+        n = len(range(r, n_periods, world))
+        chi2[r::world] = g[r, 0:n].view(np.float64)
+        depth[r::world] = g[r, n:2 * n].view(np.float64)
         packed = g[r, 2 * n:3 * n]
-        row[idx] = packed & 0xFFFFFFFF
-        t0[idx] = packed >> 32
+        row[r::world] = packed & 0xFFFFFFFF
+        t0[r::world] = packed >> 32
     return chi2, row, depth, t0
 
 
@@ -102,9 +101,10 @@ class ShardedSearch(object):
         self.searcher.set_inputs(t, y, dy, templates, params)
         self.searcher.set_periods(self.local_periods)
         self.records = torch.zeros(record_words(self.capacity), dtype=torch.int64, device="cuda:%d" % device)
-        self.gathered = None
+        self.gathered = self._gathered_host = None
         if world > 1:
             self.gathered = torch.empty(world * self.records.numel(), dtype=torch.int64, device=self.records.device)
+            self._gathered_host = torch.empty(self.gathered.numel(), dtype=torch.int64).pin_memory()
 
     def step(self, stream=None):
         ptr = stream.cuda_stream if stream is not None else 0
@@ -138,10 +138,24 @@ class ShardedSearch(object):
         if self.world == 1:
             return self.local_results()
         n = len(self.all_periods)
-        g = self.gathered.cpu().numpy()
+        g = self._fetch_gathered()
         if gathered_status(g, n, self.world) != 0:  # every rank sees the same flags: a collective decision
-            g = self._redo_exact(lambda: self.gathered.cpu().numpy())
+            g = self._redo_exact(self._fetch_gathered)
         return unpack_gathered(g, n, self.world)
+
+    def _fetch_gathered(self):
+        """One device-to-host copy of every rank's records into pinned memory."""
+        import torch
+
+        self._gathered_host.copy_(self.gathered, non_blocking=True)
+        torch.cuda.current_stream(self.records.device).synchronize()
+        return self._gathered_host.numpy()
+
+    def reload(self, t, y, dy, templates, params):
+        """New inputs from HOST buffers for the next ``step`` (the end-to-end path: light curve,
+        template bank and this rank's periods are uploaded again through the C ABI setters)."""
+        self.searcher.set_inputs(t, y, dy, templates, params)
+        self.searcher.set_periods(self.local_periods)
 
     def _redo_exact(self, fetch):
         """The device plan flagged T14 limits too close to an integer: every rank settles its own
