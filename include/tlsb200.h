@@ -145,6 +145,10 @@ int32_t tlsb_last_chunk(const tlsb_handle *h);
 /* T0 candidates one lane carried through the tap loop in the most recent search (7 with equal
  * weights, 5 with per-point weights or when 7 would cost too many offsets per chunk). */
 int32_t tlsb_last_block(const tlsb_handle *h);
+/* Tiled path: how many of the unique template widths (ascending) the most recent search took from
+ * staged chunks; the remaining, widest ones were searched from the L2 scratch.  Equals the number of
+ * unique widths on the other paths. */
+int32_t tlsb_last_tiled_widths(const tlsb_handle *h);
 /* Tiled path: the fold is sorted on chip, one phase segment at a time (segment_capacity keys per
  * segment, n_segments segments; both 0 when the sort runs in global scratch).  A period whose
  * phases cluster so strongly that a segment overflows is sorted in global scratch instead;
@@ -153,7 +157,9 @@ int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_se
                         int64_t *global_sort_periods);
 /* Force a layout (tests, experiments): path 0 = automatic (default), 1..3 as above; a search
  * fails with TLSB_ERR_ARG if the forced layout cannot hold the inputs.  chunk_doubles > 0 caps
- * the tiled path's chunk capacity so that small inputs exercise several chunks. */
+ * the tiled path's chunk capacity (never below the widest window) so that small inputs exercise
+ * several chunks; chunk_doubles < 0 caps it at exactly -chunk_doubles, so that the widest widths
+ * no longer fit a chunk and take the pass that reads the folded curve from L2 instead. */
 int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles);
 /* Launch shape of the most recent search kernel (any pointer may be NULL). */
 int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,

@@ -194,6 +194,30 @@ def test_tiled_path_matches_reference_golden(name):
     np.testing.assert_allclose(out[0], auto[0], rtol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["small", "cfg1_50ppm", "cfg1_hetero", "ragged_L", "ties_unsorted", "margin0", "cfg3"])
+def test_tiled_path_with_widths_too_wide_for_a_chunk(name):
+    """A chunk capped BELOW the widest window: the narrow widths are searched from staged chunks, the
+    widest ones in the extra pass that reads the folded curve from the L2 scratch (the layout of a
+    4-year curve with per-point uncertainties).  Same results as the automatic path."""
+    native = _native()
+    g = load_search_golden(name)
+    if len(g["periods"]) > 400:
+        sel = np.linspace(0, len(g["periods"]) - 1, 400).astype(int)
+        g = dict(g, periods=g["periods"][sel], chi2=g["chi2"][sel], row=g["row"][sel], depth=g["depth"][sel])
+    widths = np.unique(np.asarray(g["templates"]["width"]))
+    cap = int(widths[len(widths) * 2 // 3] * 1.2) + 100  # roughly the widest third of the bank does not fit
+    if cap >= widths[-1]:
+        pytest.skip("bank too narrow to split")
+    out, info = _search_with_path(native, g, "tiled", chunk=-cap)
+    assert info["path"] == "tiled" and info["chunk"] <= cap
+    assert 1 <= info["tiled_widths"] < len(widths), info
+    assert_search_parity(out[:3], g, rtol=RTOL, label=name + " tiled+L2")
+    auto, _ = _search_with_path(native, g, "auto")
+    np.testing.assert_array_equal(out[1], auto[1])
+    np.testing.assert_array_equal(out[3], auto[3])
+    np.testing.assert_allclose(out[0], auto[0], rtol=1e-12)
+
+
 @pytest.mark.parametrize("name", ["small", "cfg1_hetero", "ragged_L", "ties_unsorted", "cfg3"])
 def test_streaming_path_matches_reference_golden(name):
     """The last-resort layout (everything through L1/L2) stays correct."""

@@ -159,6 +159,7 @@ struct SearchArgs {
     int chunk;            // tiled path: doubles per staged array (cs / w / wd) in shared memory
     int seg_cap;          // tiled path, on-chip sort: elements per phase segment (0: sort in global scratch)
     int n_seg;            // number of phase segments (<= kMaxSegments)
+    int n_tiled;          // tiled path: unique widths [0, n_tiled) are searched from staged chunks, the rest from L2
 };
 
 // tls_constants.py:20-25,78 and grid.py:9-32 (T14); same operation order on host and device
@@ -1252,32 +1253,23 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         best.D = 0.0;
         best.u = -1;
         best.i = -1;
-        const int TP = (C - window_need(rec[uhi - 1].W, rec[uhi - 1].X, kBlock)) & ~1;
-        const int i_last = NM - rec[ulo].W;  // the narrowest admissible width has the most offsets
-        for (int a0 = 0; a0 <= i_last; a0 += TP) {
-            fence_proxy_async();
-            __syncthreads();  // phase A / the previous chunk are done with the staging area and the tables
-            if (tid == 0) {
-                const int len_cs = min(C, (int)cs_elems - a0);
-                const int len_wd = min(C, (int)nmp_even - a0);
-                mbar_expect_tx(bar, 8u * (unsigned)(len_cs + (kUniformW ? 1 : 2) * len_wd));
-                bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
-                if (!kUniformW) bulk_copy_g2s(w_s, w + a0, 8u * (unsigned)len_wd, bar);
-                bulk_copy_g2s(wd_s, wd + a0, 8u * (unsigned)len_wd, bar);
-                s_next[1] = 0;
-                s_next[2] = 0;
-                s_next[3] = 0;
-            }
-            if (wid == kW - 1) {  // candidate range and tiles of every admissible width in this chunk
+        // Widths [ulo, uT) are searched from staged chunks; the few widest ones whose window leaves too few start
+        // offsets in a chunk (unequal weights on a 4-year curve: three staged arrays) are searched afterwards
+        // straight from this CTA's L2 scratch, as one "chunk" that spans the whole folded curve.
+        const int uT = min(uhi, a.n_tiled);
+
+        // candidate range and tiles of the widths [ua, ub) for start offsets [a0, a0 + span): tables + s_next[4]
+        auto build_tables = [&](int a0, int span, int ua, int ub) {
+            if (wid == kW - 1) {
                 int total = 0;
-                for (int base = 0; base < uhi - ulo; base += 32) {
+                for (int base = 0; base < ub - ua; base += 32) {
                     const int idx = base + lane;
                     int tiles = 0;
-                    if (idx < uhi - ulo) {
-                        const int u = uhi - 1 - idx;
+                    if (idx < ub - ua) {
+                        const int u = ub - 1 - idx;
                         const int X = rec[u].X;
                         int lo = (a0 + X - 1) / X;
-                        int hi = (a0 + TP + X - 1) / X;
+                        int hi = (a0 + span + X - 1) / X;
                         if (hi > rec[u].ncand) hi = rec[u].ncand;
                         if (hi < lo) hi = lo;
                         tiles = (hi - lo + kTile - 1) / kTile;
@@ -1291,14 +1283,13 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 }
                 if (lane == 0) s_next[4] = total;
             }
-            __syncthreads();
-            const int tile_end = s_next[4];
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-            const double *csb = cs_s - a0, *wb = w_s - a0, *wdb = wd_s - a0;  // indexable by global offsets
+        };
 
+        // gate + taps over the tables' tiles, widths ub-1 downwards; csb / wb / wdb are indexable by global offsets
+        auto sweep = [&](const double *csb, const double *wb, const double *wdb, int ub) {
+            const int tile_end = s_next[4];
             int g_next = wid;
-            int cur_u = uhi - 1;
+            int cur_u = ub - 1;
             int u_begin = 0, u_end = ch_tiles[cur_u];
             for (;;) {
                 // B1: gate
@@ -1377,6 +1368,38 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
                 __syncthreads();
             }
+        };
+
+        if (ulo < uT) {
+            const int TP = (C - window_need(rec[uT - 1].W, rec[uT - 1].X, kBlock)) & ~1;
+            const int i_last = NM - rec[ulo].W;  // the narrowest admissible width has the most offsets
+            for (int a0 = 0; a0 <= i_last; a0 += TP) {
+                fence_proxy_async();
+                __syncthreads();  // phase A / the previous chunk are done with the staging area and the tables
+                if (tid == 0) {
+                    const int len_cs = min(C, (int)cs_elems - a0);
+                    const int len_wd = min(C, (int)nmp_even - a0);
+                    mbar_expect_tx(bar, 8u * (unsigned)(len_cs + (kUniformW ? 1 : 2) * len_wd));
+                    bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
+                    if (!kUniformW) bulk_copy_g2s(w_s, w + a0, 8u * (unsigned)len_wd, bar);
+                    bulk_copy_g2s(wd_s, wd + a0, 8u * (unsigned)len_wd, bar);
+                    s_next[1] = 0;
+                    s_next[2] = 0;
+                    s_next[3] = 0;
+                }
+                build_tables(a0, TP, ulo, uT);
+                __syncthreads();
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+                sweep(cs_s - a0, w_s - a0, wd_s - a0, uT);
+            }
+        }
+        if (uT < uhi) {  // the widest widths: gate and taps read the scratch through L1/L2
+            __syncthreads();  // the last chunk's sweep is done with the queue and the tables
+            if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
+            build_tables(0, 1 << 30, max(ulo, uT), uhi);
+            __syncthreads();
+            sweep(cs, w, wd, uhi);
         }
 
         // ---- C. block arg-min with the reference's tie order ---------------------------
@@ -1590,6 +1613,7 @@ struct Layout {
     int kb = 5;            // candidates per lane (block size R)
     int seg_cap = 0;       // on-chip sort of the tiled path: segment capacity (0 = off) and count
     int n_seg = 0;
+    int n_tiled = 0;       // tiled path: widths [0, n_tiled) fit a chunk with enough start offsets left
     int threads = 256;     // 256 (two CTAs per SM) or 512 (one)
     int ctas_per_sm = 2;
     int qcap = 4096;
@@ -1799,18 +1823,37 @@ Layout choose_layout(const tlsb_handle *h)
             const size_t fixed = (size_t)t[2] * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 + (size_t)(kMaxSegments + 2) * 4;
             if (per_cta <= fixed) continue;
             long long C = (long long)(((per_cta - fixed) / (8 * (size_t)narr)) & ~(size_t)1);
+            const bool exact_cap = h->chunk_cap < 0;  // tests: cap the chunk exactly; widths that do not fit take the L2 pass
             if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~1LL);
-            if (C <= need5) continue;
-            long long TP = C - need_max;
-            int kb = kb_pref;
-            if (kb == 7 && 5 * TP < 4 * (C - need5)) {  // the longer overshoot would cost > 20 % of the offsets per chunk
-                kb = 5;
-                TP = C - need5;
+            if (exact_cap) C = std::min<long long>(C, (long long)(-h->chunk_cap) & ~1LL);
+            int kb = kb_pref, n_tiled = h->nU;
+            long long TP = 0;
+            bool fits = C > need5;
+            if (fits) {
+                TP = C - need_max;
+                if (kb > 5 && 5 * TP < 4 * (C - need5)) {  // the longer overshoot would cost > 20 % of the offsets per chunk
+                    kb = 5;
+                    TP = C - need5;
+                }
+                if (TP < (h->chunk_cap != 0 ? 2 : 256)) fits = false;
             }
-            if (h->chunk_cap > 0 && TP < 2) continue;
-            // two CTAs per SM only when most of a chunk is start offsets (halo below ~40 %); one big CTA otherwise
-            if (h->chunk_cap <= 0 && t[1] == 2 && forced < 0 && (TP < 2048 || 5 * TP < 3 * C)) continue;
-            if (h->chunk_cap <= 0 && TP < 256) continue;
+            if (!fits) {
+                // The widest windows leave (almost) no start offsets in a chunk - e.g. three staged arrays for a
+                // 4-year curve with unequal weights.  One big CTA per SM then tiles the widths that do fit and
+                // searches the few widest ones straight from its L2 scratch (kernel: uT).
+                if (t[1] != 1 && !exact_cap) continue;
+                kb = 5;
+                const long long tp_min = exact_cap ? 64 : std::max<long long>(1024, C / 4);
+                n_tiled = 0;
+                for (const WidthRec &wr : h->recs) {
+                    if (C - window_need(wr.W, wr.X, 5) < tp_min) break;
+                    ++n_tiled;
+                }
+                if (n_tiled < 1 || (!exact_cap && 4 * n_tiled < 3 * h->nU)) continue;
+                TP = C - window_need(h->recs[(size_t)n_tiled - 1].W, h->recs[(size_t)n_tiled - 1].X, 5);
+            } else if (h->chunk_cap == 0 && t[1] == 2 && forced < 0 && (TP < 2048 || 5 * TP < 3 * C)) {
+                continue;  // two CTAs per SM only when most of a chunk is start offsets (halo below ~40 %); one big CTA otherwise
+            }
             best.resident = false;
             best.tiled = true;
             best.kb = kb;
@@ -1818,6 +1861,7 @@ Layout choose_layout(const tlsb_handle *h)
             best.ctas_per_sm = t[1];
             best.qcap = t[2];
             best.chunk = (int)C;
+            best.n_tiled = n_tiled;
             best.NB = (int)std::min<long long>(N, (long long)narr * C * 2 - 2);
             best.smem = (size_t)t[2] * 8 + (size_t)narr * (size_t)C * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 +
                         (size_t)(kMaxSegments + 2) * 4;
@@ -1925,6 +1969,7 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     a.chunk = lay.chunk;
     a.seg_cap = lay.seg_cap;
     a.n_seg = lay.n_seg;
+    a.n_tiled = lay.tiled ? lay.n_tiled : h->nU;
     const int grid = std::min(only ? n_only : P, h->num_sms * lay.ctas_per_sm);
     if (!lay.resident) {
         if (lay.NB < 1) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
@@ -2273,7 +2318,7 @@ int tlsb_set_plan_mode(tlsb_handle *h, int32_t mode)
 
 int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles)
 {
-    if (!h || path < 0 || path > 3 || chunk_doubles < 0) return fail(TLSB_ERR_ARG, "tlsb_set_path: path must be 0..3, chunk >= 0");
+    if (!h || path < 0 || path > 3) return fail(TLSB_ERR_ARG, "tlsb_set_path: path must be 0..3");
     h->path_mode = path;
     h->chunk_cap = chunk_doubles;
     return 0;
@@ -2332,6 +2377,7 @@ int32_t tlsb_last_path_resident(const tlsb_handle *h) { return h && h->layout.re
 int32_t tlsb_last_path(const tlsb_handle *h) { return !h ? 0 : h->layout.resident ? 1 : h->layout.tiled ? 2 : 3; }
 int32_t tlsb_last_chunk(const tlsb_handle *h) { return h ? h->layout.chunk : 0; }
 int32_t tlsb_last_block(const tlsb_handle *h) { return h ? h->layout.kb : 0; }
+int32_t tlsb_last_tiled_widths(const tlsb_handle *h) { return h ? (h->layout.tiled ? h->layout.n_tiled : h->nU) : 0; }
 
 int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_segments, int64_t *global_sort_periods)
 {

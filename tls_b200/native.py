@@ -22,7 +22,7 @@ EXPORTS = (
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
     "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info", "tlsb_last_block", "tlsb_resolve_plan", "tlsb_plan_repair_count",
     "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
-    "tlsb_current_device",
+    "tlsb_current_device", "tlsb_last_tiled_widths",
 )
 
 _c_i64 = ctypes.c_int64
@@ -98,6 +98,8 @@ def lib():
     L.tlsb_last_path.argtypes = [_c_vp]
     L.tlsb_last_block.restype = ctypes.c_int32
     L.tlsb_last_block.argtypes = [_c_vp]
+    L.tlsb_last_tiled_widths.restype = ctypes.c_int32
+    L.tlsb_last_tiled_widths.argtypes = [_c_vp]
     L.tlsb_last_chunk.restype = ctypes.c_int32
     L.tlsb_last_chunk.argtypes = [_c_vp]
     L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
@@ -396,7 +398,8 @@ class Searcher(object):
                "tlsb_last_layout")
         return dict(threads=th.value, ctas_per_sm=cp.value, queue_capacity=qc.value, smem_bytes=sm.value,
                     resident=self.resident, path=self.path, chunk=self.chunk,
-                    block=int(lib().tlsb_last_block(self._h)))
+                    block=int(lib().tlsb_last_block(self._h)),
+                    tiled_widths=int(lib().tlsb_last_tiled_widths(self._h)))
 
     @property
     def launch_count(self):
