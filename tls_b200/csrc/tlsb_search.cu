@@ -1836,6 +1836,22 @@ Layout choose_layout(const tlsb_handle *h)
                     TP = C - need5;
                 }
                 if (TP < (h->chunk_cap != 0 ? 2 : 256)) fits = false;
+                // One big CTA per SM: a width that would leave less than half of a chunk as start offsets (every sample
+                // staged more than twice) takes the L2 pass even though it fits (cfg-2: 22.0 -> 20.7 ms per 6,000
+                // periods with 7 of 66 widths moved; TLSB_TP_FRAC = percent, experiments).
+                if (fits && t[1] == 1 && h->chunk_cap == 0) {
+                    const char *fr = std::getenv("TLSB_TP_FRAC");
+                    const long long tp_min = C * (fr ? std::atoi(fr) : 50) / 100;
+                    int n = 0;
+                    for (const WidthRec &wr : h->recs) {
+                        if (C - window_need(wr.W, wr.X, kb) < tp_min) break;
+                        ++n;
+                    }
+                    if (4 * n >= 3 * h->nU && n < h->nU) {
+                        n_tiled = n;
+                        TP = C - window_need(h->recs[(size_t)n - 1].W, h->recs[(size_t)n - 1].X, kb);
+                    }
+                }
             }
             if (!fits) {
                 // The widest windows leave (almost) no start offsets in a chunk - e.g. three staged arrays for a
@@ -1843,7 +1859,7 @@ Layout choose_layout(const tlsb_handle *h)
                 // searches the few widest ones straight from its L2 scratch (kernel: uT).
                 if (t[1] != 1 && !exact_cap) continue;
                 kb = 5;
-                const long long tp_min = exact_cap ? 64 : std::max<long long>(1024, C / 4);
+                const long long tp_min = exact_cap ? 64 : std::max<long long>(1024, C / 2);
                 n_tiled = 0;
                 for (const WidthRec &wr : h->recs) {
                     if (C - window_need(wr.W, wr.X, 5) < tp_min) break;
