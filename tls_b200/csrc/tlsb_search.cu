@@ -60,6 +60,7 @@ constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behin
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr int kResScanItems = 19;     // ... of the resident kernel: one tile covers 19 * 256 = 4864 samples (cfg-1: one tile, 3 barriers)
 constexpr int kSegPerThread = 16;   // keys of one segment a thread keeps in registers (S <= 16 * threads)
+constexpr int kSegScanItems = 17;   // scan tile of the on-chip sort: 17 * threads > S, so one tile and three barriers per scan
 constexpr int kMaxSegments = 64;     // phase segments of the on-chip sort of the tiled path
 constexpr int kPlanThreads = 1024;
 constexpr int kPlanBins = 1024;
@@ -994,7 +995,8 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
                                              double *gkey, unsigned *gid, double *cs1, double *w, double *wd,
                                              int nmp_even, double *red_d, double &tpart_out)
 {
-    constexpr int kU = 4;
+    constexpr int kU = 4;                  // independent chains of the rank / gather loop
+    constexpr int kUP = 4;                 // ... of the partition pass
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int N = a.N, M = a.M, NM = N + M, S = a.seg_cap, ns = a.n_seg;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -1008,12 +1010,12 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     for (int j = tid; j <= ns; j += kT) cnt[j] = 0;
     __syncthreads();
     // ---- partition: one pass over t ------------------------------------------------------------
-    for (int kb = wid * 32; kb < N; kb += kT * kU) {  // warp-uniform bounds: every lane reaches the match
-        double tv[kU];
+    for (int kb = wid * 32; kb < N; kb += kT * kUP) {  // warp-uniform bounds: every lane reaches the match
+        double tv[kUP];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) tv[u] = (kb + u * kT + lane < N) ? __ldcs(a.t + kb + u * kT + lane) : 0.0;
+        for (int u = 0; u < kUP; ++u) tv[u] = (kb + u * kT + lane < N) ? __ldcs(a.t + kb + u * kT + lane) : 0.0;
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
+        for (int u = 0; u < kUP; ++u) {
             const int k = kb + u * kT + lane;
             int sg = -1;
             double ph = 0.0;
@@ -1073,7 +1075,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
             }
         }
         __syncthreads();
-        block_inclusive_scan<kT, int>(H, S + 1, reinterpret_cast<int *>(red_d));  // H[b] = keys in buckets < b
+        block_inclusive_scan<kT, int, kSegScanItems>(H, S + 1, reinterpret_cast<int *>(red_d));  // H[b] = keys in buckets < b
 #pragma unroll
         for (int i = 0; i < kSegPerThread; ++i) {
             if (tid + i * kT < nj) {
@@ -1140,14 +1142,14 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
             }
         }
         __syncthreads();
-        block_inclusive_scan<kT, double>(val_s, nj, red_d);
+        block_inclusive_scan<kT, double, kSegScanItems>(val_s, nj, red_d);
         for (int q = tid; q < nj; q += kT) cs1[off + q] = carry + val_s[q];
         carry += val_s[nj - 1];
         off += nj;
         __syncthreads();
     }
     // positions N .. NM-1 hold the wrapped d: continue the cumulative sum, weight them, zero the slack
-    wrap_weight_scan<kT, kUniformW>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry);
+    wrap_weight_scan<kT, kUniformW, kSegScanItems>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry);
     tpart_out = tpart;
     return true;
 }
