@@ -122,3 +122,76 @@ def test_multi_planet_known_answers_of_the_reference():
     np.testing.assert_almost_equal(found[1].duration, 0.15061016994013998, decimal=3)
     np.testing.assert_almost_equal(found[1].SDE, 34.9911304598618, decimal=3)
     np.testing.assert_almost_equal(found[1].rp_rs, 0.025852178872027086, decimal=3)
+
+
+def test_handle_pool_recycles_without_carrying_state():
+    """batch_power borrows its handle from native.Searcher's per-device pool; a recycled handle (other
+    curves, forced layout and plan mode left behind by the previous user) gives the same results."""
+    from tls_b200 import batch_power, native
+
+    native.Searcher.drain_pool()
+    t, ys, dys, kw = _curves(4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        first = batch_power(t, ys, **kw)
+        idle = sum(len(v) for v in native.Searcher._POOL.values())
+        assert idle == 1
+        s = native.Searcher.acquire()  # the same handle, dirtied on purpose
+        s.set_path("streaming")
+        s.set_plan_mode(1)
+        s.release()
+        again = batch_power(t, ys[::-1].copy(), **kw)
+        assert sum(len(v) for v in native.Searcher._POOL.values()) == 1
+    for key in ("SDE", "period", "T0", "depth", "chi2_min"):
+        np.testing.assert_array_equal(first[key], again[key][::-1], err_msg=key)
+    native.Searcher.drain_pool()
+    assert not native.Searcher._POOL
+
+
+def _dist_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    from tls_b200 import batch_power, search_planets, workloads
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    warnings.simplefilter("ignore")
+    t, y, dy, kw = workloads.lightcurve("small", planets=[4.3, 7.9])
+    found = search_planets(t, y, n_planets=2, dist=dist, device=rank, **kw)
+    tb, ys, dys, kwb = _curves(5)
+    res = batch_power(tb, ys, dist=dist, device=rank, **kwb)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), periods=[r.period for r in found], SDE=[r.SDE for r in found],
+             T0=[r.T0 for r in found], chi2=found[0].chi2, b_SDE=res.SDE, b_period=res.period, b_T0=res.T0)
+    dist.destroy_process_group()
+
+
+def test_power_and_batch_on_two_gpus_equal_one_gpu(tmp_path):
+    """power(dist=...) / search_planets(dist=...) (periods sharded, one NCCL all-gather) and
+    batch_power(dist=...) (curves sharded) on two GPUs, one process each: every rank gets exactly the
+    one-GPU results."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from tls_b200 import batch_power, search_planets, workloads
+
+    mp.spawn(_dist_worker, args=(2, 29571, str(tmp_path)), nprocs=2, join=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t, y, dy, kw = workloads.lightcurve("small", planets=[4.3, 7.9])
+        one = search_planets(t, y, n_planets=2, **kw)
+        tb, ys, dys, kwb = _curves(5)
+        one_b = batch_power(tb, ys, **kwb)
+    for rank in range(2):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        np.testing.assert_array_equal(z["periods"], [r.period for r in one])
+        np.testing.assert_array_equal(z["T0"], [r.T0 for r in one])
+        np.testing.assert_allclose(z["SDE"], [r.SDE for r in one], rtol=1e-12)
+        np.testing.assert_array_equal(z["chi2"], one[0].chi2)
+        np.testing.assert_array_equal(z["b_period"], one_b.period)
+        np.testing.assert_array_equal(z["b_T0"], one_b.T0)
+        np.testing.assert_allclose(z["b_SDE"], one_b.SDE, rtol=1e-12)

@@ -196,3 +196,39 @@ def test_header_cites_reference_lines():
     for cite in ("core.py:96-188", "main.py:140-185", "transit.py:108-111", "validate.py:9-46"):
         assert cite in text
     assert len(re.findall(r"\btlsb_\w+\s*\(", text)) >= 14
+
+
+def test_power_routes_the_search_through_the_collective_when_dist_is_given(monkeypatch):
+    """power(dist=...) with more than one rank must call distributed.search_periods_distributed (periods
+    sharded, one all-gather) instead of the one-process call; host orchestration unchanged."""
+    from tls_b200 import distributed, workloads
+
+    calls = []
+
+    class FakeDist(object):
+        @staticmethod
+        def is_initialized():
+            return True
+
+        @staticmethod
+        def get_world_size():
+            return 2
+
+    def fake_search(t, y, dy, periods, templates, params, dist, device=None):
+        from oracle import oracle
+
+        calls.append((len(periods), device))
+        return oracle.search_periods_c(t, y, dy, periods, templates, params)
+
+    monkeypatch.setattr(distributed, "search_periods_distributed", fake_search)
+    t, y, dy, kw = workloads.lightcurve("small")
+
+    class Model(_OracleBacked):
+        _search = transitleastsquares._search  # the product routing, not the oracle shortcut
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = Model(t, y, dy, verbose=False).power(show_progress_bar=False, verbose=False, dist=FakeDist, device=0, **kw)
+        ref = _OracleBacked(t, y, dy, verbose=False).power(show_progress_bar=False, verbose=False, **kw)
+    assert calls == [(len(res.periods), 0)]
+    assert res.period == ref.period and res.SDE == ref.SDE and res.T0 == ref.T0
