@@ -27,6 +27,7 @@ Host-side, once per search (~10 ms); not part of the GPU hot path.
 from __future__ import annotations
 
 import functools
+import os
 
 import numpy as np
 
@@ -95,8 +96,18 @@ LAWS = (
 
 @functools.lru_cache(maxsize=16)
 def _gl(n):
-    """Gauss-Legendre nodes and weights (an eigenvalue problem: computed once per order)."""
-    x, w = np.polynomial.legendre.leggauss(n)
+    """Gauss-Legendre nodes and weights.  numpy solves an n x n eigenvalue problem for them
+    (0.5 s per order, most of a first ``.power()`` call), so the two orders this module uses
+    ship as a table (``data/gauss_legendre.npz`` = ``leggauss(256)`` and ``leggauss(384)``,
+    bit for bit); any other order is computed."""
+    table = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "gauss_legendre.npz")
+    x = w = None
+    if os.path.exists(table):
+        with np.load(table) as z:
+            if "x%d" % n in z.files:
+                x, w = np.array(z["x%d" % n]), np.array(z["w%d" % n])
+    if x is None:
+        x, w = np.polynomial.legendre.leggauss(n)
     x.setflags(write=False)
     w.setflags(write=False)
     return x, w
