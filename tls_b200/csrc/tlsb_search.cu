@@ -59,6 +59,14 @@ __host__ __device__ constexpr int tile_size(int kb) { return 32 * kb * kSub; }  
 constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr int kResScanItems = 19;     // ... of the resident kernel: one tile covers 19 * 256 = 4864 samples (cfg-1: one tile, 3 barriers)
+#ifndef TLSB_RES_HSCAN
+#define TLSB_RES_HSCAN 19  // one tile for cfg-1's 4,322 histogram words, like kResScanItems (5 -> 17: 2.611 -> 2.579 ms per cfg-1 grid)
+#endif
+#ifndef TLSB_RES_SORT_U
+#define TLSB_RES_SORT_U 4
+#endif
+constexpr int kResHScanItems = TLSB_RES_HSCAN;  // ... of the bucket-histogram scan of the resident kernel
+constexpr int kResSortU = TLSB_RES_SORT_U;      // independent key chains per thread in the resident kernel's fold / scatter / rank loops
 constexpr int kSegPerThread = 16;   // keys of one segment a thread keeps in registers (S <= 16 * threads)
 constexpr int kSegScanItems = 17;   // scan tile of the on-chip sort: 17 * threads > S, so one tile and three barriers per scan
 constexpr int kMaxSegments = 64;     // phase segments of the on-chip sort of the tiled path
@@ -391,7 +399,7 @@ __device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const d
 // rank inside the bucket by (phase, index) = numpy's stable mergesort order; src1 (and src2) are
 // gathered to their sorted slots in dst1 (dst2).  dst1 doubles as the store of the unsorted
 // phases until the ranking step; skey/sid/H are scratch.  Ends WITHOUT a barrier.
-template <int kT, typename idx_t, bool kTwo, bool kEpoch, int kU = 4>
+template <int kT, typename idx_t, bool kTwo, bool kEpoch, int kU = 4, int kHScanItems = ::kScanItems>
 __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, double T0, double r, int N, int NB,
                                                  int *H, double *skey, idx_t *sid,
                                                  const double *__restrict__ src1, const double *__restrict__ src2,
@@ -418,7 +426,7 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
     }
     __syncthreads();
     // inclusive scan of H[0..NB] (H[0] = 0): H[b] = number of keys in buckets < b
-    block_inclusive_scan<kT, int>(H, NB + 1, scan_scratch);
+    block_inclusive_scan<kT, int, kHScanItems>(H, NB + 1, scan_scratch);
     for (int k0 = tid; k0 < N; k0 += kT * kU) {
         double ph[kU];
 #pragma unroll
@@ -762,7 +770,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(co
         }
 
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
-        fold_sort_gather<kT, idx_t, !kUniformW, false>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w,
+        fold_sort_gather<kT, idx_t, !kUniformW, false, (kResident ? kResSortU : 4), (kResident ? kResHScanItems : kScanItems)>(
+            a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w,
                                                        reinterpret_cast<int *>(red_d));
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
