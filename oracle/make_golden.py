@@ -252,6 +252,65 @@ def case_power():
     save_power("sentinel", t, y, dy, "no-fit branch", transit_depth_min=1000e-6, T0_fit_margin=0.1)
 
 
+# ------------------------------------------------------------------ the reference's own test scripts, end to end
+def three_year_curve(seed=0):
+    """The synthetic light curve shared by tests/test_synthetic.py:9-38, test_stats_gap.py:11-37,
+    test_transit_depth_min.py:12-38 and test_uncertainties.py:9-38: 3 yr at 12 samples per day, an Earth
+    around a Sun at 365.25 d (linear limb darkening), 5 ppm white noise.  The transit model is this repo's
+    stand-in for batman (the reference tests call batman at this point)."""
+    from tls_b200 import limbdark
+
+    np.random.seed(seed=seed)
+    start, days, samples_per_day = 48, 365.25 * 3, 12
+    samples = int(days * samples_per_day)
+    t = np.linspace(start, start + days, samples)
+    ma = limbdark.TransitParams()
+    ma.t0 = start + 20
+    ma.per = 365.25
+    ma.rp = 6371 / 696342
+    ma.a = 217
+    ma.inc = 90
+    ma.ecc = 0
+    ma.w = 90
+    ma.u = [0.5]
+    ma.limb_dark = "linear"
+    flux = limbdark.TransitModel(ma, t).light_curve(ma)
+    stdev = 10 ** -6 * 5
+    y = flux + np.random.normal(0, stdev, int(samples))
+    return t, y, stdev
+
+
+def case_ref_tests():
+    # tests/test_synthetic.py:38-48
+    t, y, stdev = three_year_curve()
+    y[1] = np.nan
+    save_power("ref_synthetic", t, y, None, "tests/test_synthetic.py", period_min=360, period_max=370,
+               transit_depth_min=10 * 10 ** -6, oversampling_factor=5, duration_grid_step=1.02)
+    # tests/test_stats_gap.py:38-56 (a gap of NaNs in t and y)
+    t, y, stdev = three_year_curve()
+    y[1] = np.nan
+    y[200:500] = np.nan
+    t[200:500] = np.nan
+    save_power("ref_stats_gap", t, y, None, "tests/test_stats_gap.py", period_min=360, period_max=370,
+               transit_depth_min=10 * 10 ** -6, oversampling_factor=2, duration_grid_step=1.1, T0_fit_margin=1.2)
+    # tests/test_uncertainties.py:40-56 (excess noise with matching dy at the end of the series)
+    t, y, stdev = three_year_curve()
+    y[10000:] = y[10000:] + np.random.normal(0, 10 * stdev, 3149)
+    dy = np.full(len(y), stdev)
+    dy[10000:] = 10 * stdev
+    save_power("ref_uncertainties", t, y, dy, "tests/test_uncertainties.py", period_min=360, period_max=370,
+               oversampling_factor=3, duration_grid_step=1.05, T0_fit_margin=0.2)
+    # tests/test_transit_depth_min.py:39-48 (nothing is fitted)
+    t, y, stdev = three_year_curve()
+    y[1] = np.nan
+    save_power("ref_transit_depth_min", t, y, None, "tests/test_transit_depth_min.py",
+               transit_depth_min=1000 * 10 ** -6, period_min=360, period_max=370, oversampling_factor=5,
+               duration_grid_step=1.02, T0_fit_margin=0.1)
+    # tests/test_shapes.py:29-36
+    t, y, dy = k2_shapes()
+    save_power("k2_epic206154641_grazing", t, y, dy, "tests/test_shapes.py grazing", transit_template="grazing")
+
+
 # ------------------------------------------------------------------ final_T0_fit goldens
 def save_t0fit(name, t, y, signal, depth, period, margin, note):
     """Reference stats.final_T0_fit (stats.py:135-204, unmodified) -> T0; the per-trial residuals
@@ -315,7 +374,7 @@ CASES = {
     "cfg1_50ppm": case_cfg1_50ppm, "cfg1_500ppm": case_cfg1_500ppm, "cfg1_hetero": case_cfg1_hetero,
     "sentinel": case_sentinel, "margins": case_margins, "small": case_small_and_ties,
     "ragged": case_ragged_templates, "no_admissible": case_no_admissible, "cfg3": case_cfg3,
-    "cfg2": case_cfg2, "k2": case_k2, "power": case_power, "t0fit": case_t0fit,
+    "cfg2": case_cfg2, "k2": case_k2, "power": case_power, "ref_tests": case_ref_tests, "t0fit": case_t0fit,
 }
 
 if __name__ == "__main__":

@@ -167,7 +167,8 @@ def _power_golden(name):
     return z, kw, dy
 
 
-@pytest.mark.parametrize("name", ["small_hetero", "sentinel", "cfg1_50ppm"])
+@pytest.mark.parametrize("name", ["small_hetero", "sentinel", "cfg1_50ppm", "ref_synthetic", "ref_stats_gap",
+                                  "ref_uncertainties", "ref_transit_depth_min"])
 def test_power_host_pipeline_matches_reference(name):
     z, kw, dy = _power_golden(name)
     with warnings.catch_warnings():
@@ -188,6 +189,51 @@ def test_power_host_pipeline_matches_reference(name):
                 "model_folded_model", "model_lightcurve_model"):
         np.testing.assert_allclose(np.asarray(res[key], dtype=float), z["a_" + key], rtol=1e-5, atol=1e-7,
                                    equal_nan=True, err_msg=key)
+
+
+def test_reference_test_scripts_known_answers_host_pipeline():
+    """The literal known answers of the reference's own test scripts (made with genuine batman) on the inputs of
+    tests/golden/power_ref_*.npz (the same scripts with this repo's transit model; oracle/make_golden.py
+    case_ref_tests).  Decimals as in the reference wherever the stand-in model allows, otherwise 3."""
+    def run(name):
+        z, kw, dy = _power_golden(name)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return _OracleBacked(z["in_t"], z["in_y"], dy, verbose=False).power(show_progress_bar=False, verbose=False, **kw)
+
+    res = run("ref_stats_gap")  # tests/test_stats_gap.py:57-85
+    np.testing.assert_almost_equal(res.period_uncertainty, 0.3153203546531813, decimal=5)
+    np.testing.assert_equal(res.per_transit_count, [0, 5, 5])
+    assert len(res.transit_times) == 3
+    np.testing.assert_almost_equal(res.period, 365.22218620040417, decimal=5)
+    np.testing.assert_almost_equal(res.transit_times, [68.08637, 433.30855, 798.53074], decimal=5)
+    np.testing.assert_almost_equal(res.depth, 0.9998972750356973, decimal=5)
+    np.testing.assert_almost_equal(res.duration, 0.41845319797978703, decimal=5)
+    np.testing.assert_almost_equal(res.SDE, 4.243572802600693, decimal=3)
+    np.testing.assert_almost_equal(res.odd_even_mismatch, 0.15059221218811772, decimal=3)
+    np.testing.assert_almost_equal(res.rp_rs, 0.009114758081257387, decimal=3)
+    np.testing.assert_almost_equal(np.sum(res.model_lightcurve_time), 38275494.19583159, decimal=3)
+    res = run("ref_uncertainties")  # tests/test_uncertainties.py:57
+    np.testing.assert_almost_equal(res.SDE, 5.292594615900944, decimal=3)
+    res = run("ref_synthetic")  # tests/test_synthetic.py:50-63
+    np.testing.assert_almost_equal(res.period_uncertainty, 0.216212529678387, decimal=5)
+    assert res.per_transit_count[0] == 7 and len(res.transit_times) == 3
+    np.testing.assert_almost_equal(res.period, 365.2582192473641, decimal=5)
+    np.testing.assert_almost_equal(res.transit_times[0], 68.00349264912924, decimal=5)
+    res = run("ref_transit_depth_min")  # tests/test_transit_depth_min.py:50-71
+    for key in ("transit_times", "period", "duration", "snr", "snr_pink_per_transit", "odd_even_mismatch",
+                "in_transit_count", "after_transit_count", "before_transit_count"):
+        assert np.all(np.isnan(np.asarray(res[key], dtype=float))), key
+    assert res.depth == 1 and res.SDE == 0 and res.SDE_raw == 0
+    np.testing.assert_almost_equal(res.chi2_min, 13148.0)
+    np.testing.assert_almost_equal(res.chi2red_min, 1.0003043213633598)
+    assert len(res.periods) == 278
+    np.testing.assert_almost_equal(max(res.periods), 369.9831654894093)
+    np.testing.assert_almost_equal(min(res.periods), 360.0118189140635)
+    np.testing.assert_almost_equal(max(res.power), 0)
+    np.testing.assert_almost_equal(min(res.power), 0)
+    np.testing.assert_almost_equal(max(res.chi2), 13148.0)
+    np.testing.assert_almost_equal(max(res.chi2red), 1.0003043213633598)
 
 
 def test_header_cites_reference_lines():
