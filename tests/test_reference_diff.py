@@ -1,0 +1,191 @@
+"""Differential tests of the HOST functions against the unmodified reference, imported from
+/root/reference through oracle/ref_shim.py.  They run in the build container only (the reference
+tree does not travel to the GPU box: skipped there); what travels are the goldens under
+tests/golden/.  Bar: identical return values (bit for bit), identical exception type, identical
+warning texts — these functions are the drop-in surface around the GPU search
+(transitleastsquares/__init__.py:13-18)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_shim  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="needs /root/reference (build container only)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return ref_shim.load()
+
+
+def _run(fn, *a, **k):
+    try:
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            r = fn(*a, **k)
+        return r, [str(x.message) for x in w]
+    except Exception as e:  # noqa: BLE001 - the exception type IS the behaviour under test
+        return type(e), []
+
+
+def _same(ra, rb):
+    (va, wa), (vb, wb) = ra, rb
+    if isinstance(va, type) or isinstance(vb, type):
+        return va is vb
+    ta = va if isinstance(va, tuple) else (va,)
+    tb = vb if isinstance(vb, tuple) else (vb,)
+    return wa == wb and len(ta) == len(tb) and all(
+        np.array_equal(np.asarray(x, dtype=float), np.asarray(z, dtype=float), equal_nan=True) for x, z in zip(ta, tb))
+
+
+def _check(name, f_ref, f_mine, *a, **k):
+    ra, rb = _run(f_ref, *a, **k), _run(f_mine, *a, **k)
+    assert _same(ra, rb), (name, k, str(ra)[:200], str(rb)[:200])
+
+
+def test_period_grid_and_duration_grid(ref):
+    """grid.py:35-131 and grid.py:134-150 over spans, stars, oversampling, limits (also the degenerate ones)."""
+    from transitleastsquares import grid as rg
+
+    from tls_b200 import grid as mg
+
+    for span in (5, 27.4, 90, 1500):
+        for R, M in ((1, 1), (0.5, 0.5), (2, 1.5), (0.1, 0.1), (3.5, 1)):
+            for ov in (1, 3, 5):
+                for pmin, pmax in ((0, float("inf")), (1, 10), (0.3, 3), (10, 5), (100, 200)):
+                    for ntm in (1, 2, 3):
+                        _check("period_grid", rg.period_grid, mg.period_grid, R_star=R, M_star=M, time_span=span,
+                               period_min=pmin, period_max=pmax, oversampling_factor=ov, n_transits_min=ntm)
+    for span in (27.4, 90, 400):
+        per = rg.period_grid(1, 1, span)
+        for shortest in (1 / 500, 1 / 4320, 1 / 70000, 0.01):
+            for step in (1.02, 1.1, 1.5):
+                _check("duration_grid", rg.duration_grid, mg.duration_grid, per, shortest=shortest, log_step=step)
+
+
+def test_helpers_and_statistics(ref):
+    """helpers.cleaned_array (:18-61), resample (:7-15), transit_mask (:64-67), stats.FAP (:8-24), core.fold (:9-12)."""
+    from transitleastsquares import core as rc
+    from transitleastsquares import helpers as rh
+    from transitleastsquares import stats as rs
+
+    from tls_b200 import helpers as mh
+    from tls_b200 import stats as ms
+
+    rng = np.random.RandomState(0)
+    t = np.linspace(0, 10, 50)
+    y = 1 + rng.normal(0, 1e-3, 50)
+    dy = np.full(50, 1e-3)
+    yo = y.astype(object)
+    yo[3], yo[7], yo[9], yo[11] = None, np.nan, np.inf, -1.0
+    to = t.astype(object)
+    to[4] = None
+    dyo = dy.copy()
+    dyo[20], dyo[21] = 0, np.nan
+    masked = np.ma.masked_invalid(np.where(y > 1, np.nan, t))
+    for args in ((t, y), (t, yo), (to, yo), (t, y, dy), (to, yo, dyo), (masked, y), (list(t), list(y))):
+        _check("cleaned_array", rh.cleaned_array, mh.cleaned_array, *args)
+    for factor in (2.0, 3.0, 1.5, 10.0):
+        for dyv in (None, dy):
+            _check("resample", rh.resample, mh.resample, t, y, dyv, factor)
+    for per, dur, T0 in ((2.0, 0.2, 0.3), (3.3, 0.5, 9.9), (0.7, 0.05, -4.0), (50, 1, 5)):
+        _check("transit_mask", rh.transit_mask, mh.transit_mask, t, per, dur, T0)
+        _check("fold", rc.fold, ms.fold, t, per, T0)
+    for sde in (0, 3.0, 6.9, 7.0, 7.5, 8.3, 9.1, 12.0, 20.0, 100.0, np.nan):
+        _check("FAP", rs.FAP, ms.FAP, sde)
+
+
+KWARGS = [
+    {}, {"use_threads": 0}, {"use_threads": "1"}, {"use_threads": 2.5}, {"period_min": 5, "period_max": 2},
+    {"period_min": -1}, {"R_star": -1}, {"M_star": 0}, {"R_star_min": 2, "R_star_max": 1},
+    {"M_star_min": 2, "M_star_max": 1}, {"R_star": 5}, {"M_star": 5}, {"transit_template": "box"},
+    {"transit_template": "grazing"}, {"transit_template": "foo"}, {"transit_template": 3}, {"n_transits_min": 1},
+    {"n_transits_min": 0}, {"n_transits_min": 2.5}, {"n_transits_min": "2"}, {"T0_fit_margin": 0.5},
+    {"T0_fit_margin": -1}, {"T0_fit_margin": 0}, {"oversampling_factor": 0}, {"oversampling_factor": 2.5},
+    {"oversampling_factor": 7}, {"duration_grid_step": 1.0}, {"duration_grid_step": 0.9}, {"duration_grid_step": 1.3},
+    {"transit_depth_min": 0}, {"transit_depth_min": -1e-6}, {"limb_dark": "linear", "u": [0.5]},
+    {"limb_dark": "nonlinear", "u": [0.1, 0.2, 0.3, 0.4]}, {"u": [0.4, 0.4]}, {"per": 5}, {"rp": 0.2}, {"a": 20},
+    {"show_progress_bar": False}, {"verbose": False}, {"period_max": 100}, {"period_min": 0.1},
+]
+
+
+def test_validate_args_and_inputs(ref):
+    """validate.py:49-181: every keyword, its default, its clamp and its ValueError; validate.py:9-46 on good
+    and malformed arrays."""
+    from transitleastsquares import validate as rv
+
+    from tls_b200 import validate as mv
+
+    rng = np.random.RandomState(1)
+    t = np.linspace(0, 30, 800)
+    y = 1 + rng.normal(0, 1e-4, 800)
+
+    class Bag(object):
+        pass
+
+    def attrs(validate_args, kw):
+        b = Bag()
+        b.t, b.y, b.dy = t, y, np.full(800, np.std(y))
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                out, _ = validate_args(b, dict(kw))
+        except Exception as e:  # noqa: BLE001
+            return type(e)
+        return {k: v for k, v in vars(out).items() if k not in ("t", "y", "dy")}
+
+    for kw in KWARGS:
+        a, b = attrs(rv.validate_args, kw), attrs(mv.validate_args, kw)
+        if isinstance(a, type) or isinstance(b, type):
+            assert a is b, (kw, a, b)
+        else:
+            assert set(a) == set(b), (kw, set(a) ^ set(b))
+            for k in a:
+                assert np.all(np.asarray(a[k] == b[k])), (kw, k, a[k], b[k])
+
+    tn, yn = t.copy(), y.copy()
+    yn[5], tn[9] = np.nan, np.inf
+    good = [(t, y, None), (t, y, np.full(800, 2.0)), (tn, yn, None), (t[::-1], y, None), (list(t), list(y), None),
+            (np.r_[t[:5], t[3], t[5:-1]], y, None)]
+    for args in good:
+        _check("validate_inputs", rv.validate_inputs, mv.validate_inputs, *args)
+    # malformed: both must refuse (the reference trips over an IndexError inside its cleaner for unequal
+    # lengths before reaching its own size check, validate.py:41-42; here that check is what fires)
+    bad = [(t[:-1], y, None), (t, y, np.ones(799)), (t, -y, None), (t, y, -np.ones(800)), (t, y * 0, None),
+           (t, y + np.inf, None)]
+    for args in bad:
+        ra, rb = _run(rv.validate_inputs, *args)[0], _run(mv.validate_inputs, *args)[0]
+        assert isinstance(ra, type) and isinstance(rb, type), (ra, rb)
+
+
+def test_template_bank_is_bit_identical(ref):
+    """transit.py:98-160 (get_cache: reference transit -> slice / lerp / trim -> overview) with the same
+    transit model underneath (the stand-in for batman): every template and every overview field equal."""
+    from transitleastsquares import grid as rg
+    from transitleastsquares import transit as rt
+
+    from tls_b200 import transit as mt
+
+    per = rg.period_grid(1, 1, 90.0)
+    planets = ((13.4, 0.103, 23.1, 89.21), (2.5, 2 ** 0.5, 3, 75.0))  # default, grazing (tls_constants.py:40-66)
+    for step, n in ((1.1, 4320), (1.02, 19440)):
+        dur = rg.duration_grid(per, shortest=1 / n, log_step=step)
+        mw = int(np.max(dur) * n)
+        mw += mw % 2
+        for law, u, p in (("quadratic", [0.4804, 0.1867], planets[0]), ("linear", [0.5], planets[0]),
+                          ("nonlinear", [0.1, 0.2, 0.3, 0.1], planets[0]), ("quadratic", [0.4804, 0.1867], planets[1])):
+            kw = dict(durations=dur, maxwidth_in_samples=mw, per=p[0], rp=p[1], a=p[2], inc=p[3], ecc=0, w=90, u=u,
+                      limb_dark=law, verbose=False)
+            oa, la = rt.get_cache(**kw)
+            ob, lb = mt.get_cache(**kw)
+            assert oa.dtype == ob.dtype and len(la) == len(lb)
+            for f in oa.dtype.names:
+                np.testing.assert_array_equal(oa[f], ob[f])
+            for x, z in zip(la, lb):
+                np.testing.assert_array_equal(x, z)
