@@ -44,8 +44,8 @@ def duration_grid(periods, shortest=None, log_step=C.DURATION_GRID_STEP):
     The end points come from the package-level stellar limits, *not* from the
     user's ``R_star_min`` etc., and ``shortest`` is accepted but unused — both as
     in the reference."""
-    longest = T14(C.R_STAR_MAX, C.M_STAR_MAX, min(periods), small=False)
-    d = T14(C.R_STAR_MIN, C.M_STAR_MIN, max(periods), small=True)
+    longest = T14(C.R_STAR_MAX, C.M_STAR_MAX, np.min(periods), small=False)
+    d = T14(C.R_STAR_MIN, C.M_STAR_MIN, np.max(periods), small=True)
     grid = [d]
     while d * log_step < longest:
         d = d * log_step

@@ -42,7 +42,7 @@ def resample(time, flux, factor):
     from .transit import _lerp_resample
 
     n_new = int(len(flux) / factor)
-    grid = np.linspace(min(time), max(time), n_new)
+    grid = np.linspace(np.min(time), np.max(time), n_new)
     return grid, _lerp_resample(grid, time, flux)
 
 

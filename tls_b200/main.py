@@ -153,7 +153,7 @@ class transitleastsquares(object):
         duration = overview["duration"][best_row]
         maxwidth_in_samples = int(np.max(durations) * np.size(t))
 
-        no_fit = max(chi2) == min(chi2)
+        no_fit = np.max(chi2) == np.min(chi2)
         if no_fit:
             warnings.warn('No transit were fit. Try smaller "transit_depth_min"')
 

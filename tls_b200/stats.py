@@ -173,7 +173,7 @@ def calculate_stretch(t, period, transit_times):
 def calculate_fill_factor(t):
     """Fraction of cadences present assuming a constant cadence (stats.py:294-301)."""
     cadence = np.median(np.diff(t))
-    return (len(t) - 1) / ((max(t) - min(t)) / cadence)
+    return (len(t) - 1) / ((np.max(t) - np.min(t)) / cadence)
 
 
 def calculate_transit_duration_in_days(t, period, transit_times, duration):
@@ -193,8 +193,8 @@ def model_lightcurve(transit_times, period, t, model_transit_single):
     ys = np.concatenate([model_transit_single for _ in epochs]) if len(epochs) else np.array([])
     if np.all(np.isnan(xs)):
         return None, None
-    start = np.nanargmax(xs > min(t))
-    stop = np.nanargmax(xs > max(t))
+    start = np.nanargmax(xs > np.min(t))
+    stop = np.nanargmax(xs > np.max(t))
     return ys[start:stop], xs[start:stop]
 
 

@@ -9,6 +9,8 @@ arrays the C ABI takes (``include/tlsb200.h``: ``tlsb_templates``).
 """
 from __future__ import annotations
 
+import collections
+
 import numpy as np
 
 from . import constants as C
@@ -104,6 +106,31 @@ def get_cache(durations, maxwidth_in_samples, per, rp, a, inc, ecc, w, u, limb_d
     ragged object array of float64 templates."""
     if verbose:
         print("Creating model cache for", str(len(durations)), "durations")
+    # The bank depends on these arguments only, and curves of one campaign (batches, the reruns of an
+    # iterative search, repeated calls) ask for the same one again and again: keep the last few.
+    key = (np.asarray(durations, dtype=np.float64).tobytes(), int(maxwidth_in_samples), float(per), float(rp),
+           float(a), float(inc), float(ecc), float(w), tuple(float(x) for x in np.ravel(u)), str(limb_dark))
+    hit = _BANKS.get(key)
+    if hit is not None:
+        _BANKS.move_to_end(key)
+        lc_arr = np.empty(len(hit[1]), dtype=object)
+        for row, signal in enumerate(hit[1]):
+            lc_arr[row] = signal  # read-only arrays, shared
+        return hit[0].copy(), lc_arr
+    overview, lc_arr = _build_bank(durations, maxwidth_in_samples, per, rp, a, inc, ecc, w, u, limb_dark)
+    for signal in lc_arr:
+        signal.setflags(write=False)
+    _BANKS[key] = (overview.copy(), list(lc_arr))
+    while len(_BANKS) > _BANKS_MAX:
+        _BANKS.popitem(last=False)
+    return overview, lc_arr
+
+
+_BANKS = collections.OrderedDict()
+_BANKS_MAX = 8
+
+
+def _build_bank(durations, maxwidth_in_samples, per, rp, a, inc, ecc, w, u, limb_dark):
     rows = np.size(durations)
     overview = np.zeros(
         rows, dtype=[("duration", "f8"), ("width_in_samples", "i8"), ("overshoot", "f8")]
@@ -119,7 +146,7 @@ def get_cache(durations, maxwidth_in_samples, per, rp, a, inc, ecc, w, u, limb_d
         overview["duration"][row] = duration
         overview["width_in_samples"][row] = int((duration / longest) * maxwidth_in_samples)
         used = np.where(full < (1 - C.NUMERICAL_STABILITY_CUTOFF))
-        signal = full[np.min(used) : np.max(used) + 1]
+        signal = np.array(full[np.min(used) : np.max(used) + 1])  # own memory: the bank outlives `full`
         bank.append(signal)
         ratio = np.mean(signal) / np.min(signal)
         overview["overshoot"][row] = 1 / (2 - ratio)

@@ -23,7 +23,7 @@ def validate_inputs(t, y, dy):
         t, y, dy = cleaned_array(t, y, dy)
         dy = dy / np.mean(dy)  # weights, not absolute errors (validate.py:18)
 
-    if max(t) - min(t) <= 0:
+    if np.max(t) - np.min(t) <= 0:
         raise ValueError("Time duration must positive")
     if np.size(y) < 3 or np.size(t) < 3:
         raise ValueError("Too few values in data set")
@@ -33,9 +33,9 @@ def validate_inputs(t, y, dy):
             "Warning: The mean flux should be normalized to 1, but it was found to be "
             + str(mean_flux)
         )
-    if min(y) < 0:
+    if np.min(y) < 0:
         raise ValueError("Flux values must be positive")
-    if max(y) >= float("inf"):
+    if np.max(y) >= float("inf"):
         raise ValueError("Flux values must be finite")
     if dy is None:
         dy = np.full(len(y), np.std(y))  # validate.py:39-40
