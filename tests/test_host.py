@@ -278,3 +278,23 @@ def test_power_routes_the_search_through_the_collective_when_dist_is_given(monke
         ref = _OracleBacked(t, y, dy, verbose=False).power(show_progress_bar=False, verbose=False, **kw)
     assert calls == [(len(res.periods), 0)]
     assert res.period == ref.period and res.SDE == ref.SDE and res.T0 == ref.T0
+
+
+def test_epoch_windows_by_binary_search_equal_the_masks(monkeypatch):
+    """stats.count_stats / intransit_stats / snr_stats take their per-epoch windows by binary search when the time
+    stamps ascend; the results must be those of the reference's boolean masks (stats.py:304-469), also with
+    repeated time stamps and epochs outside the data or NaN."""
+    from tls_b200 import stats
+
+    rng = np.random.RandomState(3)
+    t = np.sort(np.round(rng.uniform(0, 50, 3000), 2))  # repeated stamps
+    y = 1 + rng.normal(0, 1e-3, 3000)
+    times = [-1.0, 0.005, 3.3, 13.37, 25.0, np.nan, 49.99, 60.0]
+    fast = (stats.count_stats(t, y, times, 0.8), stats.intransit_stats(t, y, times, 0.8),
+            stats.snr_stats(t, y, 3.3, 0.1, 0.0, times, 0.8, np.array([5.0, 6.0])))
+    monkeypatch.setattr(stats, "_is_ascending", lambda t: False)
+    slow = (stats.count_stats(t, y, times, 0.8), stats.intransit_stats(t, y, times, 0.8),
+            stats.snr_stats(t, y, 3.3, 0.1, 0.0, times, 0.8, np.array([5.0, 6.0])))
+    assert fast[0] == slow[0]
+    for a, b in zip(fast[1] + fast[2], slow[1] + slow[2]):
+        np.testing.assert_array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))

@@ -204,49 +204,64 @@ def count_stats(t, y, transit_times, transit_duration_in_days):
     inside = after = before = 0
     d = transit_duration_in_days
     tmin, tmax = np.min(t), np.max(t)
+    ascending = _is_ascending(t)
+
+    def between(lo, hi):  # number of samples with lo < t < hi
+        if ascending:
+            return max(0, int(np.searchsorted(t, hi, side="left") - np.searchsorted(t, lo, side="right")))
+        return int(np.count_nonzero((t > lo) & (t < hi)))
+
     for mid in transit_times:
         a, b, c, e = mid - 1.5 * d, mid - 0.5 * d, mid + 0.5 * d, mid + 1.5 * d
         if a > tmin and e < tmax:
-            inside += int(np.count_nonzero((t > b) & (t < c)))
-            before += int(np.count_nonzero((t > a) & (t < b)))
-            after += int(np.count_nonzero((t > c) & (t < e)))
+            inside += between(b, c)
+            before += between(a, b)
+            after += between(c, e)
     return inside, after, before
 
 
-def _epoch_window(t, mid, d):
+def _is_ascending(t):
+    """Time stamps in non-decreasing order (the usual case): windows become binary searches."""
+    return bool(np.all(t[1:] >= t[:-1]))
+
+
+def _epoch_window(t, mid, d, ascending=False):
+    """Index of the samples with mid - d/2 < t < mid + d/2 (ascending order), None for a NaN epoch."""
     lo, hi = mid - 0.5 * d, mid + 0.5 * d
     if np.isnan(lo) or np.isnan(hi):
         return None
+    if ascending:  # the same samples in the same order as the mask below, found in O(log n)
+        start = int(np.searchsorted(t, lo, side="right"))
+        return slice(start, max(start, int(np.searchsorted(t, hi, side="left"))))
     return np.where(np.logical_and(t > lo, t < hi))
 
 
 def intransit_stats(t, y, transit_times, transit_duration_in_days):
     """Per-epoch depths/counts and the odd/even in-transit flux sets
     (stats.py:344-420)."""
-    odd = np.array([])
-    even = np.array([])
+    odd_parts, even_parts = [np.array([])], [np.array([])]
     n_epochs = len(transit_times)
     counts = np.zeros([n_epochs])
     depths = np.zeros([n_epochs])
     errors = np.zeros([n_epochs])
     m_odd = m_even = s_odd = s_even = np.nan
+    ascending = _is_ascending(t)
     for i, mid in enumerate(transit_times):
-        sel = _epoch_window(t, mid, transit_duration_in_days)
+        sel = _epoch_window(t, mid, transit_duration_in_days, ascending)
         flux = y[sel] if sel is not None else np.array([])
         n_in = np.size(flux)
         depths[i] = np.mean(flux) if n_in > 0 else np.nan
         errors[i] = np.std(flux) / np.sqrt(n_in) if n_in > 0 else np.nan
         counts[i] = n_in
-        if i % 2 == 0:
-            even = np.append(even, flux)
-        else:
-            odd = np.append(odd, flux)
-        if len(odd) > 0:
-            m_odd = np.mean(odd)
-            s_odd = np.std(odd) / len(odd) ** 0.5
-        if len(even) > 0:
-            m_even = np.mean(even)
-            s_even = np.std(even) / len(even) ** 0.5
+        (even_parts if i % 2 == 0 else odd_parts).append(flux)
+    # the reference re-evaluates these after every epoch (stats.py:399-408); only the last values survive
+    odd, even = np.concatenate(odd_parts), np.concatenate(even_parts)
+    if len(odd) > 0:
+        m_odd = np.mean(odd)
+        s_odd = np.std(odd) / len(odd) ** 0.5
+    if len(even) > 0:
+        m_even = np.mean(even)
+        s_even = np.std(even) / len(even) ** 0.5
     return m_odd, m_even, s_odd, s_even, odd, even, counts, depths, errors
 
 
@@ -261,8 +276,9 @@ def snr_stats(t, y, period, duration, T0, transit_times, transit_duration_in_day
     except Exception:
         pink = np.nan
     std = np.std(outside) if len(outside) > 0 else np.nan
+    ascending = _is_ascending(t)
     for i, mid in enumerate(transit_times):
-        sel = _epoch_window(t, mid, transit_duration_in_days)
+        sel = _epoch_window(t, mid, transit_duration_in_days, ascending)
         flux = y[sel] if sel is not None else np.array([])
         n_in = np.size(flux)
         mean_flux = np.mean(flux) if n_in > 0 else np.nan
