@@ -17,6 +17,7 @@ import json; d = json.load(open('$OUT/bench_${NAME}_$WL.json')); print('%-10s %-
   done
 }
 run main $PWD/tls_b200/libtlsb200.so cfg1
+shopt -s nullglob
 for LIBF in tls_b200/variants/lib_*.so; do
   V=$(basename $LIBF .so); V=${V#lib_}
   run $V $PWD/$LIBF cfg1
