@@ -1,0 +1,81 @@
+"""bench.py on the CPU: the reference arm's JSON line (the driver parses it), the silent exit of the other ranks,
+the roofline numerator (algorithmic bytes per period), and the refusal of the GPU arm to run
+without a device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def _bench(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(REPO, "bench.py")] + list(args), capture_output=True, text=True,
+                          env=e, cwd=REPO, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = _bench("--impl", "reference", "--steps", "1", "--warmup", "1", "--max-periods", "300")
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["unit"] == "periods/s" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("cfg1") and d["config"]["n_points"] == 4320
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "periods" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    out = _bench("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                 env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_gpu_arm_needs_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        return  # the GPU box runs the real thing
+    out = _bench("--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-secondary")
+    assert out.returncode != 0 and out.stdout.strip() == ""
+    assert "no CPU fallback" in out.stderr
+
+
+def test_algorithmic_bytes_of_cfg1():
+    """B(P) = 24 N + 8 (N+M) + sum_{W admissible} [8 (N+M) + 4 L_W] + 24: 1.10 MB per period at cfg-1 with 24.3
+    admissible widths on average, checked against a direct evaluation for a few periods."""
+    import bench
+
+    inp = bench.build_inputs("cfg1", 3)
+    assert len(inp.periods) == 9679 and len(inp.y) == 4320
+    total, mean_widths, M = bench.algorithmic_bytes(inp, inp.periods)
+    assert M == 518
+    assert abs(mean_widths - 24.25) < 0.05
+    assert abs(total / len(inp.periods) - 1.0978e6) < 1e3
+    # direct evaluation for single periods, widths filtered like core.py:143-156
+    from tls_b200.grid import T14
+
+    widths = np.asarray(inp.templates["width"])
+    lengths = np.asarray(inp.templates["length"])
+    N, span, prm = 4320, float(np.max(inp.t) - np.min(inp.t)), inp.params
+    for p in (inp.periods[0], inp.periods[4000], inp.periods[-1]):
+        dmax = T14(prm["R_star_max"], prm["M_star_max"], p, small=False)
+        dmin = T14(prm["R_star_min"], prm["M_star_min"], p, small=True)
+        corr = (span / p + 1) / (span / p)
+        lo, hi = np.floor(dmin * N), np.ceil(dmax * N * corr)
+        want = 24.0 * N + 8.0 * (N + M) + 24.0
+        for w in np.unique(widths):
+            if lo <= w <= hi:
+                want += 8.0 * (N + M) + 4.0 * lengths[int(np.argmax(widths == w))]
+        got, _, _ = bench.algorithmic_bytes(inp, [p])
+        assert got == want
