@@ -60,3 +60,32 @@ def test_null_arguments_are_rejected_without_touching_cuda():
     assert L.tlsb_set_plan_mode(None, 0) == -1
     assert L.tlsb_destroy(None) == 0
     assert L.tlsb_last_launch_count(None) == 0
+
+
+def test_integration_md_stub_runs_as_written(has_cuda):
+    """The ctypes stub INTEGRATION.md §1 shows a TLS maintainer, executed verbatim (only the library path is
+    made absolute): it must marshal the reference's own arguments (ragged lc_arr, structured overview) and, on a
+    machine without a GPU, surface the library's refusal as a RuntimeError; with a GPU it must return what
+    tls_b200.native returns."""
+    text = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes, numpy\n.*?)```", text, flags=re.S).group(1)
+    block = block.replace('ctypes.CDLL("libtlsb200.so")', "ctypes.CDLL(%r)" % native.library_path())
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    g = load_search_golden("tiny")
+    tp = g["templates"]
+    lc_arr = np.empty(len(tp["length"]), dtype=object)
+    for r in range(len(lc_arr)):
+        lc_arr[r] = np.array(tp["signal"][tp["offset"][r]: tp["offset"][r] + tp["length"][r]])
+    overview = np.zeros(len(lc_arr), dtype=[("duration", "f8"), ("width_in_samples", "i8"), ("overshoot", "f8")])
+    overview["width_in_samples"], overview["overshoot"] = tp["width"], tp["overshoot"]
+    call = lambda: ns["search_periods"](g["periods"], g["t"], g["y"], g["dy"], lc_arr, overview, **g["params"])
+    if not has_cuda:
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+        return
+    chi2, row, depth = call()
+    want = native.search_periods(g["t"], g["y"], g["dy"], g["periods"], g["templates"], g["params"])
+    np.testing.assert_array_equal(chi2, want[0])
+    np.testing.assert_array_equal(row, want[1])
+    np.testing.assert_array_equal(depth, want[2])
