@@ -106,6 +106,43 @@ def algorithmic_bytes(inp, periods):
     return total, widths_total / max(1, len(periods)), M
 
 
+def tap_work(inp, periods, sample=24):
+    """the data-dependent part of the work, counted on the actual input.  For an evenly
+    spread sample of the periods: T(P) = sum over admissible widths W of C_W * L_W, where C_W is the number
+    of window offsets i (i % stride == 0, core.py:50-55) whose mean depth passes the gate of core.py:58.
+    One tap is one fp64 FMA of the search kernel when all weights are equal (two with per-point dy).
+    Returns (mean taps per period, mean gate pass rate, periods sampled)."""
+    uniq, L, N, span, prm, T14 = admissible_ranges(inp)
+    M = int(uniq.max())
+    M += M % 2
+    margin, depth_min = prm["T0_fit_margin"], prm["transit_depth_min"]
+    periods = np.asarray(periods, dtype=float)
+    picks = periods[np.linspace(0, len(periods) - 1, min(sample, len(periods))).astype(int)]
+    d_all = 1.0 - np.asarray(inp.y, dtype=float)
+    taps, passed, offsets = 0.0, 0, 0
+    for p in picks:
+        x = np.asarray(inp.t, dtype=float) * (1.0 / p)
+        order = np.argsort(x - np.floor(x), kind="mergesort")
+        d = d_all[order]
+        cs = np.concatenate([[0.0], np.cumsum(np.concatenate([d, d[:M]]))])
+        dmax = T14(prm["R_star_max"], prm["M_star_max"], p, small=False)
+        dmin = T14(prm["R_star_min"], prm["M_star_min"], p, small=True)
+        corr = (span / p + 1) / (span / p)
+        lo, hi = np.floor(dmin * N), np.ceil(dmax * N * corr)
+        for W, Lw in zip(uniq, L):
+            if W < lo or W > hi:
+                continue
+            stride = 1
+            if margin > 0 and W > margin:
+                stride = max(1, int(W / (1 / margin)))
+            mean = (cs[W:] - cs[:-W])[::stride] / W
+            n_pass = int(np.count_nonzero(mean > depth_min))
+            taps += float(n_pass) * float(Lw)
+            passed += n_pass
+            offsets += len(mean)
+    return taps / len(picks), passed / max(1, offsets), len(picks)
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
@@ -391,6 +428,22 @@ def run_b200(args):
                      "streaming": "streaming (per-CTA L2 scratch)"}[job.searcher.path],
             "layout": job.searcher.layout,
         }
+        try:  # the second ceiling: fp64 FMAs of the tap loop against the fp64 pipe
+            taps, pass_rate, n_sampled = tap_work(inp, job.local_periods)
+            prop = torch.cuda.get_device_properties(local)
+            clk = sampler.summary().get("sm_mhz") or sampler.summary().get("sm_max_mhz") or 1965.0
+            fma_per_tap = 1 if bool(np.all(inp.dy == inp.dy[0])) else 2
+            peak_fma = prop.multi_processor_count * 64 * float(clk) * 1e6  # 64 fp64 FMA per clock per SM
+            ach_fma = taps * fma_per_tap * P_rank / (k_ms * 1e-3)
+            roofline["fp64"] = {
+                "taps_per_period": taps, "gate_pass_rate": pass_rate, "periods_sampled": n_sampled,
+                "fma_per_tap": fma_per_tap, "achieved": ach_fma / 1e12, "peak": peak_fma / 1e12, "unit": "TFMA/s",
+                "frac": ach_fma / peak_fma,
+                "peak_source": "%d SMs x 64 fp64 FMA/clk x %.0f MHz (SM clock sampled during the timed region)" % (
+                    prop.multi_processor_count, float(clk)),
+            }
+        except Exception as exc:  # never lose the line over the secondary figure
+            roofline["fp64"] = {"error": str(exc)[:200]}
         traffic_file = os.path.join(REPO, "profiles", "traffic_%s.json" % args.workload)
         if os.path.exists(traffic_file):
             try:

@@ -79,3 +79,34 @@ def test_algorithmic_bytes_of_cfg1():
                 want += 8.0 * (N + M) + 4.0 * lengths[int(np.argmax(widths == w))]
         got, _, _ = bench.algorithmic_bytes(inp, [p])
         assert got == want
+
+
+def test_tap_work_counts_the_gate_survivors():
+    """bench.tap_work: T(P) = sum_W C_W * L_W on the actual input (6.3e5 taps per period at
+    cfg-1 / 50 ppm, ten times that at 500 ppm), checked against a direct loop over offsets for one period."""
+    import bench
+
+    inp = bench.build_inputs("cfg1", 3)
+    taps, rate, n = bench.tap_work(inp, inp.periods)
+    assert n == 24 and 5.5e5 < taps < 7.0e5 and 0.08 < rate < 0.14
+    noisy = bench.build_inputs("cfg1_500ppm", 3)
+    assert 8 < bench.tap_work(noisy, noisy.periods)[0] / taps < 12
+    # one period, by the definition (core.py:50-58), on a short curve
+    small = bench.build_inputs("cfg1", 3)
+    p = float(small.periods[len(small.periods) // 2])
+    got = bench.tap_work(small, [p])[0]
+    uniq, L, N, span, prm, T14 = bench.admissible_ranges(small)
+    M = int(uniq.max()) + int(uniq.max()) % 2
+    x = small.t * (1.0 / p)
+    flux = small.y[np.argsort(x - np.floor(x), kind="mergesort")]
+    patched = np.concatenate([flux, flux[:M]])
+    lo = np.floor(T14(prm["R_star_min"], prm["M_star_min"], p, small=True) * N)
+    hi = np.ceil(T14(prm["R_star_max"], prm["M_star_max"], p, small=False) * N * ((span / p + 1) / (span / p)))
+    want = 0
+    for W, Lw in zip(uniq, L):
+        if lo <= W <= hi:
+            xth = max(1, int(W / (1 / prm["T0_fit_margin"]))) if W > prm["T0_fit_margin"] > 0 else 1
+            for i in range(0, len(patched) - W + 1):
+                if i % xth == 0 and 1 - np.mean(patched[i:i + W]) > prm["transit_depth_min"]:
+                    want += Lw
+    assert abs(got - want) <= 1e-3 * want  # window means by cumulative sums vs direct means: a handful of ties at most
