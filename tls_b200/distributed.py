@@ -90,7 +90,9 @@ class ShardedSearch(object):
     """The period search of one light curve on ``world`` GPUs, one process per GPU.
 
     ``step(stream)`` launches this rank's share (plan + search kernels) on ``stream`` and, when
-    ``world > 1``, the all-gather of the records behind it; everything is asynchronous."""
+    ``world > 1``, the all-gather of the records behind it; everything is asynchronous.  With
+    ``world > 1`` pass torch's CURRENT stream of the device (or nothing, on the default stream): the
+    collective is ordered behind the current stream, not behind an arbitrary one."""
 
     def __init__(self, t, y, dy, templates, params, periods, rank=0, world=1, device=0, dist=None):
         import torch
