@@ -189,3 +189,88 @@ def test_template_bank_is_bit_identical(ref):
                 np.testing.assert_array_equal(oa[f], ob[f])
             for x, z in zip(la, lb):
                 np.testing.assert_array_equal(x, z)
+
+
+def test_oracle_against_the_numba_search_on_random_inputs(ref):
+    """Beyond the committed goldens: the C oracle (oracle/tls_oracle.c) against the reference's own numba
+    ``core.search_period`` (core.py:96-188) on random light curves — irregular and unsorted time stamps, ties,
+    per-point dy, every T0_fit_margin regime, several gates — rows exact, chi2 / depth to 1e-9."""
+    from transitleastsquares.core import search_period
+
+    from oracle import oracle
+    from tls_b200 import transitleastsquares as mine
+
+    rng = np.random.RandomState(11)
+    checked = 0
+    for case in range(30):
+        n = int(rng.choice([60, 150, 400, 900]))
+        span = float(rng.choice([8.0, 27.0, 90.0]))
+        t = np.sort(rng.uniform(0.5, 0.5 + span, n)) if case % 2 else np.linspace(0.5, 0.5 + span, n)
+        if case % 5 == 0:
+            t = np.round(t, 1)  # ties
+        if case % 4 == 3:
+            t = t[rng.permutation(n)]  # unsorted
+        ppm = float(rng.choice([50e-6, 500e-6, 3e-3]))
+        y = 1 + rng.normal(0, ppm, n)
+        per, dur = rng.uniform(1.0, span / 3), rng.uniform(0.05, 0.3)
+        y[np.abs((t - 0.7) % per) < dur] -= rng.uniform(2, 8) * ppm
+        dy = None if case % 3 else ppm * rng.uniform(0.5, 2.0, n)
+        kw = dict(T0_fit_margin=float(rng.choice([0.0, 0.01, 0.1])), transit_depth_min=float(rng.choice([10e-6, 1e-4, 2e-3])),
+                  oversampling_factor=int(rng.choice([1, 3])), duration_grid_step=float(rng.choice([1.1, 1.3])))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                inp = mine(t, y, dy, verbose=False).prepare(verbose=False, **kw)
+            except ValueError:
+                continue
+        periods = inp.periods[np.linspace(0, len(inp.periods) - 1, min(25, len(inp.periods))).astype(int)]
+        chi2, row, depth = oracle.search_periods_c(inp.t, inp.y, inp.dy, periods, inp.templates, inp.params)
+        for k, p in enumerate(periods):
+            out = search_period(p, inp.t, inp.y, inp.dy, lc_arr=inp.lc_arr, lc_cache_overview=inp.overview, **inp.params)
+            assert int(out[2]) == int(row[k]), (case, p, out, chi2[k], row[k])
+            if np.isfinite(out[1]):
+                np.testing.assert_allclose(chi2[k], out[1], rtol=1e-9)
+                np.testing.assert_allclose(depth[k], out[3], rtol=1e-9, atol=1e-15)
+            else:
+                assert chi2[k] == out[1]
+            checked += 1
+    assert checked >= 400
+
+
+def test_oracle_spectra_and_t0_fit_against_the_reference_on_random_inputs(ref):
+    """oracle.spectra_numpy vs stats.spectra (stats.py:105-132) and oracle.final_T0_fit_numpy vs
+    stats.final_T0_fit (stats.py:135-204) beyond the goldens: short and long chi2 rows (with and without the
+    median detrending), inf entries, every oversampling; T0 of random templates, margins and periods."""
+    from transitleastsquares import stats as rs
+
+    from oracle import oracle
+
+    rng = np.random.RandomState(5)
+    for P, ov in ((40, 1), (181, 1), (182, 1), (183, 1), (600, 2), (1500, 3), (3000, 5), (547, 3)):
+        chi2 = 1000 - rng.rand(P) * 30
+        chi2[rng.randint(P)] -= 200
+        if P % 2:
+            chi2[rng.randint(P)] = np.inf
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = rs.spectra(chi2.copy(), ov)
+            got = oracle.spectra_numpy(chi2.copy(), ov)
+        for a, b in zip(want, got):
+            np.testing.assert_allclose(np.asarray(b, dtype=float), np.asarray(a, dtype=float), rtol=1e-12, atol=1e-12, equal_nan=True)
+    for case in range(10):
+        n = int(rng.choice([200, 500, 1200]))
+        t = np.sort(rng.uniform(1.0, 40.0, n)) if case % 2 else np.linspace(1.0, 40.0, n)
+        y = 1 + rng.normal(0, 2e-4, n)
+        period = float(rng.uniform(1.5, 12.0))
+        L = int(rng.randint(5, 40))
+        signal = 1 - 0.5 * np.sin(np.linspace(0, np.pi, L)) ** 2 * 1e-3
+        depth = 1 - rng.uniform(1e-4, 2e-3)
+        y[np.abs((t - 2.2) % period) < 0.15] -= 1e-3
+        margin = float(rng.choice([0.0, 0.01, 0.1, 1.0]))
+        dy = np.full(n, np.std(y))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = rs.final_T0_fit(signal=signal.copy(), depth=depth, t=t, y=y, dy=dy.copy(), period=period,
+                                   T0_fit_margin=margin, show_progress_bar=False, verbose=False)
+            got = oracle.final_T0_fit_numpy(signal.copy(), depth, t, y, dy.copy(), period, margin)[0]
+        assert got == want, (case, got, want)
