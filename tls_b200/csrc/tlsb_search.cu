@@ -691,7 +691,7 @@ __device__ __forceinline__ void block_min(const WidthRec &wr, const double *cs, 
 }
 
 template <int kT, bool kResident, bool kUniformW, int kBlock>
-__global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
+__global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
 {
     constexpr int kW = kT / 32;
     constexpr int kTile = tile_size(kBlock);
@@ -1789,7 +1789,13 @@ Layout choose_layout(const tlsb_handle *h)
     const int kb_pref = (h->uniform_w && !(kbe && std::atoi(kbe) == 5)) ? 7 : 5;
     best.kb = kb_pref;
     if (N < 65536 && h->path_mode <= 1) {
-        const int tries[2][2] = {{256, 2}, {512, 1}};
+        int tries[2][2] = {{256, 2}, {512, 1}};
+        // experiments: TLSB_THREADS=320 (or 384) -> two CTAs of that size per SM at 96 (80) registers per thread, i.e.
+        // 20 (24) warps per SM instead of 16; pair it with TLSB_BLOCK=5.  Equal weights only.
+        if (const char *te = std::getenv("TLSB_THREADS")) {
+            const int tt = std::atoi(te);
+            if ((tt == 320 || tt == 384) && h->uniform_w) tries[0][0] = tt;
+        }
         const int qcaps[3] = {4096, 3584, 3072};
         for (const auto &t : tries) {
             for (int qcap : qcaps) {
@@ -2014,6 +2020,12 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
             if (uni && lay.kb == 7) TLSB_GO((tlsb_search_kernel<256, true, true, 7>));
             else if (uni) TLSB_GO((tlsb_search_kernel<256, true, true, 5>));
             else TLSB_GO((tlsb_search_kernel<256, true, false, 5>));
+        } else if (lay.threads == 320) {  // experiments (TLSB_THREADS)
+            if (lay.kb == 7) TLSB_GO((tlsb_search_kernel<320, true, true, 7>));
+            else TLSB_GO((tlsb_search_kernel<320, true, true, 5>));
+        } else if (lay.threads == 384) {
+            if (lay.kb == 7) TLSB_GO((tlsb_search_kernel<384, true, true, 7>));
+            else TLSB_GO((tlsb_search_kernel<384, true, true, 5>));
         } else {
             if (uni && lay.kb == 7) TLSB_GO((tlsb_search_kernel<512, true, true, 7>));
             else if (uni) TLSB_GO((tlsb_search_kernel<512, true, true, 5>));
