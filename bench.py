@@ -456,6 +456,11 @@ def run_b200(args):
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d of %d periods (evenly spread) of the same workload, C restatement of "
                              "core.search_period under oracle/, OpenMP over periods" % (n, P_rank)}
+            try:  # the 1-core figure beside the all-cores one (about 3 s more)
+                rate1, n1, _ = cpu_sample(inp, job.local_periods, min(3.0, args.cpu_seconds), threads=1)
+                cpu["serial"] = {"value": rate1, "unit": UNIT, "cores": 1, "sample": "%d periods" % n1}
+            except Exception as exc:
+                cpu["serial"] = {"error": str(exc)[:200]}
 
     secondary = None
     if rank == 0 and n_gpus == 1 and not args.no_secondary and not args.max_periods:
