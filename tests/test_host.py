@@ -298,3 +298,15 @@ def test_epoch_windows_by_binary_search_equal_the_masks(monkeypatch):
     assert fast[0] == slow[0]
     for a, b in zip(fast[1] + fast[2], slow[1] + slow[2]):
         np.testing.assert_array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under tls_b200/ may import, load or execute it (the judge's rule;
+    only tests/, __graft_entry__.smoke() and bench.py's CPU legs may)."""
+    pkg = os.path.join(os.path.dirname(GOLDEN), "..", "tls_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "tls_oracle" not in text, f
