@@ -11,11 +11,14 @@ for spec in sys.argv[1:]:
     name, _, defs = spec.partition(":")
     defines = [d for d in defs.split(",") if d]
     out = os.path.join(REPO, "tls_b200", "variants", "lib_%s.so" % name)
-    cmd = [build.nvcc_path()] + build.NVCC_FLAGS + ["-Xptxas", "-v"] + ["-D" + d for d in defines] + ["-o", out] + build.SRC
-    env = dict(os.environ); env.pop("CC", None); env.pop("CXX", None)
-    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if proc.returncode:
-        print(name, "FAILED\n", proc.stderr[-2000:]); continue
+    import contextlib, io
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            build.build(force=True, verbose=True, defines=defines, out=out)
+    except RuntimeError as exc:
+        print(name, "FAILED\n", str(exc)[-2000:]); continue
+    class proc: stderr = buf.getvalue()
     lines = proc.stderr.splitlines()
     for i, l in enumerate(lines):
         if "Compiling entry function" in l and re.search(r"search_kernelILi256ELb1ELb1ELi[79]|search_tiled_kernelILi512ELb1ELi[579]|search_kernelILi256ELb1ELb0ELi5", l):

@@ -11,12 +11,14 @@ def kernels(path):
     out = {}
     for part in re.split(r"\n\s*Function : ", txt)[1:]:
         name, _, body = part.partition("\n")
-        out[name.strip()] = body
+        m = re.search(r"\d+(tlsb_\w+?_kernel)(I.*?EEE)?", name.strip())  # kernel + template arguments, without the
+        key = m.group(1) + (m.group(2) or "") if m else name.strip()       # per-translation-unit namespace hash
+        out[key] = re.findall(r"/\*[0-9a-f]{4,}\*/\s+(.*?;)", body)        # the instruction stream only
     return out
 
 
 a, b = kernels(sys.argv[1]), kernels(sys.argv[2])
-short = lambda k: re.sub(r"^_ZN\d+_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]+\d\d", "", k)[:90]
+short = lambda k: k[:90]
 changed = [k for k in a if k in b and a[k] != b[k]]
 print("%d kernels in %s, %d in %s" % (len(a), sys.argv[1], len(b), sys.argv[2]))
 print("identical: %d" % sum(1 for k in a if k in b and a[k] == b[k]))

@@ -8,14 +8,18 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "tlsb_search.cu"), os.path.join(HERE, "csrc", "tlsb_spectra.cu")]
-HEADERS = [os.path.join(os.path.dirname(HERE), "include", "tlsb200.h"), os.path.join(HERE, "csrc", "tlsb_internal.h")]
+SRC = [os.path.join(HERE, "csrc", f) for f in (
+    "tlsb_host.cu", "tlsb_resident.cu", "tlsb_tiled.cu", "tlsb_aux_kernels.cu", "tlsb_spectra.cu")]
+HEADERS = [os.path.join(os.path.dirname(HERE), "include", "tlsb200.h"), os.path.join(HERE, "csrc", "tlsb_internal.h"),
+           os.path.join(HERE, "csrc", "tlsb_device.cuh")]
+OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtlsb200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def nvcc_path():
@@ -32,21 +36,35 @@ def is_stale():
     return any(os.path.getmtime(p) > built for p in SRC + HEADERS + [os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False, defines=(), out=None):
-    """Compile if the library is missing or older than its sources; returns the path.
-    `defines` / `out` build an experimental variant next to the product library (scripts/gpu_variants.sh)."""
-    if out is None and not force and not is_stale():
-        return LIB
-    out = out or LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-o", out] + SRC
+def _run(cmd):
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports a gcc wrapper that nvcc must not pick up
     env.pop("CXX", None)
     proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return proc.stderr
+
+
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile if the library is missing or older than its sources; returns the path.
+    One nvcc -c per translation unit (in parallel), then one link.
+    `defines` / `out` build an experimental variant next to the product library (scripts/gpu_variants.sh)."""
+    if out is None and not force and not is_stale():
+        return LIB
+    out = out or LIB
+    tag = os.path.splitext(os.path.basename(out))[0]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = nvcc_path()
+    objs = [os.path.join(OBJ_DIR, "%s_%s.o" % (tag, os.path.splitext(os.path.basename(src))[0])) for src in SRC]
+    cmds = [[nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-c", "-o", obj, src]
+            for src, obj in zip(SRC, objs)]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(cmds)) as pool:
+        logs = list(pool.map(_run, cmds))
+    _run([nvcc] + LINK_FLAGS + ["-o", out] + objs)
     if verbose:
-        print(proc.stderr)
+        print("".join(logs))
     return out
 
 

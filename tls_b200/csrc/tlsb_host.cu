@@ -1,0 +1,1197 @@
+// tlsb_host.cu — the host side of libtlsb200.so: the search handle (device buffers, light curves, template bank,
+// period grid), the choice of the on-chip layout, the plan/search/repair sequencing and the C ABI of
+// include/tlsb200.h.  The kernels live in tlsb_resident.cu, tlsb_tiled.cu, tlsb_aux_kernels.cu and
+// tlsb_spectra.cu; this file launches them through the tlsb::launch_* functions of tlsb_internal.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/tlsb200.h"
+#include "tlsb_internal.h"
+
+namespace tlsb {
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_error = msg;
+    return code;
+}
+}  // namespace tlsb
+
+namespace {
+using namespace tlsb;
+using tlsb::fail;
+using tlsb::g_error;
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(TLSB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// How one search is laid out on the SM (chosen per search from N, M, the bank and the device).
+struct Layout {
+    bool resident = false;
+    bool tiled = false;    // not resident: phase B from shared-memory chunks staged by bulk async copies
+    int chunk = 0;         // doubles per staged array
+    int kb = 5;            // candidates per lane (block size R)
+    int seg_cap = 0;       // on-chip sort of the tiled path: segment capacity (0 = off) and count
+    int n_seg = 0;
+    int n_tiled = 0;       // tiled path: widths [0, n_tiled) fit a chunk with enough start offsets left
+    int threads = 256;     // 256 (two CTAs per SM) or 512 (one)
+    int ctas_per_sm = 2;
+    int qcap = 4096;
+    int NB = 0;
+    size_t smem = 0;
+    size_t scratch_per_cta = 0;
+};
+
+}  // namespace
+
+struct tlsb_handle {
+    int device = 0;
+    int num_sms = 0;
+    size_t max_smem = 0;     // per CTA (opt-in)
+    size_t smem_per_sm = 0;
+    // light curve
+    int N = 0;
+    double span = 0.0;
+    bool uniform_w = false;  // every dy identical (dy=None -> std(y) everywhere, validate.py:39-40)
+    double w0 = 0.0;         // 1/dy^2 in that case
+    DevBuf t, y, dy, dval, wval;   // n_curves light curves back to back (t: one copy when shared)
+    bool have_lc = false;
+    int n_curves = 1;              // tlsb_set_lightcurves
+    bool shared_t = true;          // every curve uses the same time stamps
+    int cur = 0;                   // the curve tlsb_search_async / tlsb_final_t0_fit work on
+    std::vector<double> c_span, c_w0;
+    std::vector<char> c_uniform;
+    bool dev_plan_valid = false;   // ulo/uhi/order on the device match (periods, templates, span)
+    double dev_plan_span = 0.0;
+    DevBuf asc_order, brec, bchi, bSR, bpr, bpw, bscal, bamax;  // batch pipeline
+    std::vector<int> h_asc_order;
+    bool asc_valid = false;        // asc_order matches the current periods (made on demand by the batch call)
+    bool defer_sync = false;       // one-shot call: the caller's buffers outlive the whole call, setters need not wait
+    std::vector<double> h_tq;      // host copy of tq (keeps the upload source alive without a synchronisation)
+    // templates
+    tlsb_params prm{};
+    int nU = 0, M = 0, pad = 0;
+    std::vector<WidthRec> recs;   // unique widths, ascending
+    DevBuf tq, d_rec;
+    bool have_tp = false;
+    bool recs_stale = true;       // ncand/tiles/cum depend on N + M
+    int rec_kb = 0;               // ... and on the block size R the tiles were counted for
+    // periods
+    int P = 0;
+    std::vector<double> h_periods;
+    DevBuf periods, ulo, uhi, order, bin_of;
+    bool have_periods = false;
+    int path_mode = 0;            // 0 auto, 1 resident, 2 tiled, 3 streaming (tlsb_set_path)
+    int chunk_cap = 0;            // tiled path: cap of the chunk capacity in doubles (tests), 0 = none
+    int plan_mode = 0;            // 0 device plan, 1 exact host plan, 2 device plan flagging every period (tests)
+    bool host_plan_valid = false;
+    // outputs / scheduling / scratch
+    DevBuf out, counter, scratch, plan_bins, unsure;
+    // final_T0_fit
+    DevBuf t0_trials, t0_model, t0_resid;
+    bool t0_resident = false;
+    double t0_ms = 0.0;
+    // bookkeeping
+    int64_t launches = 0;
+    int64_t fallbacks = 0;        // searches redone completely with the exact host plan
+    int64_t repairs = 0;          // periods re-searched because their exact limits differed from the device's
+    Layout layout;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+namespace {
+
+int upload(DevBuf &buf, const void *src, size_t bytes, cudaStream_t s = nullptr)
+{
+    if (buf.ensure(bytes ? bytes : 8)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+// candidates and scheduler tiles per width (depend on N + M and on the block size R), wide -> narrow prefix
+int refresh_records(tlsb_handle *h, int kb, cudaStream_t s)
+{
+    const int kTile = tile_size(kb);
+    int cum = 0;
+    for (int u = h->nU - 1; u >= 0; --u) {
+        WidthRec &wr = h->recs[u];
+        wr.ncand = (h->N + h->M - wr.W) / wr.X + 1;  // offsets i = c*X, i in [0, N+M-W]
+        wr.tiles = (wr.ncand + kTile - 1) / kTile;
+        wr.cum = cum;
+        cum += wr.tiles;
+    }
+    int rc;
+    if ((rc = upload(h->d_rec, h->recs.data(), sizeof(WidthRec) * (size_t)h->nU, s))) return rc;  // ordered behind earlier launches on s
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(s));  // h->recs itself stays alive and is only rewritten here
+    h->recs_stale = false;
+    h->rec_kb = kb;
+    h->host_plan_valid = false;
+    h->dev_plan_valid = false;
+    return 0;
+}
+
+// The exact plan on the host (libm pow, bit-identical to the reference's T14): admissible
+// unique-width range per period (core.py:143-156) + processing order.  Used when the device
+// plan reports a limit too close to an integer to trust its pow(), and by plan_mode 1.
+void exact_range(const tlsb_handle *h, double period, int *lo, int *hi)
+{
+    const double dmax = t14_fraction(h->prm.R_star_max, h->prm.M_star_max, period, false);
+    const double dmin = t14_fraction(h->prm.R_star_min, h->prm.M_star_min, period, true);
+    const double naive = h->span / period;
+    const double corr = (naive + 1) / naive;
+    const double wmin_f = std::floor(dmin * (double)h->N);
+    const double wmax_f = std::ceil(dmax * (double)h->N * corr);
+    int a = 0;
+    while (a < h->nU && (double)h->recs[a].W < wmin_f) ++a;
+    int b = h->nU;
+    while (b > a && (double)h->recs[b - 1].W > wmax_f) --b;
+    if (!(wmax_f >= wmin_f)) b = a;  // NaN / empty
+    *lo = a;
+    *hi = b;
+}
+
+int host_plan(tlsb_handle *h)
+{
+    const int P = h->P;
+    std::vector<int> lo(P), hi(P), order(P);
+    for (int p = 0; p < P; ++p) exact_range(h, h->h_periods[p], &lo[p], &hi[p]);
+    std::iota(order.begin(), order.end(), 0);
+    // most expensive first: cost ~ number of candidate tiles in the admissible range
+    auto cost = [&](int p) {
+        return hi[p] > lo[p] ? h->recs[lo[p]].cum + h->recs[lo[p]].tiles - h->recs[hi[p] - 1].cum : 0;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost(x) > cost(y); });
+    int rc;
+    if ((rc = upload(h->ulo, lo.data(), sizeof(int) * P))) return rc;
+    if ((rc = upload(h->uhi, hi.data(), sizeof(int) * P))) return rc;
+    if ((rc = upload(h->order, order.data(), sizeof(int) * P))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(nullptr));  // the vectors above go out of scope
+    h->host_plan_valid = true;
+    h->dev_plan_valid = false;
+    return 0;
+}
+
+size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+size_t tail_bytes(int nU, int threads)
+{
+    const int kW = threads / 32;
+    return (size_t)nU * sizeof(WidthRec) + (size_t)(2 * kW + 2) * 8 + (size_t)2 * kW * 4 + 16;
+}
+
+size_t resident_smem_bytes(int N, int M, int pad, int nU, bool uniform, int qcap, int threads)
+{
+    const size_t NM = (size_t)N + M, NMP = NM + pad;
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
+    return cs + (uniform ? 1 : 2) * NMP * 8 + (size_t)qcap * 8 + tail_bytes(nU, threads);
+}
+
+// Pick the on-chip layout: two 256-thread CTAs per SM when two folded curves fit the SM's
+// shared memory, else one 512-thread CTA, else the streaming path (global scratch in L2).
+Layout choose_layout(const tlsb_handle *h)
+{
+    Layout best;
+    const int N = h->N;
+    // block size R: 7 candidates per lane when all weights are equal, 5 with two correlations (registers)
+    const char *kbe = std::getenv("TLSB_BLOCK");  // experiments: force 5
+    const int kb_pref = (h->uniform_w && !(kbe && std::atoi(kbe) == 5)) ? 7 : 5;
+    best.kb = kb_pref;
+    if (N < 65536 && h->path_mode <= 1) {
+        const int tries[2][2] = {{256, 2}, {512, 1}};
+        const int qcaps[3] = {4096, 3584, 3072};
+        for (const auto &t : tries) {
+            for (int qcap : qcaps) {
+                const size_t bytes = resident_smem_bytes(N, h->M, h->pad, h->nU, h->uniform_w, qcap, t[0]);
+                if (bytes > h->max_smem) continue;
+                if ((bytes + 1024) * (size_t)t[1] > h->smem_per_sm) continue;
+                // the sort borrows the queue: H (NB+1 ints) + sid (N u16)
+                const long long room = (long long)qcap * 8 - 2LL * N - 8;
+                if (room < 4LL * 64) continue;
+                int NB = (int)std::min<long long>(N, room / 4 - 1);
+                if (NB < N / 16) continue;
+                best.resident = true;
+                best.threads = t[0];
+                best.ctas_per_sm = t[1];
+                best.qcap = qcap;
+                best.NB = NB;
+                best.smem = bytes;
+                return best;
+            }
+        }
+    }
+    // Tiled path: phase A in global scratch, phase B from staged chunks.  The chunk must hold the
+    // widest window of the bank plus a useful number of start offsets.
+    const size_t NM = (size_t)N + h->M, NMP = NM + h->pad;
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
+    const size_t nmp_even = (NMP + 1) & ~(size_t)1;
+    const int narr = h->uniform_w ? 2 : 3;
+    int need_max = 0, need5 = 0;
+    for (const WidthRec &wr : h->recs) {
+        need_max = std::max(need_max, window_need(wr.W, wr.X, kb_pref));
+        need5 = std::max(need5, window_need(wr.W, wr.X, 5));
+    }
+    const char *force = std::getenv("TLSB_TILED");  // "0": never, "256"/"512": force that CTA size (experiments)
+    const int forced = force ? std::atoi(force) : -1;
+    if (forced != 0 && h->path_mode != 3) {
+        const int tries[2][3] = {{256, 2, 3072}, {512, 1, 4096}};  // threads, CTAs per SM, queue entries
+        for (const auto &t : tries) {
+            if (forced > 0 && forced != t[0]) continue;
+            size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);
+            if (const char *cap = std::getenv("TLSB_SMEM_KB"))  // experiments: leave part of the SM's 256 KB to L1
+                per_cta = std::min(per_cta, (size_t)std::atoi(cap) * 1024 / (size_t)t[1]);
+            const size_t fixed = (size_t)t[2] * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 + (size_t)(kMaxSegments + 2) * 4;
+            if (per_cta <= fixed) continue;
+            long long C = (long long)(((per_cta - fixed) / (8 * (size_t)narr)) & ~(size_t)1);
+            const bool exact_cap = h->chunk_cap < 0;  // tests: cap the chunk exactly; widths that do not fit take the L2 pass
+            if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~1LL);
+            if (exact_cap) C = std::min<long long>(C, (long long)(-h->chunk_cap) & ~1LL);
+            int kb = kb_pref, n_tiled = h->nU;
+            long long TP = 0;
+            bool fits = C > need5;
+            if (fits) {
+                TP = C - need_max;
+                if (kb > 5 && 5 * TP < 4 * (C - need5)) {  // the longer overshoot would cost > 20 % of the offsets per chunk
+                    kb = 5;
+                    TP = C - need5;
+                }
+                if (TP < (h->chunk_cap != 0 ? 2 : 256)) fits = false;
+                // One big CTA per SM: a width that would leave less than half of a chunk as start offsets (every sample
+                // staged more than twice) takes the L2 pass even though it fits (cfg-2: 22.0 -> 20.7 ms per 6,000
+                // periods with 7 of 66 widths moved; TLSB_TP_FRAC = percent, experiments).
+                if (fits && t[1] == 1 && h->chunk_cap == 0) {
+                    const char *fr = std::getenv("TLSB_TP_FRAC");
+                    const long long tp_min = C * (fr ? std::atoi(fr) : 50) / 100;
+                    int n = 0;
+                    for (const WidthRec &wr : h->recs) {
+                        if (C - window_need(wr.W, wr.X, kb) < tp_min) break;
+                        ++n;
+                    }
+                    if (4 * n >= 3 * h->nU && n < h->nU) {
+                        n_tiled = n;
+                        TP = C - window_need(h->recs[(size_t)n - 1].W, h->recs[(size_t)n - 1].X, kb);
+                    }
+                }
+            }
+            if (!fits) {
+                // The widest windows leave (almost) no start offsets in a chunk - e.g. three staged arrays for a
+                // 4-year curve with unequal weights.  One big CTA per SM then tiles the widths that do fit and
+                // searches the few widest ones straight from its L2 scratch (kernel: uT).
+                if (t[1] != 1 && !exact_cap) continue;
+                kb = 5;
+                const long long tp_min = exact_cap ? 64 : std::max<long long>(1024, C / 2);
+                n_tiled = 0;
+                for (const WidthRec &wr : h->recs) {
+                    if (C - window_need(wr.W, wr.X, 5) < tp_min) break;
+                    ++n_tiled;
+                }
+                if (n_tiled < 1 || (!exact_cap && 4 * n_tiled < 3 * h->nU)) continue;
+                TP = C - window_need(h->recs[(size_t)n_tiled - 1].W, h->recs[(size_t)n_tiled - 1].X, 5);
+            } else if (h->chunk_cap == 0 && t[1] == 2 && forced < 0 && (TP < 2048 || 5 * TP < 3 * C)) {
+                continue;  // two CTAs per SM only when most of a chunk is start offsets (halo below ~40 %); one big CTA otherwise
+            }
+            best.resident = false;
+            best.tiled = true;
+            best.kb = kb;
+            best.threads = t[0];
+            best.ctas_per_sm = t[1];
+            best.qcap = t[2];
+            best.chunk = (int)C;
+            best.n_tiled = n_tiled;
+            best.NB = (int)std::min<long long>(N, (long long)narr * C * 2 - 2);
+            best.smem = (size_t)t[2] * 8 + (size_t)narr * (size_t)C * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 +
+                        (size_t)(kMaxSegments + 2) * 4;
+            best.scratch_per_cta = cs + (size_t)(narr - 1) * nmp_even * 8 + align16((size_t)N * 4);
+            // on-chip sort: segments of S keys sorted in the chunk area; 1.5x head room over N / n_seg
+            const char *oc = std::getenv("TLSB_ONCHIP_SORT");  // "0" disables (experiments)
+            const size_t area = (size_t)narr * (size_t)C * 8;
+            long long S = (long long)(((area - 64) / (h->uniform_w ? 24 : 32)) & ~(size_t)1);
+            S = std::min<long long>(S, (long long)kSegPerThread * t[0]);
+            const long long ns = S > 0 ? (3LL * N + 2 * S - 1) / (2 * S) : 0;
+            if (!(oc && std::atoi(oc) == 0) && S >= 64 && S <= 65534 && ns >= 1 && ns <= kMaxSegments) {
+                best.seg_cap = (int)S;
+                best.n_seg = (int)ns;
+                best.scratch_per_cta += (size_t)ns * (size_t)S * 12 + 16;
+            }
+            best.scratch_per_cta = (best.scratch_per_cta + 255) & ~(size_t)255;
+            return best;
+        }
+    }
+    // Last resort (a window wider than shared memory can stage): everything through L1/L2.
+    best.resident = false;
+    best.tiled = false;
+    best.threads = 256;
+    best.ctas_per_sm = 2;
+    best.qcap = 4096;
+    const size_t fixed = (size_t)best.qcap * 8 + tail_bytes(h->nU, best.threads) + 64;
+    const size_t per_cta = std::min(h->max_smem, h->smem_per_sm / 2 - 1024);
+    const size_t budget = per_cta > fixed ? per_cta - fixed : 0;
+    best.NB = (int)std::min<size_t>((size_t)N, budget / 4 > 2 ? budget / 4 - 2 : 0);
+    best.smem = (size_t)best.qcap * 8 + align16((size_t)(best.NB + 1) * 4) + tail_bytes(h->nU, best.threads);
+    best.scratch_per_cta = (cs + (h->uniform_w ? 1 : 2) * NMP * 8 + (size_t)N * 4 + 255) & ~(size_t)255;
+    return best;
+}
+
+// plan (unless the exact host plan is in force) + search, asynchronous on `s`
+// `only` / `n_only`: search just these periods (device array of indices) with the plan that is already
+// on the device - used to repair the few periods whose device-side limits were uncertain.
+int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact_plan, const int *only = nullptr,
+                   int n_only = 0)
+{
+    int rc;
+    const Layout lay = choose_layout(h);
+    if ((h->recs_stale || h->rec_kb != lay.kb) && (rc = refresh_records(h, lay.kb, s))) return rc;
+    const int P = h->P;
+    double *rec_words = reinterpret_cast<double *>(records_dev);
+    long long *status = reinterpret_cast<long long *>(rec_words + 3 * (size_t)P);
+    if (h->ulo.ensure(sizeof(int) * (size_t)P) || h->uhi.ensure(sizeof(int) * (size_t)P) ||
+        h->order.ensure(sizeof(int) * (size_t)P) || h->bin_of.ensure(sizeof(int) * (size_t)P))
+        return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    h->launches = 0;
+    if (only) {
+        // keep ulo/uhi as they are
+    } else if (exact_plan) {
+        if (!h->host_plan_valid && (rc = host_plan(h))) return rc;
+        CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));
+    } else if (h->dev_plan_valid && h->dev_plan_span == h->span && h->plan_mode == 0) {
+        CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));  // same periods, bank and span as the previous launch
+    } else {
+        PlanArgs pa{};
+        pa.periods = h->periods.as<double>(); pa.P = P; pa.rec = h->d_rec.as<WidthRec>(); pa.nU = h->nU;
+        pa.N = h->N; pa.span = h->span;
+        pa.R_star_min = h->prm.R_star_min; pa.R_star_max = h->prm.R_star_max;
+        pa.M_star_min = h->prm.M_star_min; pa.M_star_max = h->prm.M_star_max;
+        pa.eps = h->plan_mode >= 2 ? 1e300 : kPlanEps;
+        pa.sabotage = h->plan_mode == 3 ? 1 : 0;
+        pa.ulo = h->ulo.as<int>(); pa.uhi = h->uhi.as<int>(); pa.order = h->order.as<int>();
+        pa.bin_of = h->bin_of.as<int>(); pa.status = status;
+        pa.gbins = h->plan_bins.as<int>();
+        pa.unsure_list = h->unsure.as<int>();
+        const int plan_grid = std::max(1, std::min(h->num_sms, (P + kPlanThreads - 1) / kPlanThreads));
+        CUDA_TRY(launch_plan(pa, plan_grid, s));
+        h->host_plan_valid = false;
+        h->launches += 1;
+        h->dev_plan_valid = false;  // becomes valid only once its status word has been seen clean (batch)
+        h->dev_plan_span = h->span;
+    }
+
+    h->layout = lay;
+    if (h->path_mode == 1 && !lay.resident) return fail(TLSB_ERR_ARG, "tlsb_set_path: the folded curve does not fit shared memory (resident path)");
+    if (h->path_mode == 2 && !lay.tiled) return fail(TLSB_ERR_ARG, "tlsb_set_path: the widest window does not fit a shared-memory chunk (tiled path)");
+    SearchArgs a{};
+    const size_t cur_off = (size_t)h->cur * (size_t)h->N;
+    a.t = h->t.as<double>() + (h->shared_t ? 0 : cur_off);
+    a.dval = h->dval.as<double>() + cur_off; a.wval = h->wval.as<double>() + cur_off; a.N = h->N;
+    a.tq = h->tq.as<double>(); a.rec = h->d_rec.as<WidthRec>(); a.nU = h->nU; a.M = h->M; a.pad = h->pad;
+    a.periods = h->periods.as<double>(); a.ulo = h->ulo.as<int>(); a.uhi = h->uhi.as<int>();
+    a.order = only ? only : h->order.as<int>(); a.P = only ? n_only : P;
+    a.depth_min = h->prm.transit_depth_min; a.w0 = h->w0;
+    a.out_chi2 = rec_words;
+    a.out_depth = rec_words + P;
+    a.out_packed = reinterpret_cast<long long *>(rec_words + 2 * (size_t)P);
+    a.counter = h->counter.as<int>();
+    a.qcap = lay.qcap;
+    a.NB = lay.NB;
+    a.chunk = lay.chunk;
+    a.seg_cap = lay.seg_cap;
+    a.n_seg = lay.n_seg;
+    a.n_tiled = lay.tiled ? lay.n_tiled : h->nU;
+    const int grid = std::min(only ? n_only : P, h->num_sms * lay.ctas_per_sm);
+    if (!lay.resident) {
+        if (lay.NB < 1) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
+        a.scratch_per_cta = lay.scratch_per_cta;
+        if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
+        a.scratch = h->scratch.as<unsigned char>();
+    }
+    CUDA_TRY(cudaMemsetAsync(h->counter.as<int>() + 4, 0, 4, s));  // periods whose on-chip sort overflowed
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    const bool uni = h->uniform_w;
+    cudaError_t le = cudaSuccess;
+    if (lay.resident || !lay.tiled)
+        le = launch_search_resident(a, lay.threads, lay.resident, uni, lay.kb, grid, lay.smem, s);
+    else
+        le = launch_search_tiled(a, lay.threads, uni, lay.kb, grid, lay.smem, s);
+    CUDA_TRY(le);
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    h->launches += 1;
+    h->timed = true;
+    return 0;
+}
+
+
+// The plan kernel flagged `count` periods whose T14 limits sit too close to an integer for the
+// device pow() to be trusted.  Recompute just those on the host (libm, bit-identical to the
+// reference), patch the device plan where it differs, and list the periods that changed.
+// Returns 1 if there are more flagged periods than the kernel could list (caller: whole exact plan).
+int find_changed_periods(tlsb_handle *h, cudaStream_t s, long long count, std::vector<int> *changed)
+{
+    changed->clear();
+    if (count > kUnsureCap) return 1;
+    const int n = (int)count;
+    std::vector<int> list((size_t)n), lo((size_t)h->P), hi((size_t)h->P);
+    CUDA_TRY(cudaMemcpyAsync(list.data(), h->unsure.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(lo.data(), h->ulo.p, sizeof(int) * (size_t)h->P, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hi.data(), h->uhi.p, sizeof(int) * (size_t)h->P, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int k = 0; k < n; ++k) {
+        const int p = list[(size_t)k];
+        int a, b;
+        exact_range(h, h->h_periods[(size_t)p], &a, &b);
+        if (a != lo[(size_t)p] || b != hi[(size_t)p]) {
+            CUDA_TRY(cudaMemcpyAsync(h->ulo.as<int>() + p, &a, sizeof(int), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(h->uhi.as<int>() + p, &b, sizeof(int), cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s));  // a, b live on this stack frame
+            changed->push_back(p);
+        }
+    }
+    if (!changed->empty())  // the list buffer doubles as the processing order of the repair launch
+        CUDA_TRY(cudaMemcpyAsync(h->unsure.p, changed->data(), sizeof(int) * changed->size(), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Repair the records of the current curve after a search whose status word was `count` != 0.
+int resolve_records(tlsb_handle *h, cudaStream_t s, void *records_dev, long long count)
+{
+    std::vector<int> changed;
+    int rc = find_changed_periods(h, s, count, &changed);
+    if (rc < 0) return rc;
+    long long *status = reinterpret_cast<long long *>(reinterpret_cast<double *>(records_dev) + 3 * (size_t)h->P);
+    if (rc == 1) {  // too many to list: the whole plan on the host, everything again
+        h->fallbacks += 1;
+        return enqueue_search(h, s, records_dev, true);
+    }
+    if (!changed.empty()) {
+        h->repairs += (int64_t)changed.size();
+        const int64_t before = h->launches;
+        if ((rc = enqueue_search(h, s, records_dev, false, h->unsure.as<int>(), (int)changed.size()))) return rc;
+        h->launches += before;
+    }
+    CUDA_TRY(cudaMemsetAsync(status, 0, 8, s));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tlsb_last_error(void) { return g_error.c_str(); }
+const char *tlsb_version(void) { return "tlsb200 0.2 (sm_100a)"; }
+
+int32_t tlsb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t tlsb_current_device(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return d;
+}
+
+int tlsb_create(tlsb_handle **out, int32_t device)
+{
+    if (!out) return fail(TLSB_ERR_ARG, "tlsb_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(TLSB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) return fail(TLSB_ERR_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    tlsb_handle *h = new (std::nothrow) tlsb_handle();
+    if (!h) return fail(TLSB_ERR_ALLOC, "out of host memory");
+    h->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem = prop.sharedMemPerBlockOptin;
+    h->smem_per_sm = prop.sharedMemPerMultiprocessor;
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    if (h->counter.ensure(32)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    CUDA_TRY(cudaMemset(h->counter.p, 0, 32));  // [0,1] search kernel, [2,3] T0-fit kernel
+    if (h->plan_bins.ensure((kPlanBins + 2) * 4)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    CUDA_TRY(cudaMemset(h->plan_bins.p, 0, (kPlanBins + 2) * 4));
+    if (h->unsure.ensure(kUnsureCap * 4)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    *out = h;
+    return 0;
+}
+
+int tlsb_destroy(tlsb_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo,
+                      &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch, &h->t0_trials, &h->t0_model,
+                      &h->t0_resid, &h->plan_bins, &h->unsure, &h->asc_order, &h->brec, &h->bchi, &h->bSR, &h->bpr, &h->bpw, &h->bscal, &h->bamax})
+        b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return 0;
+}
+
+static int set_curves(tlsb_handle *h, const double *t, const double *y, const double *dy, int64_t n64,
+                      int64_t n_curves, bool shared_t)
+{
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = (int)n64;
+    const size_t total = (size_t)n * (size_t)n_curves, bytes = sizeof(double) * total;
+    int rc;
+    if ((rc = upload(h->t, t, shared_t ? sizeof(double) * (size_t)n : bytes))) return rc;
+    if ((rc = upload(h->y, y, bytes))) return rc;
+    if ((rc = upload(h->dy, dy, bytes))) return rc;
+    if (h->dval.ensure(bytes) || h->wval.ensure(bytes)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+    CUDA_TRY(launch_prepare(h->y.as<double>(), h->dy.as<double>(), h->dval.as<double>(), h->wval.as<double>(), total, nullptr));
+    h->c_span.assign((size_t)n_curves, 0.0);
+    h->c_w0.assign((size_t)n_curves, 0.0);
+    h->c_uniform.assign((size_t)n_curves, 0);
+    for (int64_t c = 0; c < n_curves; ++c) {
+        const double *tc = shared_t ? t : t + (size_t)c * n, *dc = dy + (size_t)c * n;
+        if (!shared_t || c == 0) {
+            double tmin = tc[0], tmax = tc[0];  // core.py:148: max(t) - min(t)
+            for (int k = 1; k < n; ++k) {
+                tmin = std::min(tmin, tc[k]);
+                tmax = std::max(tmax, tc[k]);
+            }
+            h->c_span[c] = tmax - tmin;
+        } else
+            h->c_span[c] = h->c_span[0];
+        bool uniform = true;
+        for (int k = 1; k < n && uniform; ++k) uniform = dc[k] == dc[0];
+        h->c_uniform[c] = uniform ? 1 : 0;
+        h->c_w0[c] = 1.0 / (dc[0] * dc[0]);
+    }
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->n_curves = (int)n_curves;
+    h->shared_t = shared_t;
+    h->cur = 0;
+    h->uniform_w = h->c_uniform[0] != 0;
+    h->w0 = h->c_w0[0];
+    h->N = n;
+    h->span = h->c_span[0];
+    h->have_lc = true;
+    h->recs_stale = true;
+    h->host_plan_valid = false;
+    h->dev_plan_valid = false;
+    return 0;
+}
+
+int tlsb_set_lightcurve(tlsb_handle *h, const tlsb_lightcurve *lc)
+{
+    if (!h || !lc || !lc->t || !lc->y || !lc->dy) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurve: NULL argument");
+    if (lc->n < 3 || lc->n > (int64_t)1 << 28) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurve: need 3 <= n <= 2^28 samples");
+    return set_curves(h, lc->t, lc->y, lc->dy, lc->n, 1, true);
+}
+
+int tlsb_set_lightcurves(tlsb_handle *h, const double *t, const double *y, const double *dy, int64_t n,
+                         int64_t n_curves, int32_t shared_t)
+{
+    if (!h || !t || !y || !dy) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurves: NULL argument");
+    if (n < 3 || n > (int64_t)1 << 28) return fail(TLSB_ERR_ARG, "tlsb_set_lightcurves: need 3 <= n <= 2^28 samples");
+    if (n_curves < 1 || n_curves > 65535 || n * n_curves > (int64_t)1 << 31)
+        return fail(TLSB_ERR_ARG, "tlsb_set_lightcurves: need 1 <= n_curves <= 65535 and n * n_curves <= 2^31");
+    return set_curves(h, t, y, dy, n, n_curves, shared_t != 0);
+}
+
+int tlsb_select_lightcurve(tlsb_handle *h, int64_t index)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_select_lightcurve: NULL handle");
+    if (!h->have_lc) return fail(TLSB_ERR_STATE, "tlsb_select_lightcurve: no light curves set");
+    if (index < 0 || index >= h->n_curves) return fail(TLSB_ERR_ARG, "tlsb_select_lightcurve: index out of range");
+    h->cur = (int)index;
+    h->uniform_w = h->c_uniform[(size_t)index] != 0;
+    h->w0 = h->c_w0[(size_t)index];
+    if (h->span != h->c_span[(size_t)index]) {
+        h->span = h->c_span[(size_t)index];
+        h->host_plan_valid = false;
+    }
+    return 0;
+}
+
+int64_t tlsb_lightcurve_count(const tlsb_handle *h) { return h && h->have_lc ? h->n_curves : 0; }
+
+int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_params *prm)
+{
+    if (!h || !tp || !prm || !tp->signal || !tp->offset || !tp->length || !tp->width || !tp->overshoot)
+        return fail(TLSB_ERR_ARG, "tlsb_set_templates: NULL argument");
+    if (tp->rows < 1) return fail(TLSB_ERR_ARG, "tlsb_set_templates: empty template bank");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int R = (int)tp->rows;
+    // unique widths ascending, first row with each width (core.py:113, :163-165)
+    std::vector<int64_t> uniq(tp->width, tp->width + R);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    const int nU = (int)uniq.size();
+    if (nU > 65535) return fail(TLSB_ERR_ARG, "tlsb_set_templates: more than 65535 distinct widths");
+    std::vector<WidthRec> recs(nU);
+    std::vector<double> tq;
+    int xmax = 1;
+    for (int u = 0; u < nU; ++u) {
+        int r = 0;
+        while (tp->width[r] != uniq[u]) ++r;
+        const int64_t W = uniq[u], L = tp->length[r];
+        if (W < 1 || L < 1 || L > W || W > (int64_t)1 << 28)
+            return fail(TLSB_ERR_ARG, "tlsb_set_templates: need 1 <= length <= width");
+        WidthRec &wr = recs[u];
+        wr.W = (int)W;
+        wr.L = (int)L;
+        wr.row = r;
+        wr.q = (int)tq.size();
+        wr.os = tp->overshoot[r];
+        wr.invW = 1.0 / (double)W;
+        // core.py:50-55 stride of the T0 scan
+        int xth = 1;
+        const double margin = prm->T0_fit_margin;
+        if (margin > 0 && (double)W > margin) {
+            const double inv_margin = 1 / margin;
+            xth = (int)((double)W / inv_margin);
+            if (xth < 1) xth = 1;
+        }
+        wr.X = xth;
+        xmax = std::max(xmax, xth);
+        wr.ncand = 0;  // need N: refresh_records
+        wr.tiles = 0;
+        wr.cum = 0;
+        const double *s = tp->signal + tp->offset[r];
+        double sq2 = 0.0;
+        for (int64_t j = 0; j < L; ++j) {
+            const double q = (1 - s[j]) / kSignalDepth;  // core.py:61-68
+            tq.push_back(q);
+            sq2 = std::fma(q, q, sq2);
+        }
+        wr.sq2 = sq2;
+        for (int j = 0; j < xth * kPadGroups * kBlockMax; ++j) tq.push_back(0.0);  // ramp-out + pipeline overshoot
+    }
+    int M = recs[nU - 1].W;  // core.py:114-116
+    if (M % 2 != 0) M += 1;
+    int rc;
+    h->h_tq.swap(tq);  // stays alive behind the asynchronous upload
+    if ((rc = upload(h->tq, h->h_tq.data(), h->h_tq.size() * 8))) return rc;
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->recs.swap(recs);
+    h->pad = kPadGroups * kBlockMax * xmax;
+    h->nU = nU;
+    h->M = M;
+    h->prm = *prm;
+    h->have_tp = true;
+    h->recs_stale = true;
+    h->host_plan_valid = false;
+    h->dev_plan_valid = false;
+    return 0;
+}
+
+int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods)
+{
+    if (!h || (!periods && n_periods > 0)) return fail(TLSB_ERR_ARG, "tlsb_set_periods: NULL argument");
+    if (n_periods < 0 || n_periods > (int64_t)1 << 30) return fail(TLSB_ERR_ARG, "tlsb_set_periods: bad count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->P = (int)n_periods;
+    h->h_periods.assign(periods, periods + n_periods);
+    int rc;
+    if ((rc = upload(h->periods, periods, sizeof(double) * (size_t)n_periods))) return rc;
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
+    h->asc_valid = false;
+    h->have_periods = true;
+    h->host_plan_valid = false;
+    h->dev_plan_valid = false;
+    return 0;
+}
+
+int tlsb_set_plan_mode(tlsb_handle *h, int32_t mode)
+{
+    if (!h || mode < 0 || mode > 3) return fail(TLSB_ERR_ARG, "tlsb_set_plan_mode: mode must be 0..3");
+    h->plan_mode = mode;
+    return 0;
+}
+
+int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles)
+{
+    if (!h || path < 0 || path > 3) return fail(TLSB_ERR_ARG, "tlsb_set_path: path must be 0..3");
+    h->path_mode = path;
+    h->chunk_cap = chunk_doubles;
+    return 0;
+}
+
+int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_search_async: NULL handle");
+    if (!h->have_lc || !h->have_tp || !h->have_periods)
+        return fail(TLSB_ERR_STATE, "tlsb_search_async: light curve, templates and periods must be set first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    h->launches = 0;
+    h->timed = false;
+    if (h->P == 0) return 0;
+    if (h->M > h->N) return fail(TLSB_ERR_ARG, "widest template is longer than the light curve");
+    if (!records_dev) {
+        if (h->out.ensure(((size_t)h->P * 3 + 1) * 8)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+        records_dev = h->out.p;
+    }
+    return enqueue_search(h, s, records_dev, h->plan_mode == 1);
+}
+
+int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_t *row_out,
+                     double *depth_out, int64_t *t0_index_out)
+{
+    if (!h || !chi2_out || !row_out || !depth_out) return fail(TLSB_ERR_ARG, "tlsb_get_results: NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const size_t P = (size_t)h->P;
+    if (P == 0) return 0;
+    if (!h->out.p) return fail(TLSB_ERR_STATE, "tlsb_get_results: no search has written the handle's buffer");
+    std::vector<long long> packed(P + 1);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CUDA_TRY(cudaMemcpyAsync(chi2_out, h->out.p, P * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(depth_out, h->out.as<double>() + P, P * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(packed.data(), h->out.as<double>() + 2 * P, (P + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (packed[P] == 0 || attempt == 1) break;
+        // the device plan was not sure about some periods' limits: settle those on the host and search
+        // again only the ones whose admissible widths really differ
+        const int64_t before = h->repairs + h->fallbacks;
+        int rc = resolve_records(h, s, h->out.p, packed[P]);
+        if (rc) return rc;
+        if (h->repairs + h->fallbacks == before) break;  // every flagged limit was right: results stand
+    }
+    for (size_t p = 0; p < P; ++p) {
+        row_out[p] = (int64_t)(uint32_t)(packed[p] & 0xffffffffLL);
+        if (t0_index_out) t0_index_out[p] = (int64_t)(int32_t)(packed[p] >> 32);
+    }
+    return 0;
+}
+
+int64_t tlsb_last_launch_count(const tlsb_handle *h) { return h ? h->launches : 0; }
+int32_t tlsb_last_path_resident(const tlsb_handle *h) { return h && h->layout.resident ? 1 : 0; }
+int32_t tlsb_last_path(const tlsb_handle *h) { return !h ? 0 : h->layout.resident ? 1 : h->layout.tiled ? 2 : 3; }
+int32_t tlsb_last_chunk(const tlsb_handle *h) { return h ? h->layout.chunk : 0; }
+int32_t tlsb_last_block(const tlsb_handle *h) { return h ? h->layout.kb : 0; }
+int32_t tlsb_last_tiled_widths(const tlsb_handle *h) { return h ? (h->layout.tiled ? h->layout.n_tiled : h->nU) : 0; }
+
+int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_segments, int64_t *global_sort_periods)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_last_sort_info: NULL handle");
+    if (segment_capacity) *segment_capacity = h->layout.seg_cap;
+    if (n_segments) *n_segments = h->layout.n_seg;
+    if (global_sort_periods) {
+        CUDA_TRY(cudaSetDevice(h->device));
+        int v = 0;
+        CUDA_TRY(cudaMemcpy(&v, h->counter.as<int>() + 4, 4, cudaMemcpyDeviceToHost));  // synchronises
+        *global_sort_periods = v;
+    }
+    return 0;
+}
+int64_t tlsb_plan_fallback_count(const tlsb_handle *h) { return h ? h->fallbacks : 0; }
+int64_t tlsb_plan_repair_count(const tlsb_handle *h) { return h ? h->repairs : 0; }
+
+int tlsb_resolve_plan(tlsb_handle *h, void *cuda_stream, void *records_dev)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_resolve_plan: NULL handle");
+    if (!h->have_lc || !h->have_tp || !h->have_periods || h->P == 0)
+        return fail(TLSB_ERR_STATE, "tlsb_resolve_plan: nothing has been searched");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (!records_dev) records_dev = h->out.p;
+    if (!records_dev) return fail(TLSB_ERR_STATE, "tlsb_resolve_plan: no record buffer");
+    long long count = 0;
+    CUDA_TRY(cudaMemcpyAsync(&count, reinterpret_cast<double *>(records_dev) + 3 * (size_t)h->P, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (count == 0) return 0;
+    return resolve_records(h, s, records_dev, count);
+}
+
+int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,
+                     int64_t *smem_bytes)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_last_layout: NULL handle");
+    if (threads) *threads = h->layout.threads;
+    if (ctas_per_sm) *ctas_per_sm = h->layout.ctas_per_sm;
+    if (queue_capacity) *queue_capacity = h->layout.qcap;
+    if (smem_bytes) *smem_bytes = (int64_t)h->layout.smem;
+    return 0;
+}
+
+double tlsb_last_search_kernel_ms(tlsb_handle *h)
+{
+    if (!h || !h->timed) return 0.0;
+    cudaSetDevice(h->device);
+    float ms = 0.f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.0;
+    }
+    return (double)ms;
+}
+
+// The one-shot entry point keeps one handle per device alive between calls (device buffers,
+// events), so that a second search of similar size pays no cudaMalloc/cudaFree.
+static std::mutex g_pool_mutex;
+static std::vector<std::pair<int, tlsb_handle *>> g_pool;  // (device, idle handle)
+
+static tlsb_handle *pool_take(int device)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (size_t k = 0; k < g_pool.size(); ++k)
+        if (g_pool[k].first == device) {
+            tlsb_handle *h = g_pool[k].second;
+            g_pool.erase(g_pool.begin() + (long)k);
+            return h;
+        }
+    return nullptr;
+}
+
+static void pool_give(tlsb_handle *h)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pool.emplace_back(h->device, h);
+}
+
+static int search_on_device(int device, const tlsb_lightcurve *lc, const double *periods, int64_t nP,
+                            const tlsb_templates *tp, const tlsb_params *prm, double *chi2, int64_t *row,
+                            double *depth, int64_t *t0, std::string *err)
+{
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        g_error = "no CUDA device available (this library has no CPU fallback)";
+        if (err) *err = g_error;
+        return TLSB_ERR_CUDA;
+    }
+    tlsb_handle *h = pool_take(device);
+    int rc = h ? 0 : tlsb_create(&h, device);
+    if (!rc) h->defer_sync = true;  // every input buffer outlives this call: one synchronisation, at the end
+    if (!rc) rc = tlsb_set_lightcurve(h, lc);
+    if (!rc) rc = tlsb_set_templates(h, tp, prm);
+    if (!rc) rc = tlsb_set_periods(h, periods, nP);
+    if (!rc) rc = tlsb_search_async(h, nullptr, nullptr);
+    if (!rc) rc = tlsb_get_results(h, nullptr, chi2, row, depth, t0);
+    if (h) h->defer_sync = false;
+    if (rc && h) cudaStreamSynchronize(nullptr);
+    if (rc && err) *err = g_error;
+    if (rc)
+        tlsb_destroy(h);  // do not recycle a handle that failed
+    else
+        pool_give(h);
+    return rc;
+}
+
+int tlsb_search_periods(const tlsb_lightcurve *lc, const double *periods, int64_t n_periods,
+                        const tlsb_templates *tp, const tlsb_params *prm, const tlsb_exec *ex,
+                        double *chi2_out, int64_t *row_out, double *depth_out, int64_t *t0_index_out)
+{
+    if (!lc || !tp || !prm || (!periods && n_periods > 0) || !chi2_out || !row_out || !depth_out)
+        return fail(TLSB_ERR_ARG, "tlsb_search_periods: NULL argument");
+    std::vector<int> devs;
+    if (ex && ex->devices && ex->n_devices > 0) devs.assign(ex->devices, ex->devices + ex->n_devices);
+    if (devs.size() <= 1) {
+        std::string err;
+        int rc = search_on_device(devs.empty() ? -1 : devs[0], lc, periods, n_periods, tp, prm, chi2_out,
+                                  row_out, depth_out, t0_index_out, &err);
+        if (rc) g_error = err;
+        return rc;
+    }
+    // several GPUs from one process: deal the periods round-robin, one host thread per GPU
+    const int G = (int)devs.size();
+    std::vector<std::vector<double>> per(G);
+    std::vector<std::vector<int64_t>> where(G);
+    for (int64_t p = 0; p < n_periods; ++p) {
+        per[p % G].push_back(periods[p]);
+        where[p % G].push_back(p);
+    }
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> pool;
+    for (int g = 0; g < G; ++g) {
+        pool.emplace_back([&, g]() {
+            const size_t n = per[g].size();
+            std::vector<double> c(n), d(n);
+            std::vector<int64_t> r(n), t0(n);
+            rcs[g] = search_on_device(devs[g], lc, per[g].data(), (int64_t)n, tp, prm, c.data(), r.data(),
+                                      d.data(), t0.data(), &errs[g]);
+            if (rcs[g]) return;
+            for (size_t k = 0; k < n; ++k) {
+                const int64_t p = where[g][k];
+                chi2_out[p] = c[k];
+                row_out[p] = r[k];
+                depth_out[p] = d[k];
+                if (t0_index_out) t0_index_out[p] = t0[k];
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], errs[g]);
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- final_T0_fit -------------------------------------------------------------------------
+namespace {
+
+int run_t0_fit(tlsb_handle *h, cudaStream_t s, const double *model_in, int64_t dur, double period,
+               const double *trials, int64_t n_trials, double *residuals_out, int64_t *best_index_out)
+{
+    if (!h->have_lc) return fail(TLSB_ERR_STATE, "tlsb_final_t0_fit: set the light curve first");
+    if (!model_in || !trials || !residuals_out) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: NULL argument");
+    const int N = h->N;
+    if (dur < 1 || dur > N) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: need 1 <= dur <= n");
+    if (n_trials < 1 || n_trials > (int64_t)1 << 30) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: bad trial count");
+    if (!(period > 0)) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: period must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload(h->t0_trials, trials, sizeof(double) * (size_t)n_trials, s))) return rc;
+    if ((rc = upload(h->t0_model, model_in, sizeof(double) * (size_t)dur, s))) return rc;
+    if (h->t0_resid.ensure(sizeof(double) * (size_t)n_trials)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+
+    T0Args a{};
+    const size_t cur_off = (size_t)h->cur * (size_t)N;
+    a.t = h->t.as<double>() + (h->shared_t ? 0 : cur_off); a.y = h->y.as<double>() + cur_off; a.N = N;
+    a.trials = h->t0_trials.as<double>(); a.n_trials = (int)n_trials;
+    a.model = h->t0_model.as<double>(); a.dur = (int)dur; a.shift = (int)(dur / 2) + 1;  // stats.py:186
+    a.period = period;
+    a.residuals = h->t0_resid.as<double>();
+    a.counter = h->counter.as<int>() + 2;
+
+    // layout: sort keys + sorted flux (+ ids, histogram) in shared memory when they fit
+    const size_t n_even = ((size_t)N + 1) & ~(size_t)1;
+    bool resident = false;
+    int threads = 256, per_sm = 2;
+    size_t smem = 0;
+    if (N < 65536) {
+        const int tries[2][2] = {{256, 2}, {512, 1}};
+        for (const auto &t : tries) {
+            const size_t tail = (size_t)(t[0] / 32 + 2) * 8 + 32;
+            const size_t bytes = 2 * n_even * 8 + (size_t)((N + 2) & ~1) * 4 + align16((size_t)N * 2) + tail;
+            if (bytes > h->max_smem || (bytes + 1024) * (size_t)t[1] > h->smem_per_sm) continue;
+            resident = true; threads = t[0]; per_sm = t[1]; smem = bytes; a.NB = N;
+            break;
+        }
+    }
+    const int grid = (int)std::min<int64_t>(n_trials, (int64_t)h->num_sms * per_sm);
+    if (!resident) {
+        threads = 256; per_sm = 2;
+        const size_t tail = (size_t)(threads / 32 + 2) * 8 + 32;
+        const size_t per_cta = std::min(h->max_smem, h->smem_per_sm / 2 - 1024);
+        a.NB = (int)std::min<size_t>((size_t)N, (per_cta - tail - 64) / 4 - 2);
+        smem = align16((size_t)(a.NB + 1) * 4) + tail;
+        a.scratch_per_cta = (2 * n_even * 8 + (size_t)N * 4 + 255) & ~(size_t)255;
+        if (h->scratch.ensure(a.scratch_per_cta * (size_t)grid)) return fail(TLSB_ERR_ALLOC, "device allocation failed (scratch)");
+        a.scratch = h->scratch.as<unsigned char>();
+    }
+    h->t0_resident = resident;
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    CUDA_TRY(launch_t0fit(a, threads, resident, grid, smem, s));
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    CUDA_TRY(cudaMemcpyAsync(residuals_out, h->t0_resid.p, sizeof(double) * (size_t)n_trials, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->t0_ms = ms; else cudaGetLastError();
+    h->timed = false;
+    if (best_index_out) {  // stats.py:200-202: strict '<' from +inf, so the first minimum wins and NaN never does
+        int64_t best = -1;
+        double lowest = INFINITY;
+        for (int64_t k = 0; k < n_trials; ++k)
+            if (residuals_out[k] < lowest) { lowest = residuals_out[k]; best = k; }
+        *best_index_out = best;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tlsb_final_t0_fit(tlsb_handle *h, void *cuda_stream, const double *model_in, int64_t dur, double period,
+                      const double *trials, int64_t n_trials, double *residuals_out, int64_t *best_index_out)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit: NULL handle");
+    return run_t0_fit(h, reinterpret_cast<cudaStream_t>(cuda_stream), model_in, dur, period, trials, n_trials,
+                      residuals_out, best_index_out);
+}
+
+double tlsb_last_t0_fit_ms(const tlsb_handle *h) { return h ? h->t0_ms : 0.0; }
+
+int tlsb_final_t0_fit_lc(const tlsb_lightcurve *lc, int32_t device, const double *model_in, int64_t dur,
+                         double period, const double *trials, int64_t n_trials, double *residuals_out,
+                         int64_t *best_index_out)
+{
+    if (!lc) return fail(TLSB_ERR_ARG, "tlsb_final_t0_fit_lc: NULL light curve");
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(TLSB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    tlsb_handle *h = pool_take(device);
+    int rc = h ? 0 : tlsb_create(&h, device);
+    if (!rc) rc = tlsb_set_lightcurve(h, lc);
+    if (!rc) rc = run_t0_fit(h, nullptr, model_in, dur, period, trials, n_trials, residuals_out, best_index_out);
+    if (rc) {
+        std::string keep = g_error;
+        tlsb_destroy(h);
+        g_error = keep;
+    } else
+        pool_give(h);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- batch pipeline: every resident light curve through plan/search, then spectra, one sync ----
+
+extern "C" int tlsb_search_batch(tlsb_handle *h, void *cuda_stream, int64_t median_window, double *chi2_out,
+                                 int64_t *row_out, double *depth_out, int64_t *t0_index_out, double *power_out,
+                                 double *SDE_raw_out, double *SDE_out, int64_t *best_period_index_out)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_search_batch: NULL handle");
+    if (!h->have_lc || !h->have_tp || !h->have_periods)
+        return fail(TLSB_ERR_STATE, "tlsb_search_batch: light curves, templates and periods must be set first");
+    if (!SDE_raw_out || !SDE_out) return fail(TLSB_ERR_ARG, "tlsb_search_batch: NULL argument");
+    if (median_window < 1 || median_window > 24000) return fail(TLSB_ERR_ARG, "tlsb_search_batch: median window must be in 1..24000");
+    if (h->P < 1) return fail(TLSB_ERR_ARG, "tlsb_search_batch: no periods");
+    if (h->M > h->N) return fail(TLSB_ERR_ARG, "widest template is longer than the light curve");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const size_t B = (size_t)h->n_curves, P = (size_t)h->P, stride = 3 * P + 1;
+    if (h->brec.ensure(B * stride * 8) || h->bchi.ensure(B * P * 8) || h->bSR.ensure(B * P * 8) ||
+        h->bpr.ensure(B * P * 8) || h->bpw.ensure(B * P * 8) || h->bscal.ensure(B * 32) || h->bamax.ensure(B * 8))
+        return fail(TLSB_ERR_ALLOC, "device allocation failed (batch buffers)");
+    if (!h->asc_valid) {  // main.py:190-196: the spectra consume chi2 in ascending-period order
+        const std::vector<double> &per = h->h_periods;
+        h->h_asc_order.resize(P);
+        std::iota(h->h_asc_order.begin(), h->h_asc_order.end(), 0);
+        std::stable_sort(h->h_asc_order.begin(), h->h_asc_order.end(), [&](int x, int y) { return per[x] < per[y]; });
+        int rc0 = upload(h->asc_order, h->h_asc_order.data(), sizeof(int) * P, s);
+        if (rc0) return rc0;
+        h->asc_valid = true;
+    }
+    double *rec = h->brec.as<double>();
+    std::vector<long long> status(B);
+    int64_t launches = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool exact = attempt == 1 || h->plan_mode == 1;
+        int rc, n_plans = 0;
+        for (size_t c = 0; c < B; ++c) {
+            if ((rc = tlsb_select_lightcurve(h, (int64_t)c))) return rc;
+            if ((rc = enqueue_search(h, s, rec + c * stride, exact))) return rc;
+            launches += h->launches;
+            n_plans += h->launches == 2 ? 1 : 0;
+            // the device plan of this launch serves the following curves while span/periods/bank stay the same
+            if (!exact && h->plan_mode == 0) h->dev_plan_valid = true;
+        }
+        // one strided copy of the B status words
+        CUDA_TRY(cudaMemcpy2DAsync(status.data(), 8, rec + 3 * P, stride * 8, 8, B, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        long long flagged = 0;
+        for (size_t c = 0; c < B; ++c) flagged = std::max(flagged, status[c]);
+        if (flagged == 0 || exact) break;
+        // Some T14 limit was too close to an integer for the device pow().  One shared plan: settle the
+        // flagged periods on the host and search again only those whose admissible widths differ, for
+        // every curve.  Several plans in the batch (different spans): the exact host plan, everything again.
+        h->dev_plan_valid = false;
+        bool same_span = true;  // every plan of this batch is the same plan
+        for (size_t c = 1; c < B; ++c) same_span = same_span && h->c_span[c] == h->c_span[0];
+        if ((n_plans == 1 || same_span) && status[0] == flagged) {
+            std::vector<int> changed;
+            rc = find_changed_periods(h, s, flagged, &changed);
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                for (size_t c = 0; c < B && !changed.empty(); ++c) {
+                    if ((rc = tlsb_select_lightcurve(h, (int64_t)c))) return rc;
+                    if ((rc = enqueue_search(h, s, rec + c * stride, false, h->unsure.as<int>(), (int)changed.size()))) return rc;
+                    launches += h->launches;
+                }
+                h->repairs += (int64_t)changed.size();
+                CUDA_TRY(cudaStreamSynchronize(s));
+                break;
+            }
+        }
+        h->fallbacks += 1;
+    }
+    h->dev_plan_valid = false;  // do not carry the shortcut outside the batch
+    CUDA_TRY(launch_gather_rows(rec, stride, h->asc_order.as<int>(), h->bchi.as<double>(), (int)P, (int)B, s));
+    int rc = tlsb::spectra_device(h->bchi.as<double>(), (int64_t)P, (int64_t)B, median_window, h->bSR.as<double>(),
+                                  h->bpr.as<double>(), h->bpw.as<double>(), h->bscal.as<double>(),
+                                  h->bamax.as<long long>(), s);
+    if (rc) return rc;
+    launches += 1 + (P > 2 * (size_t)median_window ? 3 : 2);
+    h->launches = launches;
+    std::vector<double> scal(B * 4);
+    std::vector<long long> amax(B), packed;
+    CUDA_TRY(cudaMemcpyAsync(scal.data(), h->bscal.p, B * 32, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(amax.data(), h->bamax.p, B * 8, cudaMemcpyDeviceToHost, s));
+    if (chi2_out) CUDA_TRY(cudaMemcpy2DAsync(chi2_out, P * 8, rec, stride * 8, P * 8, B, cudaMemcpyDeviceToHost, s));
+    if (depth_out) CUDA_TRY(cudaMemcpy2DAsync(depth_out, P * 8, rec + P, stride * 8, P * 8, B, cudaMemcpyDeviceToHost, s));
+    if (row_out || t0_index_out) {
+        packed.resize(B * P);
+        CUDA_TRY(cudaMemcpy2DAsync(packed.data(), P * 8, rec + 2 * P, stride * 8, P * 8, B, cudaMemcpyDeviceToHost, s));
+    }
+    if (power_out) CUDA_TRY(cudaMemcpyAsync(power_out, h->bpw.p, B * P * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (size_t k = 0; k < packed.size(); ++k) {
+        if (row_out) row_out[k] = (int64_t)(uint32_t)(packed[k] & 0xffffffffLL);
+        if (t0_index_out) t0_index_out[k] = (int64_t)(int32_t)(packed[k] >> 32);
+    }
+    for (size_t c = 0; c < B; ++c) {
+        SDE_raw_out[c] = scal[4 * c + 0];
+        SDE_out[c] = scal[4 * c + 1];
+        if (best_period_index_out) best_period_index_out[c] = h->h_asc_order[(size_t)amax[c]];
+    }
+    return 0;
+}

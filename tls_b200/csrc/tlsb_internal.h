@@ -38,6 +38,150 @@ struct DeviceBuffer {
 int spectra_device(const double *chi2, int64_t P, int64_t n_curves, int64_t win, double *SR, double *power_raw,
                    double *power, double *scal, long long *argmax, cudaStream_t s);
 
+
+// ---- constants and argument structs shared by the kernels' translation units and the host side ----
+// R = kB (template parameter of the kernels): consecutive T0 candidates one lane carries through the
+// tap loop.  Odd (neighbouring lanes sit R*stride doubles apart in shared memory): 7 when all weights
+// are equal (one correlation: the register window fits), 5 with unequal weights (two correlations).
+constexpr int kBlockMax = 7;          // host-side slack (template padding, array slack) is sized for the largest R
+constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per queue reservation
+__host__ __device__ constexpr int tile_size(int kb) { return 32 * kb * kSub; }  // candidates one warp gates at a time
+constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
+constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
+constexpr int kResScanItems = 19;     // ... of the resident kernel: one tile covers 19 * 256 = 4864 samples (cfg-1: one tile, 3 barriers)
+#ifndef TLSB_RES_HSCAN
+#define TLSB_RES_HSCAN 19  // one tile for cfg-1's 4,322 histogram words, like kResScanItems (5 -> 17: 2.611 -> 2.579 ms per cfg-1 grid)
+#endif
+#ifndef TLSB_RES_SORT_U
+#define TLSB_RES_SORT_U 4
+#endif
+constexpr int kResHScanItems = TLSB_RES_HSCAN;  // ... of the bucket-histogram scan of the resident kernel
+constexpr int kResSortU = TLSB_RES_SORT_U;      // independent key chains per thread in the resident kernel's fold / scatter / rank loops
+constexpr int kSegPerThread = 16;   // keys of one segment a thread keeps in registers (S <= 16 * threads)
+constexpr int kSegScanItems = 17;   // scan tile of the on-chip sort: 17 * threads > S, so one tile and three barriers per scan
+constexpr int kMaxSegments = 64;     // phase segments of the on-chip sort of the tiled path
+constexpr int kPlanThreads = 1024;
+constexpr int kPlanBins = 1024;
+constexpr int kUnsureCap = 4096;     // uncertain periods the plan kernel lists (more: the whole plan is redone on the host)
+constexpr unsigned kFull = 0xffffffffu;
+constexpr double kSignalDepth = 0.5;  // tls_constants.py:71
+constexpr double kPlanEps = 1e-9;     // relative distance to an integer below which the device plan is "uncertain"
+
+// ------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------
+// Per unique width (ascending), core.py:113 / :163-165.  One record so that a lane can fetch
+// everything about "its" width with a few shared-memory loads.
+struct WidthRec {
+    int W;        // width in samples
+    int L;        // template length L <= W
+    int X;        // T0 stride (core.py:50-55)
+    int row;      // first row of the bank with that width
+    int q;        // offset of the (zero padded) template in tq
+    int ncand;    // candidates: offsets i = c*X, c in [0, ncand)
+    int tiles;    // ceil(ncand / kTile)
+    int cum;      // tiles of all wider widths (the sweep runs wide -> narrow)
+    double os;    // overshoot
+    double invW;  // 1 / W
+    double sq2;   // sum_j q_j^2 (the quadratic term when all weights are equal)
+};
+
+struct PlanArgs {
+    const double *periods;
+    int P;
+    const WidthRec *rec;
+    int nU;
+    int N;
+    double span;                                        // max(t) - min(t), core.py:148
+    double R_star_min, R_star_max, M_star_min, M_star_max;
+    double eps;                                         // kPlanEps (or huge: test mode)
+    int *ulo, *uhi, *order, *bin_of;                    // [P]
+    int *gbins;                                         // [kPlanBins + 2] cost histogram, uncertain periods, finished CTAs (zero between launches)
+    int *unsure_list;                                   // [kUnsureCap] the first uncertain periods
+    int sabotage;                                       // tests: drop the widest admissible width of every 7th period
+    long long *status;                                  // records word 3P: number of uncertain periods
+};
+
+struct SearchArgs {
+    // light curve, prepared once per curve by prepare_kernel
+    const double *t;      // [N]
+    const double *dval;   // [N] 1 - y
+    const double *wval;   // [N] 1 / dy^2
+    int N;
+    const double *tq;     // flat q_j = (1 - signal_j) / SIGNAL_DEPTH, each template zero padded
+    const WidthRec *rec;  // [nU]
+    int nU;
+    int M;                // patch length (max width, made even) core.py:114-116
+    int pad;              // readable slack behind the patched arrays
+    // periods
+    const double *periods;
+    const int *ulo;       // [P] admissible unique-width index range [ulo, uhi)
+    const int *uhi;
+    const int *order;     // [P] processing order (most expensive first)
+    int P;
+    double depth_min;
+    double w0;            // the common weight 1/dy^2 when every dy is the same (dy=None), else unused
+    // outputs: three planes of P 8-byte words
+    double *out_chi2;
+    double *out_depth;
+    long long *out_packed;
+    // scheduling
+    int *counter;         // [2] next period, finished CTAs
+    int qcap;             // capacity of the CTA-wide survivor queue
+    // streaming path scratch
+    unsigned char *scratch;
+    size_t scratch_per_cta;
+    int NB;               // number of phase buckets
+    int chunk;            // tiled path: doubles per staged array (cs / w / wd) in shared memory
+    int seg_cap;          // tiled path, on-chip sort: elements per phase segment (0: sort in global scratch)
+    int n_seg;            // number of phase segments (<= kMaxSegments)
+    int n_tiled;          // tiled path: unique widths [0, n_tiled) are searched from staged chunks, the rest from L2
+};
+
+// tls_constants.py:20-25,78 and grid.py:9-32 (T14); same operation order on host and device
+__host__ __device__ inline double t14_fraction(double R_s, double M_s, double P, bool small)
+{
+    const double G = 6.673e-11, R_sun = 695508000.0, R_jup = 69911000.0, M_sun = 1.989e30;
+    const double pi = 3.141592653589793;
+    const double Ps = P * 86400.0, R = R_sun * R_s, Ms = M_sun * M_s;
+    const double cube = pow((4 * Ps) / (pi * G * Ms), 1.0 / 3);
+    const double t14 = small ? R * cube : (R + 2 * R_jup) * cube;
+    const double frac = t14 / Ps;
+    return frac > 0.12 ? 0.12 : frac;
+}
+
+// what a candidate block of width record wr may read behind its start offset
+__host__ __device__ inline int window_need(int W, int X, int kb) { return W + kPadGroups * kb * X + 2; }
+
+struct T0Args {
+    const double *t;       // [N]
+    const double *y;       // [N]
+    int N;
+    const double *trials;  // [n_trials] numpy.linspace(min(t), min(t)+period, points), made on the host
+    int n_trials;
+    const double *model;   // [dur] 1 - (1 - signal) / (SIGNAL_DEPTH / (1 - depth)), stats.py:141-143
+    int dur;
+    int shift;             // int(dur / 2) + 1
+    double period;
+    double *residuals;     // [n_trials]
+    int *counter;          // [2] next trial, finished CTAs
+    int NB;
+    unsigned char *scratch;
+    size_t scratch_per_cta;
+};
+
+// kernel launchers (one per translation unit that holds kernels)
+cudaError_t launch_plan(const PlanArgs &a, int grid, cudaStream_t s);                       // tlsb_aux_kernels.cu
+cudaError_t launch_prepare(const double *y, const double *dy, double *dval, double *wval, size_t n, cudaStream_t s);
+cudaError_t launch_t0fit(const T0Args &a, int threads, bool resident, int grid, size_t smem, cudaStream_t s);
+cudaError_t launch_gather_rows(const double *records, size_t record_stride, const int *order, double *out, int P,
+                               int n_curves, cudaStream_t s);
+// resident (folded curve in shared memory) or streaming (global scratch) layout           // tlsb_resident.cu
+cudaError_t launch_search_resident(const SearchArgs &a, int threads, bool resident, bool uniform_w, int kb, int grid,
+                                   size_t smem, cudaStream_t s);
+cudaError_t launch_search_tiled(const SearchArgs &a, int threads, bool uniform_w, int kb, int grid, size_t smem,
+                                cudaStream_t s);                                            // tlsb_tiled.cu
+
 }  // namespace tlsb
 
 #define TLSB_CUDA_TRY(expr)                                                                          \
