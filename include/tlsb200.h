@@ -161,6 +161,15 @@ int tlsb_last_sort_info(tlsb_handle *h, int32_t *segment_capacity, int32_t *n_se
  * several chunks; chunk_doubles < 0 caps it at exactly -chunk_doubles, so that the widest widths
  * no longer fit a chunk and take the pass that reads the folded curve from L2 instead. */
 int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles);
+/* Equal weights (dy=None): every gate survivor first gets an fp32 correlation with a rigorous error bound, and only
+ * the candidates whose chi2 lower bound does not exceed the smallest upper bound seen so far are evaluated in fp64
+ * (core.py:57-74 restated).  mode 1 (default) = filter on, mode 0 = every survivor through the exact
+ * evaluation; results are bit-identical either way (tests/test_gpu_filter.py).  count_stats != 0 makes the next
+ * searches count survivors and finalists on the device. */
+int tlsb_set_filter(tlsb_handle *h, int32_t mode, int32_t count_stats);
+/* Counters of the most recent search when counting was on (synchronises): gate survivors that took the fp32 pass,
+ * finalists evaluated in fp64, and how many of those did not fit the finalist queue.  Any pointer may be NULL. */
+int tlsb_last_filter_stats(tlsb_handle *h, int64_t *candidates, int64_t *finalists, int64_t *overflows);
 /* Launch shape of the most recent search kernel (any pointer may be NULL). */
 int tlsb_last_layout(const tlsb_handle *h, int32_t *threads, int32_t *ctas_per_sm, int32_t *queue_capacity,
                      int64_t *smem_bytes);

@@ -1,0 +1,74 @@
+"""The fp32 filter pass (equal weights): an fp32 correlation with a rigorous error bound decides which gate
+survivors can still be the minimum; only those are evaluated in fp64.  The claim is that nothing changes:
+results with the filter on are BIT-IDENTICAL to results with the filter off (every survivor through the
+exact fp64 evaluation), on every layout, and both match the reference goldens (core.py:57-74)."""
+import numpy as np
+import pytest
+
+from conftest import assert_search_parity, load_search_golden, search_goldens
+
+pytestmark = pytest.mark.gpu
+
+
+def _uniform(g):
+    return np.all(g["dy"] == g["dy"][0])
+
+
+def _run(g, on, path="auto", chunk=0, stats=False, periods=None):
+    from tls_b200 import native
+
+    s = native.Searcher()
+    try:
+        s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
+        s.set_periods(g["periods"] if periods is None else periods)
+        s.set_path(path, chunk)
+        s.set_filter(on, stats)
+        s.search_async()
+        out = s.results()
+        return out, (s.filter_stats if stats else None), s.path
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("name", [n for n in search_goldens()])
+def test_filter_on_equals_filter_off_bit_for_bit(name):
+    g = load_search_golden(name)
+    if not _uniform(g):
+        pytest.skip("per-point weights take the two-correlation fp64 path (no filter)")
+    on, _, path = _run(g, True)
+    off, _, _ = _run(g, False)
+    for a, b, what in zip(on, off, ("chi2", "row", "depth", "t0_index")):
+        np.testing.assert_array_equal(a, b, err_msg="%s differs with the filter on (%s, %s path)" % (what, name, path))
+    assert_search_parity(on[:3], g, rtol=1e-5, label=name)
+
+
+@pytest.mark.parametrize("name,path,chunk", [("cfg1_500ppm", "tiled", 1536), ("small", "tiled", 512),
+                                              ("ragged_L", "tiled", 700), ("cfg3", "tiled", 0),
+                                              ("ties_unsorted", "tiled", 600)])
+def test_filter_on_equals_off_on_the_tiled_layout(name, path, chunk):
+    g = load_search_golden(name)
+    on, _, used = _run(g, True, path, chunk)
+    off, _, _ = _run(g, False, path, chunk)
+    assert used == "tiled"
+    for a, b, what in zip(on, off, ("chi2", "row", "depth", "t0_index")):
+        np.testing.assert_array_equal(a, b, err_msg="%s differs with the filter on (%s, tiled)" % (what, name))
+    assert_search_parity(on[:3], g, rtol=1e-5, label=name)
+
+
+def test_filter_passes_few_candidates_on_noisy_data():
+    """cfg-1 at 500 ppm: about half of all offsets pass the gate; the filter must leave the fp64 evaluation
+    a small fraction of them (the bound is rigorous, not tuned: a regression here means a slow kernel,
+    never a wrong one)."""
+    from tls_b200 import transitleastsquares, workloads
+
+    t, y, dy, kw = workloads.lightcurve("cfg1_500ppm")
+    inp = transitleastsquares(t, y, dy, verbose=False).prepare(verbose=False, **kw)
+    g = dict(t=inp.t, y=inp.y, dy=inp.dy, templates=inp.templates, params=inp.params, periods=inp.periods[::16])
+    on, st, path = _run(g, True, stats=True)
+    off, _, _ = _run(g, False)
+    assert path == "resident"
+    for a, b in zip(on, off):
+        np.testing.assert_array_equal(a, b)
+    assert st["candidates"] > 1000 * len(g["periods"])
+    assert st["finalists"] < 0.05 * st["candidates"], st
+    assert st["overflows"] == 0, st

@@ -63,7 +63,7 @@ __device__ __forceinline__ int bucket_of(double phase, int NB)
 }
 
 // In-place block-wide inclusive scan of data[0..n) (all threads must call).
-template <int kT, typename T, int kScanItems = ::kScanItems>
+template <int kT, typename T, int kScanItems = tlsb::kScanItems>
 __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] shared */)
 {
     constexpr int kW = kT / 32;
@@ -115,10 +115,10 @@ __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] sh
 // inside its bucket by (phase, index) = numpy's stable mergesort order, and gather src1 (src2) to the sorted
 // slots of dst1 (dst2).  Bucket b spans [H[b-1], H[b]) with kShift = 0 (H[-1] = 0), [H[b], H[b+1]) with
 // kShift = 1.  Ends WITHOUT a barrier.
-template <int kT, typename idx_t, bool kTwo, int kU, int kShift>
+template <int kT, typename idx_t, bool kTwo, int kU, int kShift, bool kKeepIds = false>
 __device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const double *skey, const idx_t *sid,
                                             const double *__restrict__ src1, const double *__restrict__ src2,
-                                            double *dst1, double *dst2)
+                                            double *dst1, double *dst2, idx_t *sid_sorted = nullptr)
 {
     const int tid = threadIdx.x;
     for (int q0 = tid; q0 < N; q0 += kT * kU) {
@@ -165,6 +165,7 @@ __device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const d
             if (q0 + u * kT < N) {
                 dst1[rank[u]] = v1[u];
                 if (kTwo) dst2[rank[u]] = v2[u];
+                if (kKeepIds) sid_sorted[rank[u]] = (idx_t)id[u];
             }
         }
     }
@@ -175,11 +176,12 @@ __device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const d
 // rank inside the bucket by (phase, index) = numpy's stable mergesort order; src1 (and src2) are
 // gathered to their sorted slots in dst1 (dst2).  dst1 doubles as the store of the unsorted
 // phases until the ranking step; skey/sid/H are scratch.  Ends WITHOUT a barrier.
-template <int kT, typename idx_t, bool kTwo, bool kEpoch, int kU = 4, int kHScanItems = ::kScanItems>
+template <int kT, typename idx_t, bool kTwo, bool kEpoch, int kU = 4, int kHScanItems = tlsb::kScanItems, bool kKeepIds = false>
 __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, double T0, double r, int N, int NB,
                                                  int *H, double *skey, idx_t *sid,
                                                  const double *__restrict__ src1, const double *__restrict__ src2,
-                                                 double *dst1, double *dst2, int *scan_scratch)
+                                                 double *dst1, double *dst2, int *scan_scratch,
+                                                 idx_t *sid_sorted = nullptr)
 {
     // kU independent load chains per thread (the streaming layouts sort in L2/HBM)
     const int tid = threadIdx.x;
@@ -218,7 +220,7 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
         }
     }
     __syncthreads();  // now H[b] = end of bucket b; the unsorted phases are dead
-    rank_gather<kT, idx_t, kTwo, kU, 0>(N, NB, H, skey, sid, src1, src2, dst1, dst2);
+    rank_gather<kT, idx_t, kTwo, kU, 0, kKeepIds>(N, NB, H, skey, sid, src1, src2, dst1, dst2, sid_sorted);
 }
 
 // After the sort: cs1[0..N) holds the sorted d = 1 - y (cs1 = cs + 1).  Wrap the first M samples to
@@ -226,10 +228,11 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
 // (helpers.py:70-73), writes wd = w * d and returns this thread's share of T = sum_{k<N} w d^2.
 // With begin > 0 the pass resumes at position `begin` with the running sum `carry` (the samples
 // there already hold their d; nothing is wrapped).
-template <int kT, bool kUniformW, int kScanItems = ::kScanItems>
+// kWd64 / kWd32: write the products w*d in fp64 (wd) and / or rounded to fp32 (wd32, the filter pass's samples).
+template <int kT, bool kUniformW, int kScanItems = tlsb::kScanItems, bool kWd64 = true, bool kWd32 = false>
 __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, double *wd, double w0, int N, int NM,
                                                    int NMP, double *warp_tot /* [kT/32 + 1] shared */,
-                                                   int begin = 0, double carry = 0.0)
+                                                   int begin = 0, double carry = 0.0, float *wd32 = nullptr)
 {
     constexpr int kW = kT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -240,7 +243,8 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
                 if (!kUniformW) w[k] = w[k - N];
             }
         } else {  // slack read (never used) by the unguarded tap groups
-            wd[k] = 0.0;
+            if (kWd64) wd[k] = 0.0;
+            if (kWd32) wd32[k] = 0.f;
             if (!kUniformW) w[k] = 0.0;
         }
     }
@@ -264,7 +268,8 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
             if (e < NM) {
                 d = dv[k];
                 const double x = wv[k] * d;
-                wd[e] = x;
+                if (kWd64) wd[e] = x;
+                if (kWd32) wd32[e] = (float)x;
                 if (e < N) tpart = fma(x, d, tpart);
             }
             run += d;
@@ -464,6 +469,352 @@ __device__ __forceinline__ void block_min(const WidthRec &wr, const double *cs, 
         if (on && chi < blk_chi) { blk_chi = chi; blk_D = D; blk_i = i; }
     }
     if (blk_i >= 0 && better(blk_chi, u, blk_i, best)) { best.chi2 = blk_chi; best.D = blk_D; best.u = u; best.i = blk_i; }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 filter pass (equal weights).  chi2 of a candidate is T + D (D Aq - 2 B) with B = sum_j q_j (w d)_{i+j}; B is
+// the only O(L) piece.  The filter computes B in fp32 (128 FMA/clk/SM instead of 64, half the shared-memory
+// bytes per sample) together with a RIGOROUS bound on |B32 - B64|, keeps the smallest upper bound U on chi2 seen so
+// far, and passes on ("finalist") only candidates whose lower bound does not exceed U.  Finalists are then evaluated
+// in fp64 exactly as before (eval_exact), and the lexicographic arg-min runs over them alone.  Because the true
+// minimum m satisfies lo(c*) <= chi2(c*) = m <= U at all times, the arg-min candidate (and every candidate that
+// ties with it) is always a finalist: results are bit-identical with the filter on or off.
+//
+// The bound: inputs rounded to fp32 (relative 2^-24 each) and an FMA chain of L terms give
+//   |B32 - sum q_j wd_j| <= ((1 + u)^2 (1 + gamma_L) - 1) sum |q_j| |wd_j|,  u = 2^-24, gamma_L = L u / (1 - L u),
+// which is below (L + 4) u S for L u < 1e-3; the fp64 chain adds L 2^-53 S.  With S <= max|wd| sum_j |q_j| the
+// host stores eb = (L + 8) 2^-24 sum_j |q_j| (1 + 1e-6) per width, and the kernel multiplies by max|w d| of the light curve.
+// Zero padded taps add exact zeros.  NaN / inf anywhere make the comparison fail safe (the candidate is a finalist).
+// ------------------------------------------------------------------------------------------
+// One pass of the fp32 tap loop over a residue class (V = 1) or a pair of adjacent classes (V = 2, even strides:
+// samples and template values are then aligned float2).  Step m multiplies the sample vector at sp + m*X with the
+// template vectors of steps m, m-1, ..., m-kBlock+1 (one per candidate).  Steps run in unguarded groups of kG = 8;
+// the template values of two consecutive groups live in two register sets that swap roles every group: the set of
+// the previous group is refilled with the NEXT group's values as soon as its entries are dead (entry k is last used
+// at step k-2), so there is no window copy, and samples are loaded one group ahead.
+template <int kBlock, int V, bool kUnit>
+__device__ __forceinline__ void tap_pass32(const float *__restrict__ qp, const float *__restrict__ sp, int X, int groups,
+                                           float (&B)[kBlock])
+{
+    constexpr int kG = kGroup32;
+    static_assert(kBlock + 1 <= kG, "entry k of the previous group must be dead after step k-2");
+    const int Xs = kUnit ? 1 : X;
+    float qa[kG][V], qb[kG][V];  // template values of the even / odd groups
+    float sa[kG][V], sb[kG][V];  // samples, one group ahead
+    auto load_q = [&](float (&dst)[kG][V], const float *__restrict__ p, int from) {  // entries [from, from + 4)
+        if (kUnit) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p + from));
+            dst[from][0] = v.x; dst[from + 1][0] = v.y; dst[from + 2][0] = v.z; dst[from + 3][0] = v.w;
+        } else if (V == 2) {
+#pragma unroll
+            for (int k = from; k < from + 4; ++k) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(p + k * Xs));
+                dst[k][0] = v.x; dst[k][V - 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = from; k < from + 4; ++k) dst[k][0] = __ldg(p + k * Xs);
+        }
+    };
+    auto load_s = [&](float (&dst)[kG][V], const float *__restrict__ p) {
+#pragma unroll
+        for (int k = 0; k < kG; ++k) {
+            if (V == 2) {
+                const float2 v = *reinterpret_cast<const float2 *>(p + k * Xs);
+                dst[k][0] = v.x; dst[k][V - 1] = v.y;
+            } else {
+                dst[k][0] = p[k * Xs];
+            }
+        }
+    };
+    // one group: cur = this group's template values, prev = the previous group's, refilled with the next group's
+    auto group = [&](float (&cur)[kG][V], float (&prev)[kG][V], const float (&sv)[kG][V], const float *__restrict__ qnext) {
+#pragma unroll
+        for (int mm = 0; mm < kG; ++mm) {
+#pragma unroll
+            for (int r = 0; r < kBlock; ++r) {
+                const int slot = mm - r;
+#pragma unroll
+                for (int v = 0; v < V; ++v) B[r] = fmaf(slot >= 0 ? cur[slot][v] : prev[slot + kG][v], sv[mm][v], B[r]);
+            }
+            if (mm == 2) load_q(prev, qnext, 0);  // prev[0..3] are dead after step 1
+            if (mm == 6) load_q(prev, qnext, 4);  // prev[4..7] are dead after step 5
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < kG; ++k)
+#pragma unroll
+        for (int v = 0; v < V; ++v) qb[k][v] = 0.f;  // "group -1": nothing before the first tap
+    load_q(qa, qp, 0);
+    load_q(qa, qp, 4);
+    load_s(sa, sp);
+#pragma unroll 1
+    for (int g = 0; g < groups; g += 2) {
+        load_s(sb, sp + kG * Xs);
+        group(qa, qb, sa, qp + kG * Xs);   // qb <- template values of group g + 1
+        if (g + 1 >= groups) break;
+        load_s(sa, sp + 2 * kG * Xs);
+        group(qb, qa, sb, qp + 2 * kG * Xs);  // qa <- template values of group g + 2
+        qp += 2 * kG * Xs;
+        sp += 2 * kG * Xs;
+    }
+}
+
+// The fp32 correlation B[r] = sum_j q_j (w d)_{i0 + r X + j} of one block of kBlock candidates of width record wr.
+// With the stride X the taps split into residue classes j = X a + b; odd strides run one pass per class (neighbouring
+// lanes sit kBlock*X floats apart: odd, so the 32 banks are conflict free), even strides one pass per PAIR of classes
+// with 8-byte loads (candidates start at multiples of X, so the pairs are aligned, and lanes sit kBlock*X/2 eight-byte
+// units apart: odd again).  Every lane of a warp walks the classes in the same order: template loads are broadcasts.
+template <int kBlock, bool kUnit>
+__device__ __forceinline__ void tap_block32(const WidthRec &wr, const float *__restrict__ tq32,
+                                            const float *__restrict__ wd32, int c0, float (&B)[kBlock])
+{
+    constexpr int kG = kGroup32;
+    const int L = wr.L, X = kUnit ? 1 : wr.X;
+#pragma unroll
+    for (int r = 0; r < kBlock; ++r) B[r] = 0.f;
+    const float *__restrict__ qp = tq32 + wr.q;
+    const float *__restrict__ sp = wd32 + c0 * X;
+    const int groups = ((L + X - 1) / X + kBlock - 1 + kG - 1) / kG;  // steps: taps of the widest class + kBlock - 1
+    if (kUnit) {
+        tap_pass32<kBlock, 1, true>(qp, sp, 1, groups, B);
+    } else if ((X & 1) == 0) {
+        for (int b = 0; b < X && b < L; b += 2) tap_pass32<kBlock, 2, false>(qp + b, sp + b, X, groups, B);
+    } else {
+        for (int b = 0; b < X && b < L; ++b) tap_pass32<kBlock, 1, false>(qp + b, sp + b, X, groups, B);
+    }
+}
+
+__device__ __forceinline__ double chi2_value(double T, double D, double Aq, double B)
+{
+    return __fma_rn(D, __fma_rn(D, Aq, -2.0 * B), T);  // T + D (D Aq - 2 B), core.py:67-70 after the algebra of DESIGN.md §3
+}
+
+// What the exact evaluation of a finalist reads: cumulative sums, the fp64 products w*d (resident kernel: rebuilt
+// from the sorted sample ids, w0 * d[id], the same product the folded array held; tiled kernel: the CTA's scratch).
+template <bool kGather>
+struct ExactView {
+    const double *cs;      // cumulative sums, indexable by the global offset
+    const double *wd;      // !kGather: w*d per folded position
+    const double *dval;    // kGather: 1 - y per sample
+    const unsigned short *sid;  // kGather: sample id per folded position < N
+    const double *tq;
+    double w0, T;
+    int N;
+    __device__ __forceinline__ double wdv(int k) const
+    {
+        if (kGather) return __dmul_rn(w0, __ldg(dval + sid[k < N ? k : k - N]));
+        return wd[k];
+    }
+};
+
+// Exact fp64 chi2 of candidate c0 + rr of width record u, by one WARP (all 32 lanes must call with the same
+// arguments): lane l accumulates the taps j = l, l + 32, ... in ascending order, a fixed butterfly adds the 32
+// partial sums (every lane ends with the same bits), and every lane offers the candidate to its running best.
+// This is the ONLY place the equal-weights paths evaluate chi2 in fp64, so results do not depend on what the
+// filter let through.
+template <bool kGather>
+__device__ __forceinline__ void eval_exact_warp(const ExactView<kGather> &v, const WidthRec *rec, int c0, int rr, int u,
+                                                Best &best)
+{
+    const int lane = threadIdx.x & 31;
+    const WidthRec wr = rec[u];
+    const int L = wr.L, i = (c0 + rr) * wr.X;
+    const double *__restrict__ q = v.tq + wr.q;
+    double B = 0.0;
+#pragma unroll 4
+    for (int j = lane; j < L; j += 32) B = fma(__ldg(q + j), v.wdv(i + j), B);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) B += __shfl_xor_sync(kFull, B, off);
+    const double mean = (v.cs[i + wr.W] - v.cs[i]) * wr.invW;
+    const double D = mean * wr.os;
+    double chi = chi2_value(v.T, D, v.w0 * wr.sq2, B);
+    if (L < wr.W) {  // samples L..W-1 are in neither sum
+        double rest = 0.0;
+        for (int k = i + L + lane; k < i + wr.W; k += 32) {
+            const double x = v.wdv(k);
+            rest += x * x / v.w0;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) rest += __shfl_xor_sync(kFull, rest, off);
+        chi -= rest;
+    }
+    if (better(chi, u, i, best)) { best.chi2 = chi; best.D = D; best.u = u; best.i = i; }
+}
+
+// CTA-wide state of the filter in shared memory
+struct FilterShared {
+    unsigned long long U;  // bits of the smallest upper bound on chi2 so far (positive doubles order like integers)
+    int fq_fill;           // finalists queued in this round (may exceed the capacity: see kRedoFlag)
+    int pad_;
+};
+
+// Per-lane view of the threshold: U and the reduction a candidate has to reach, G = T - U, rounded down to fp32
+struct Threshold {
+    double U;
+    float G32;
+    __device__ __forceinline__ void set(double u, double T)
+    {
+        U = u;
+        G32 = __double2float_rd(T - u);
+    }
+    __device__ __forceinline__ void refresh(const FilterShared *fs, double T)
+    {
+        const double Ush = __longlong_as_double((long long)*(volatile const unsigned long long *)&fs->U);
+        if (Ush < U) set(Ush, T);
+    }
+};
+
+constexpr int kRedoFlag = 1 << 30;  // survivor-queue entry: the finalist queue was full, evaluate the whole block exactly
+
+// After tap_block32, cheap screen in fp32.  chi2 = T - R with the reduction R = D (2 B - D Aq); a candidate can only
+// matter if R + (error bounds) >= G = T - U.  R is evaluated in fp32 from D rounded to fp32: against the exact
+// R(B32) that costs less than 16 u relative to the magnitude of its terms (D: 3 roundings, Aq: 1, three
+// operations), covered by 2e-6 |D| (2 |B| + |D| Aq); 2 |D| EB bounds |R(B32) - R(B64)| (see tap_block32) and slopT the
+// fp64 evaluation roundings.  Returns the candidates that are NOT ruled out (they get exact fp64 bounds next).  NaN
+// anywhere fails safe.  diff[] returns the window sums cs[i+W] - cs[i].
+template <int kBlock, bool kUnit>
+__device__ __forceinline__ int block_screen(const WidthRec &wr, const double *cs, double w0, int c0, int mask,
+                                            const float (&B)[kBlock], float G32, float EB2f, float slopTf,
+                                            double (&diff)[kBlock])
+{
+    double lo[kBlock], hi[kBlock];
+    const int X = kUnit ? 1 : wr.X;
+    const double *__restrict__ p = cs + c0 * X;
+    const double *__restrict__ ph = p + wr.W;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        lo[rr] = p[rr * X];
+        hi[rr] = ph[rr * X];
+    }
+    const float c1 = (float)(wr.invW * wr.os), Aq32 = (float)(w0 * wr.sq2);
+    int keep = 0;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        diff[rr] = hi[rr] - lo[rr];
+        const float Df = (float)diff[rr] * c1, aD = fabsf(Df);
+        const float R = Df * fmaf(-Df, Aq32, 2.f * B[rr]);
+        const float m = fmaf(aD * fmaf(aD, Aq32, 2.f * fabsf(B[rr])), 2e-6f, fmaf(aD, EB2f, slopTf));
+        keep |= (R + m < G32 ? 0 : 1) << rr;
+    }
+    if (wr.L < wr.W) keep = -1;  // the untouched tail adds to R: no screen for trimmed templates (rare)
+    return keep & mask;
+}
+
+// Exact fp64 bounds of the candidates in `keep` (clo; +inf for the others) and update of the threshold with their
+// upper bounds.
+template <int kBlock, bool kUnit>
+__device__ __forceinline__ int block_bounds(const WidthRec &wr, const float *wd32, double w0, double T, double EB, int c0,
+                                            int keep, const float (&B)[kBlock], const double (&diff)[kBlock],
+                                            Threshold &th, FilterShared *fs, double (&clo)[kBlock])
+{
+    const int X = kUnit ? 1 : wr.X;
+    const int i0 = c0 * X;
+    const double Aq = w0 * wr.sq2;
+    double U_new = th.U;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        clo[rr] = INFINITY;
+        if (!((keep >> rr) & 1)) continue;
+        const double D = diff[rr] * wr.invW * wr.os;
+        const double Bd = (double)B[rr];
+        const double chi = chi2_value(T, D, Aq, Bd);
+        // |chi32 - chi64| <= 2 |D| EB + the roundings of two fp64 evaluations of the same expression
+        const double E = 2.0 * fabs(D) * EB + 1e-14 * (fabs(T) + fabs(D) * (fabs(D) * Aq + 2.0 * fabs(Bd)));
+        double l = chi - E, h = chi + E;
+        if (wr.L < wr.W) {  // the untouched tail only lowers chi2: [tail (1 - e), tail (1 + e)] from the fp32 samples
+            float rest = 0.f;
+            for (int k = i0 + rr * X + wr.L; k < i0 + rr * X + wr.W; ++k) rest = fmaf(wd32[k], wd32[k], rest);
+            const double tail = (double)rest / w0, e = (double)(wr.W - wr.L + 4) * 1.2e-7;
+            l -= tail * (1.0 + e);
+            h -= tail * (1.0 - e);
+        }
+        clo[rr] = l;
+        if (h < U_new) U_new = h;
+    }
+    if (U_new < th.U) {
+        th.set(U_new, T);
+        if (U_new > 0.0) atomicMin(&fs->U, (unsigned long long)__double_as_longlong(U_new));
+    }
+    int fin = 0;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) fin |= (((keep >> rr) & 1) && !(clo[rr] > th.U) ? 1 : 0) << rr;
+    return fin;
+}
+
+// Finalists (bit rr of `fin`) go to the finalist queue together with their lower bound (rounded down to fp32; it is
+// checked again against the final threshold before the exact evaluation).  Queue full: the block's entry in the
+// survivor queue is flagged and drain_finalists evaluates all of its candidates.
+template <int kBlock>
+__device__ __forceinline__ void block_push(int c0, int fin, int u, const double (&clo)[kBlock], FilterShared *fs, int2 *fq,
+                                           float *fq_lo, int fq_cap, int2 *entry)
+{
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        if ((fin >> rr) & 1) {
+            const int slot = atomicAdd(&fs->fq_fill, 1);
+            if (slot < fq_cap) {
+                fq[slot] = make_int2(c0, u | (rr << 16));
+                fq_lo[slot] = __double2float_rd(clo[rr]);
+            } else {
+                entry->y |= kRedoFlag;
+            }
+        }
+    }
+}
+
+// The queued finalists, one per warp at a time (call after a barrier, all threads of the CTA): each is checked
+// against the current threshold once more (most were queued while it was still settling), evaluated in fp64, and
+// its exact chi2 tightens the threshold for the rest.
+template <int kT, int kBlock, bool kGather>
+__device__ __forceinline__ void drain_finalists(const WidthRec *rec, FilterShared *fs, const int2 *fq, const float *fq_lo,
+                                                int fq_cap, const int2 *queue, int qfill, const ExactView<kGather> &view,
+                                                Best &best, unsigned long long *stats)
+{
+    constexpr int kW = kT / 32;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int filled = fs->fq_fill;
+    const int nf = min(filled, fq_cap);
+    for (int k = wid; k < nf; k += kW) {
+        const double U = __longlong_as_double((long long)*(volatile unsigned long long *)&fs->U);
+        if ((double)fq_lo[k] > U) continue;
+        const int2 e = fq[k];
+        const double before = best.chi2;
+        eval_exact_warp<kGather>(view, rec, e.x, e.y >> 16, e.y & 0xffff, best);
+        if (lane == 0 && best.chi2 < before && best.chi2 > 0.0)
+            atomicMin(&fs->U, (unsigned long long)__double_as_longlong(best.chi2));
+        if (stats && lane == 0) atomicAdd(stats + 1, 1ull);
+    }
+    if (filled > fq_cap) {  // the finalist queue overflowed: every candidate of the flagged blocks, exactly
+        for (int k = wid; k < qfill; k += kW) {
+            const int2 e = queue[k];
+            if (!(e.y & kRedoFlag)) continue;
+            const int u = e.y & 0xffff, mask = (e.y >> 16) & 0x3fff;
+            for (int rr = 0; rr < kBlock; ++rr)
+                if ((mask >> rr) & 1) {
+                    eval_exact_warp<kGather>(view, rec, e.x, rr, u, best);
+                    if (stats && lane == 0) atomicAdd(stats + 2, 1ull);
+                }
+        }
+    }
+}
+
+// max |x_k| over k < n, the same value in every thread (all threads must call; scratch: kT/32 doubles, shared)
+template <int kT>
+__device__ double block_max_abs(const double *__restrict__ x, int n, double *scratch)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double m = 0.0;
+    for (int k = tid; k < n; k += kT) m = fmax(m, fabs(__ldg(x + k)));
+#pragma unroll
+    for (int off = 16; off; off >>= 1) m = fmax(m, __shfl_xor_sync(kFull, m, off));
+    __syncthreads();
+    if (lane == 0) scratch[wid] = m;
+    __syncthreads();
+    double r = 0.0;
+    for (int k = 0; k < kT / 32; ++k) r = fmax(r, scratch[k]);
+    __syncthreads();
+    return r;
 }
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }

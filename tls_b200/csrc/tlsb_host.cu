@@ -83,6 +83,7 @@ struct Layout {
     int threads = 256;     // 256 (two CTAs per SM) or 512 (one)
     int ctas_per_sm = 2;
     int qcap = 4096;
+    int fq_cap = 0;        // finalist queue of the fp32 filter pass (0: the layout has no filter)
     int NB = 0;
     size_t smem = 0;
     size_t scratch_per_cta = 0;
@@ -118,7 +119,10 @@ struct tlsb_handle {
     tlsb_params prm{};
     int nU = 0, M = 0, pad = 0;
     std::vector<WidthRec> recs;   // unique widths, ascending
-    DevBuf tq, d_rec;
+    DevBuf tq, tq32, d_rec, filter_stats;
+    std::vector<float> h_tq32;    // float copy of h_tq for the fp32 filter pass
+    int filter_mode = 1;          // 1: fp32 filter pass on (equal weights); 0: every candidate through the exact evaluation
+    bool want_stats = false;      // count candidates / finalists on the device (tlsb_last_filter_stats)
     bool have_tp = false;
     bool recs_stale = true;       // ncand/tiles/cum depend on N + M
     int rec_kb = 0;               // ... and on the block size R the tiles were counted for
@@ -220,10 +224,18 @@ int host_plan(tlsb_handle *h)
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-size_t tail_bytes(int nU, int threads)
+size_t tail_bytes(int nU, int threads) { return filter_tail_bytes(nU, threads); }
+
+// resident layout with the fp32 filter pass (equal weights): cs | sorted ids (u16) | tail | area, the area being the
+// larger of the sort's scratch (keys, histogram with N buckets, bucket-ordered ids) and the search's arrays (w*d in
+// fp32, survivor queue, finalist queue); mirrors the carve in tlsb_search_kernel
+size_t resident_filter_smem_bytes(int N, int M, int pad, int nU, int qcap, int fq_cap, int threads, int NB)
 {
-    const int kW = threads / 32;
-    return (size_t)nU * sizeof(WidthRec) + (size_t)(2 * kW + 2) * 8 + (size_t)2 * kW * 4 + 16;
+    const size_t NM = (size_t)N + M, NMP = NM + pad;
+    const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
+    const size_t sort_area = (size_t)N * 8 + ((size_t)NB + 1) * 4 + (size_t)N * 2;
+    const size_t search_area = ((NMP + 3) & ~(size_t)3) * 4 + (size_t)qcap * 8 + (size_t)fq_cap * 12;
+    return cs + align16((size_t)N * 2) + tail_bytes(nU, threads) + align16(std::max(sort_area, search_area));
 }
 
 size_t resident_smem_bytes(int N, int M, int pad, int nU, bool uniform, int qcap, int threads)
@@ -243,6 +255,26 @@ Layout choose_layout(const tlsb_handle *h)
     const char *kbe = std::getenv("TLSB_BLOCK");  // experiments: force 5
     const int kb_pref = (h->uniform_w && !(kbe && std::atoi(kbe) == 5)) ? 7 : 5;
     best.kb = kb_pref;
+    if (N < 65536 && h->path_mode <= 1 && h->uniform_w && kb_pref == 7) {
+        // equal weights: fp32 filter pass; the folded curve costs 8 (cs) + 4 (w*d in fp32) + 2 (ids) bytes per sample
+        // threads, CTAs per SM, survivor queue, finalist queue, phase buckets of the sort as a divisor of N
+        const int tries[7][5] = {{256, 2, 3584, 1024, 1}, {256, 2, 3072, 1024, 1}, {256, 2, 3072, 1024, 2}, {256, 2, 3072, 512, 3},
+                                 {256, 2, 2560, 512, 4}, {512, 1, 8192, 2048, 1}, {512, 1, 4096, 1024, 1}};
+        for (const auto &t : tries) {
+            const int NB = std::max(64, N / t[4]);
+            const size_t bytes = resident_filter_smem_bytes(N, h->M, h->pad, h->nU, t[2], t[3], t[0], NB);
+            if (bytes > h->max_smem) continue;
+            if ((bytes + 1024) * (size_t)t[1] > h->smem_per_sm) continue;
+            best.resident = true;
+            best.threads = t[0];
+            best.ctas_per_sm = t[1];
+            best.qcap = t[2];
+            best.fq_cap = t[3];
+            best.NB = NB;
+            best.smem = bytes;
+            return best;
+        }
+    }
     if (N < 65536 && h->path_mode <= 1) {
         const int tries[2][2] = {{256, 2}, {512, 1}};
         const int qcaps[3] = {4096, 3584, 3072};
@@ -442,6 +474,15 @@ int enqueue_search(tlsb_handle *h, cudaStream_t s, void *records_dev, bool exact
     a.seg_cap = lay.seg_cap;
     a.n_seg = lay.n_seg;
     a.n_tiled = lay.tiled ? lay.n_tiled : h->nU;
+    a.tq32 = h->tq32.as<float>();
+    a.filter = h->filter_mode;
+    a.fq_cap = lay.fq_cap;
+    a.stats = nullptr;
+    if (h->want_stats && lay.fq_cap > 0) {
+        if (h->filter_stats.ensure(32)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
+        if (!only) CUDA_TRY(cudaMemsetAsync(h->filter_stats.p, 0, 32, s));
+        a.stats = h->filter_stats.as<unsigned long long>();
+    }
     const int grid = std::min(only ? n_only : P, h->num_sms * lay.ctas_per_sm);
     if (!lay.resident) {
         if (lay.NB < 1) return fail(TLSB_ERR_ARG, "too many distinct template widths for shared memory");
@@ -559,6 +600,7 @@ int tlsb_create(tlsb_handle **out, int32_t device)
     tlsb_handle *h = new (std::nothrow) tlsb_handle();
     if (!h) return fail(TLSB_ERR_ALLOC, "out of host memory");
     h->device = device;
+    if (const char *fe = std::getenv("TLSB_FILTER")) h->filter_mode = std::atoi(fe) != 0;  // experiments / tests
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
@@ -580,7 +622,7 @@ int tlsb_destroy(tlsb_handle *h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     for (DevBuf *b : {&h->t, &h->y, &h->dy, &h->dval, &h->wval, &h->tq, &h->d_rec, &h->periods, &h->ulo,
-                      &h->uhi, &h->order, &h->bin_of, &h->out, &h->counter, &h->scratch, &h->t0_trials, &h->t0_model,
+                      &h->uhi, &h->order, &h->bin_of, &h->out, &h->tq32, &h->filter_stats, &h->counter, &h->scratch, &h->t0_trials, &h->t0_model,
                       &h->t0_resid, &h->plan_bins, &h->unsure, &h->asc_order, &h->brec, &h->bchi, &h->bSR, &h->bpr, &h->bpw, &h->bscal, &h->bamax})
         b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -695,6 +737,7 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
         wr.W = (int)W;
         wr.L = (int)L;
         wr.row = r;
+        while (tq.size() % 4) tq.push_back(0.0);  // the fp32 copy is read as float4: 16-byte aligned template starts
         wr.q = (int)tq.size();
         wr.os = tp->overshoot[r];
         wr.invW = 1.0 / (double)W;
@@ -712,20 +755,24 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
         wr.tiles = 0;
         wr.cum = 0;
         const double *s = tp->signal + tp->offset[r];
-        double sq2 = 0.0;
+        double sq2 = 0.0, qabs = 0.0;
         for (int64_t j = 0; j < L; ++j) {
             const double q = (1 - s[j]) / kSignalDepth;  // core.py:61-68
             tq.push_back(q);
             sq2 = std::fma(q, q, sq2);
+            qabs += std::fabs(q);
         }
         wr.sq2 = sq2;
+        wr.eb = (double)(L + 8) * 5.9604644775390625e-08 * qabs * (1.0 + 1e-6);  // tlsb_device.cuh: the filter's bound
         for (int j = 0; j < xth * kPadGroups * kBlockMax; ++j) tq.push_back(0.0);  // ramp-out + pipeline overshoot
     }
     int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
     int rc;
     h->h_tq.swap(tq);  // stays alive behind the asynchronous upload
+    h->h_tq32.assign(h->h_tq.begin(), h->h_tq.end());
     if ((rc = upload(h->tq, h->h_tq.data(), h->h_tq.size() * 8))) return rc;
+    if ((rc = upload(h->tq32, h->h_tq32.data(), h->h_tq32.size() * 4))) return rc;
     if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
     h->recs.swap(recs);
     h->pad = kPadGroups * kBlockMax * xmax;
@@ -768,6 +815,28 @@ int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles)
     if (!h || path < 0 || path > 3) return fail(TLSB_ERR_ARG, "tlsb_set_path: path must be 0..3");
     h->path_mode = path;
     h->chunk_cap = chunk_doubles;
+    return 0;
+}
+
+int tlsb_set_filter(tlsb_handle *h, int32_t mode, int32_t count_stats)
+{
+    if (!h || mode < 0 || mode > 1) return fail(TLSB_ERR_ARG, "tlsb_set_filter: mode must be 0 or 1");
+    h->filter_mode = mode;
+    h->want_stats = count_stats != 0;
+    return 0;
+}
+
+int tlsb_last_filter_stats(tlsb_handle *h, int64_t *candidates, int64_t *finalists, int64_t *overflows)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_last_filter_stats: NULL handle");
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (h->filter_stats.p && h->want_stats) {
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaMemcpy(v, h->filter_stats.p, 32, cudaMemcpyDeviceToHost));  // synchronises
+    }
+    if (candidates) *candidates = (int64_t)v[0];
+    if (finalists) *finalists = (int64_t)(v[1] + v[2]);
+    if (overflows) *overflows = (int64_t)v[2];
     return 0;
 }
 

@@ -46,7 +46,8 @@ int spectra_device(const double *chi2, int64_t P, int64_t n_curves, int64_t win,
 constexpr int kBlockMax = 7;          // host-side slack (template padding, array slack) is sized for the largest R
 constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per queue reservation
 __host__ __device__ constexpr int tile_size(int kb) { return 32 * kb * kSub; }  // candidates one warp gates at a time
-constexpr int kPadGroups = 3;         // slack (in groups of kBlock steps) behind templates and patched arrays
+constexpr int kPadGroups = 4;         // slack (in groups of kBlock steps) behind templates and patched arrays
+constexpr int kGroup32 = 8;           // steps per unrolled group of the fp32 tap loop (template values arrive as two float4)
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr int kResScanItems = 19;     // ... of the resident kernel: one tile covers 19 * 256 = 4864 samples (cfg-1: one tile, 3 barriers)
 #ifndef TLSB_RES_HSCAN
@@ -84,6 +85,7 @@ struct WidthRec {
     double os;    // overshoot
     double invW;  // 1 / W
     double sq2;   // sum_j q_j^2 (the quadratic term when all weights are equal)
+    double eb;    // fp32 filter pass: |B32 - B64| <= eb * max|w d|, eb = (L + 8) * 2^-24 * sum_j |q_j| (rounded up)
 };
 
 struct PlanArgs {
@@ -136,6 +138,13 @@ struct SearchArgs {
     int seg_cap;          // tiled path, on-chip sort: elements per phase segment (0: sort in global scratch)
     int n_seg;            // number of phase segments (<= kMaxSegments)
     int n_tiled;          // tiled path: unique widths [0, n_tiled) are searched from staged chunks, the rest from L2
+    // fp32 filter pass (equal weights): every surviving candidate gets an fp32 correlation with a rigorous error
+    // bound first; only candidates whose lower bound does not exceed the best upper bound so far ("finalists") are
+    // evaluated in fp64.  Results are bit-identical with the filter on or off (filter = 0: everyone is a finalist).
+    const float *tq32;    // float copy of tq (same offsets)
+    int filter;           // 1: filter on; 0: every candidate goes through the exact evaluation (tests)
+    int fq_cap;           // capacity of the CTA-wide finalist queue
+    unsigned long long *stats;  // [4] optional device counters: candidates, finalists, queue overflows (NULL: off)
 };
 
 // tls_constants.py:20-25,78 and grid.py:9-32 (T14); same operation order on host and device
@@ -148,6 +157,13 @@ __host__ __device__ inline double t14_fraction(double R_s, double M_s, double P,
     const double t14 = small ? R * cube : (R + 2 * R_jup) * cube;
     const double frac = t14 / Ps;
     return frac > 0.12 ? 0.12 : frac;
+}
+
+// bytes of the small shared-memory tail (width records, reduction scratch, filter state, scheduler words), 16-aligned
+__host__ __device__ inline size_t filter_tail_bytes(int nU, int threads)
+{
+    const int kW = threads / 32;
+    return ((size_t)nU * sizeof(WidthRec) + (size_t)(2 * kW + 2) * 8 + 16 + (size_t)2 * kW * 4 + 16 + 15) & ~(size_t)15;
 }
 
 // what a candidate block of width record wr may read behind its start offset

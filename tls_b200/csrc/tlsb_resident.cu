@@ -22,13 +22,35 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     // w    : NMP doubles      weights (not kept when all weights are equal)
     // wd   : NMP doubles      w*d                                   [the sorted d before that]
     // queue: qcap int2        survivor blocks                       [resident: H + sid while sorting]
+    // kFilter (resident, equal weights): cs | sorted sample ids (u16) | tail | area, where the area holds the sort's
+    // keys, histogram and bucket-ordered ids first and then wd32 (the products w*d rounded to fp32), the survivor
+    // queue and the finalist queue.
+    constexpr bool kFilter = kResident && kUniformW;
     const size_t cs_elems = (size_t)(NM + 2) & ~(size_t)1;
     double *cs, *w, *wd;
     idx_t *sid;
     int *H;
     int2 *queue;
     unsigned char *tail;
-    if (kResident) {
+    float *wd32 = nullptr;
+    idx_t *sid_sorted = nullptr;
+    int2 *fq = nullptr;
+    float *fq_lo = nullptr;
+    double *skey;
+    if (kFilter) {
+        cs = reinterpret_cast<double *>(smem_raw);
+        w = wd = nullptr;
+        sid_sorted = reinterpret_cast<idx_t *>(cs + cs_elems);
+        tail = reinterpret_cast<unsigned char *>(sid_sorted) + (((size_t)N * sizeof(idx_t) + 15) & ~(size_t)15);
+        unsigned char *area = tail + filter_tail_bytes(nU, kT);
+        skey = reinterpret_cast<double *>(area);
+        H = reinterpret_cast<int *>(skey + N);
+        sid = reinterpret_cast<idx_t *>(H + NB + 1);
+        wd32 = reinterpret_cast<float *>(area);
+        queue = reinterpret_cast<int2 *>(wd32 + (((size_t)NMP + 3) & ~(size_t)3));
+        fq = queue + a.qcap;
+        fq_lo = reinterpret_cast<float *>(fq + a.fq_cap);
+    } else if (kResident) {
         cs = reinterpret_cast<double *>(smem_raw);
         w = cs + cs_elems;
         wd = kUniformW ? w : w + NMP;
@@ -36,6 +58,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         H = reinterpret_cast<int *>(queue);
         sid = reinterpret_cast<idx_t *>(H + NB + 1);
         tail = reinterpret_cast<unsigned char *>(queue + a.qcap);
+        skey = wd;  // the sort keys borrow the wd area; the sorted d go straight to cs[1..N]
     } else {
         unsigned char *g = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
         cs = reinterpret_cast<double *>(g);
@@ -45,11 +68,12 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         queue = reinterpret_cast<int2 *>(smem_raw);
         H = reinterpret_cast<int *>(queue + a.qcap);
         tail = smem_raw + (size_t)a.qcap * 8 + (((size_t)(NB + 1) * 4 + 15) & ~(size_t)15);
+        skey = wd;
     }
-    double *skey = wd;  // the sort keys borrow the wd area; the sorted d go straight to cs[1..N]
     WidthRec *rec = reinterpret_cast<WidthRec *>(tail);                       // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
-    int *red_i = reinterpret_cast<int *>(red_d + 2 * kW + 2);                 // [2*kW]
+    FilterShared *fs = reinterpret_cast<FilterShared *>(red_d + 2 * kW + 2);  // (kFilter)
+    int *red_i = reinterpret_cast<int *>(fs + 1);                             // [2*kW]
     int *s_next = red_i + 2 * kW;  // [4] period slot, "tiles left" flag, queue fill, queue head
 
     for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
@@ -58,6 +82,9 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     const unsigned lt_mask = (1u << lane) - 1u;
     const double depth_min = a.depth_min;
     const int qstop = a.qcap - kW * 32 * kSub;  // gating pauses here: every warp can still add one tile
+    // filter pass: scale of the error bound = max |w d| over the light curve (period independent)
+    double eb_scale = 0.0;
+    if (kFilter) eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
 
     for (;;) {
         if (tid == 0) {
@@ -65,6 +92,10 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             s_next[1] = 0;
             s_next[2] = 0;
             s_next[3] = 0;
+            if (kFilter) {
+                fs->U = (unsigned long long)__double_as_longlong((double)N);  // core.py:46: a model must beat N to count
+                fs->fq_fill = 0;
+            }
         }
         __syncthreads();
         const int slot_p = s_next[0];
@@ -85,13 +116,12 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         }
 
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
-        fold_sort_gather<kT, idx_t, !kUniformW, false, (kResident ? kResSortU : 4), (kResident ? kResHScanItems : kScanItems)>(
-            a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w,
-                                                       reinterpret_cast<int *>(red_d));
+        fold_sort_gather<kT, idx_t, !kUniformW, false, (kResident ? kResSortU : 4), (kResident ? kResHScanItems : kScanItems), kFilter>(
+            a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w, reinterpret_cast<int *>(red_d), sid_sorted);
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
-        double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems)>(cs + 1, w, wd, a.w0, N, NM,
-                                                                                                 NMP, red_d);
+        double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems), !kFilter, kFilter>(
+            cs + 1, w, wd, a.w0, N, NM, NMP, red_d, 0, 0.0, wd32);
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
         if (lane == 0) red_d[kW + 1 + wid] = tpart;
@@ -169,6 +199,69 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             const int qfill = s_next[2];
             const bool more = s_next[1] != 0;
             // B2
+            if constexpr (kFilter) {
+                // fp32 correlation + rigorous bounds for every survivor; the few candidates that can still be the minimum
+                // go to the finalist queue and are evaluated in fp64 by all lanes afterwards
+                ExactView<true> view;
+                view.cs = cs; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
+                view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
+                Threshold th;
+                th.set((double)N, T);
+                th.refresh(fs, T);
+                const float slopTf = __double2float_ru(4e-14 * fabs(T));
+                bool first = true;  // the first batch of every warp settles the threshold before anything is queued
+                for (;;) {
+                    int h = 0;
+                    if (lane == 0) h = atomicAdd(&s_next[3], 32);
+                    h = __shfl_sync(kFull, h, 0);
+                    if (h >= qfill) {
+                        if (first) __syncthreads();
+                        break;
+                    }
+                    const bool have = h + lane < qfill;
+                    int2 e = make_int2(0, 0);
+                    double clo[kBlock];
+                    int fin = 0;
+                    if (have) {
+                        e = queue[h + lane];
+                        const int u = e.y & 0xffff, mask = e.y >> 16;
+                        const WidthRec wr = rec[u];
+                        const double EB = wr.eb * eb_scale;
+                        const float EB2f = __double2float_ru(2.000001 * EB);
+                        float B[kBlock];
+                        double diff[kBlock];
+                        th.refresh(fs, T);
+                        if (wr.X == 1) {
+                            tap_block32<kBlock, true>(wr, a.tq32, wd32, e.x, B);
+                            const int keep = block_screen<kBlock, true>(wr, cs, a.w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+                            if (keep) fin = block_bounds<kBlock, true>(wr, wd32, a.w0, T, EB, e.x, keep, B, diff, th, fs, clo);
+                        } else {
+                            tap_block32<kBlock, false>(wr, a.tq32, wd32, e.x, B);
+                            const int keep = block_screen<kBlock, false>(wr, cs, a.w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+                            if (keep) fin = block_bounds<kBlock, false>(wr, wd32, a.w0, T, EB, e.x, keep, B, diff, th, fs, clo);
+                        }
+                        if (a.stats) atomicAdd(a.stats, (unsigned long long)__popc(mask));
+                    }
+                    if (first) {
+                        __syncthreads();
+                        first = false;
+                        th.refresh(fs, T);
+                        if (fin) {  // the bounds were taken against a threshold that was still settling
+                            int still = 0;
+#pragma unroll
+                            for (int rr = 0; rr < kBlock; ++rr) still |= (((fin >> rr) & 1) && !(clo[rr] > th.U) ? 1 : 0) << rr;
+                            fin = still;
+                        }
+                    }
+                    if (fin) block_push<kBlock>(e.x, fin, e.y & 0xffff, clo, fs, fq, fq_lo, a.fq_cap, &queue[h + lane]);
+                }
+                __syncthreads();  // every finalist of this round is in the queue
+                drain_finalists<kT, kBlock, true>(rec, fs, fq, fq_lo, a.fq_cap, queue, qfill, view, best, a.stats);
+                if (!more) break;
+                __syncthreads();  // everyone has left the queues before they are reused
+                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; fs->fq_fill = 0; }
+                __syncthreads();
+            } else {
             for (;;) {
                 int h = 0;
                 if (lane == 0) h = atomicAdd(&s_next[3], 32);
@@ -193,6 +286,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             __syncthreads();  // everyone has left B2 before the queue is reused
             if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
             __syncthreads();
+            }
         }
 
         // ---- C. block arg-min with the reference's tie order ---------------------------

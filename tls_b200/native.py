@@ -22,7 +22,7 @@ EXPORTS = (
     "tlsb_final_t0_fit", "tlsb_final_t0_fit_lc", "tlsb_last_t0_fit_ms",
     "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info", "tlsb_last_block", "tlsb_resolve_plan", "tlsb_plan_repair_count",
     "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
-    "tlsb_current_device", "tlsb_last_tiled_widths",
+    "tlsb_current_device", "tlsb_last_tiled_widths", "tlsb_set_filter", "tlsb_last_filter_stats",
 )
 
 _c_i64 = ctypes.c_int64
@@ -104,6 +104,8 @@ def lib():
     L.tlsb_last_chunk.argtypes = [_c_vp]
     L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
     L.tlsb_last_sort_info.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp]
+    L.tlsb_set_filter.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
+    L.tlsb_last_filter_stats.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_spectra.argtypes = [ctypes.c_int32, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_set_lightcurves.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_int32]
     L.tlsb_select_lightcurve.argtypes = [_c_vp, _c_i64]
@@ -249,6 +251,7 @@ class Searcher(object):
             s = idle.pop()
             s.set_path("auto")
             s.set_plan_mode(0)
+            s.set_filter(os.environ.get("TLSB_FILTER", "1") != "0", False)
             return s
         s = cls(device=device)
         s._pool_key = device
@@ -369,6 +372,19 @@ class Searcher(object):
         path's chunk capacity in doubles (tests)."""
         code = {v: k for k, v in self.PATHS.items()}[path] if isinstance(path, str) else int(path)
         _check(lib().tlsb_set_path(self._h, code, int(chunk)), "tlsb_set_path")
+
+    def set_filter(self, on=True, count_stats=False):
+        """Equal weights: fp32 filter pass on (default) or off (every gate survivor through the exact fp64
+        evaluation; same results, slower); ``count_stats`` counts survivors / finalists on the device."""
+        _check(lib().tlsb_set_filter(self._h, 1 if on else 0, 1 if count_stats else 0), "tlsb_set_filter")
+
+    @property
+    def filter_stats(self):
+        """dict(candidates, finalists, overflows) of the last search (needs ``set_filter(count_stats=True)``)."""
+        c, f, o = _c_i64(0), _c_i64(0), _c_i64(0)
+        _check(lib().tlsb_last_filter_stats(self._h, ctypes.byref(c), ctypes.byref(f), ctypes.byref(o)),
+               "tlsb_last_filter_stats")
+        return dict(candidates=c.value, finalists=f.value, overflows=o.value)
 
     @property
     def path(self):
