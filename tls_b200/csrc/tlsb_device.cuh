@@ -799,6 +799,84 @@ __device__ __forceinline__ void drain_finalists(const WidthRec *rec, FilterShare
     }
 }
 
+// Phase B2 with the filter, one round of the survivor queue (all threads of the CTA must call; contains barriers).
+// Warps grab batches of 32 queue entries, run the fp32 correlation, the fp32 screen and - for what the screen lets
+// through - the exact bounds, and queue the finalists; then everybody drains the finalist queue.  `settle` (the
+// first round of a period): the threshold is still at its start value N, so every warp first takes ONE batch from
+// the TAIL of the queue (the narrowest widths: short templates, so the barrier behind them is cheap) and the
+// finalists of that batch are picked only after all warps have posted their upper bounds.
+// cs / wd32 must be indexable by the global offsets of the queue entries.
+template <int kT, int kBlock, bool kGather>
+__device__ __forceinline__ void filter_round(int2 *queue, int qfill, int *q_head, bool settle, const WidthRec *rec,
+                                             const double *cs, const float *wd32, const float *__restrict__ tq32, double w0,
+                                             double T, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo, int fq_cap,
+                                             const ExactView<kGather> &view, Best &best, unsigned long long *stats)
+{
+    constexpr int kW = kT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Threshold th;
+    th.set(INFINITY, T);
+    th.refresh(fs, T);
+    const float slopTf = __double2float_ru(4e-14 * fabs(T));
+    const int nbatch = (qfill + 31) / 32;
+    const int reserved = settle ? min(kW, nbatch) : 0;  // batches at the tail, one per warp, taken first
+    const int qlimit = 32 * (nbatch - reserved);
+    int stage = settle ? 0 : 1;
+    for (;;) {
+        int h = 0;
+        if (stage == 0) {
+            h = 32 * (nbatch - 1 - wid);
+            if (h < 0) {  // fewer batches than warps: nothing to take, but the barrier is for everybody
+                __syncthreads();
+                stage = 1;
+                continue;
+            }
+        } else {
+            if (lane == 0) h = atomicAdd(q_head, 32);
+            h = __shfl_sync(kFull, h, 0);
+            if (h >= qlimit) break;
+        }
+        const bool have = h + lane < qfill;
+        int2 e = make_int2(0, 0);
+        double clo[kBlock];
+        int fin = 0;
+        if (have) {
+            e = queue[h + lane];
+            const int u = e.y & 0xffff, mask = e.y >> 16;
+            const WidthRec wr = rec[u];
+            const double EB = wr.eb * eb_scale;
+            const float EB2f = __double2float_ru(2.000001 * EB);
+            float B[kBlock];
+            double diff[kBlock];
+            th.refresh(fs, T);
+            if (wr.X == 1) {
+                tap_block32<kBlock, true>(wr, tq32, wd32, e.x, B);
+                const int keep = block_screen<kBlock, true>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+                if (keep) fin = block_bounds<kBlock, true>(wr, wd32, w0, T, EB, e.x, keep, B, diff, th, fs, clo);
+            } else {
+                tap_block32<kBlock, false>(wr, tq32, wd32, e.x, B);
+                const int keep = block_screen<kBlock, false>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+                if (keep) fin = block_bounds<kBlock, false>(wr, wd32, w0, T, EB, e.x, keep, B, diff, th, fs, clo);
+            }
+            if (stats) atomicAdd(stats, (unsigned long long)__popc(mask));
+        }
+        if (stage == 0) {
+            __syncthreads();
+            stage = 1;
+            th.refresh(fs, T);
+            if (fin) {  // the bounds were taken against a threshold that was still settling
+                int still = 0;
+#pragma unroll
+                for (int rr = 0; rr < kBlock; ++rr) still |= (((fin >> rr) & 1) && !(clo[rr] > th.U) ? 1 : 0) << rr;
+                fin = still;
+            }
+        }
+        if (fin) block_push<kBlock>(e.x, fin, e.y & 0xffff, clo, fs, fq, fq_lo, fq_cap, &queue[h + lane]);
+    }
+    __syncthreads();  // every finalist of this round is in the queue
+    drain_finalists<kT, kBlock, kGather>(rec, fs, fq, fq_lo, fq_cap, queue, qfill, view, best, stats);
+}
+
 // max |x_k| over k < n, the same value in every thread (all threads must call; scratch: kT/32 doubles, shared)
 template <int kT>
 __device__ double block_max_abs(const double *__restrict__ x, int n, double *scratch)

@@ -304,6 +304,11 @@ Layout choose_layout(const tlsb_handle *h)
     const size_t cs = ((NM + 2) & ~(size_t)1) * 8;
     const size_t nmp_even = (NMP + 1) & ~(size_t)1;
     const int narr = h->uniform_w ? 2 : 3;
+    // bytes a folded sample takes in a staged chunk: cs (8) + w*d in fp32 (4) with equal weights (filter pass),
+    // cs + w + w*d in fp64 otherwise
+    const size_t elem = h->uniform_w ? 12 : 24;
+    const size_t nmp4 = (NMP + 3) & ~(size_t)3;
+    const int fq_cap = h->uniform_w ? 1024 : 0;
     int need_max = 0, need5 = 0;
     for (const WidthRec &wr : h->recs) {
         need_max = std::max(need_max, window_need(wr.W, wr.X, kb_pref));
@@ -318,12 +323,13 @@ Layout choose_layout(const tlsb_handle *h)
             size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);
             if (const char *cap = std::getenv("TLSB_SMEM_KB"))  // experiments: leave part of the SM's 256 KB to L1
                 per_cta = std::min(per_cta, (size_t)std::atoi(cap) * 1024 / (size_t)t[1]);
-            const size_t fixed = (size_t)t[2] * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 + (size_t)(kMaxSegments + 2) * 4;
+            const size_t fixed = (size_t)t[2] * 8 + (size_t)fq_cap * 12 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 +
+                                 (size_t)(kMaxSegments + 2) * 4;
             if (per_cta <= fixed) continue;
-            long long C = (long long)(((per_cta - fixed) / (8 * (size_t)narr)) & ~(size_t)1);
+            long long C = (long long)(((per_cta - fixed) / elem) & ~(size_t)3);
             const bool exact_cap = h->chunk_cap < 0;  // tests: cap the chunk exactly; widths that do not fit take the L2 pass
-            if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~1LL);
-            if (exact_cap) C = std::min<long long>(C, (long long)(-h->chunk_cap) & ~1LL);
+            if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~3LL);
+            if (exact_cap) C = std::min<long long>(C, (long long)(-h->chunk_cap) & ~3LL);
             int kb = kb_pref, n_tiled = h->nU;
             long long TP = 0;
             bool fits = C > need5;
@@ -376,13 +382,14 @@ Layout choose_layout(const tlsb_handle *h)
             best.qcap = t[2];
             best.chunk = (int)C;
             best.n_tiled = n_tiled;
-            best.NB = (int)std::min<long long>(N, (long long)narr * C * 2 - 2);
-            best.smem = (size_t)t[2] * 8 + (size_t)narr * (size_t)C * 8 + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 +
+            best.fq_cap = fq_cap;
+            best.NB = (int)std::min<long long>(N, (long long)(elem * (size_t)C / 4) - 2);
+            best.smem = (size_t)t[2] * 8 + (size_t)fq_cap * 12 + elem * (size_t)C + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 +
                         (size_t)(kMaxSegments + 2) * 4;
-            best.scratch_per_cta = cs + (size_t)(narr - 1) * nmp_even * 8 + align16((size_t)N * 4);
+            best.scratch_per_cta = cs + (size_t)(narr - 1) * nmp_even * 8 + (h->uniform_w ? nmp4 * 4 : 0) + align16((size_t)N * 4);
             // on-chip sort: segments of S keys sorted in the chunk area; 1.5x head room over N / n_seg
             const char *oc = std::getenv("TLSB_ONCHIP_SORT");  // "0" disables (experiments)
-            const size_t area = (size_t)narr * (size_t)C * 8;
+            const size_t area = elem * (size_t)C;
             long long S = (long long)(((area - 64) / (h->uniform_w ? 24 : 32)) & ~(size_t)1);
             S = std::min<long long>(S, (long long)kSegPerThread * t[0]);
             const long long ns = S > 0 ? (3LL * N + 2 * S - 1) / (2 * S) : 0;

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         int g_next = rec[uhi - 1].cum + wid;
         int cur_u = uhi - 1;
         int u_begin = rec[cur_u].cum, u_end = u_begin + rec[cur_u].tiles;  // tile range of width cur_u
+        int round = 0;
         for (;;) {
             // B1
             while (g_next < tile_end) {
@@ -205,58 +206,9 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
                 ExactView<true> view;
                 view.cs = cs; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
                 view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
-                Threshold th;
-                th.set((double)N, T);
-                th.refresh(fs, T);
-                const float slopTf = __double2float_ru(4e-14 * fabs(T));
-                bool first = true;  // the first batch of every warp settles the threshold before anything is queued
-                for (;;) {
-                    int h = 0;
-                    if (lane == 0) h = atomicAdd(&s_next[3], 32);
-                    h = __shfl_sync(kFull, h, 0);
-                    if (h >= qfill) {
-                        if (first) __syncthreads();
-                        break;
-                    }
-                    const bool have = h + lane < qfill;
-                    int2 e = make_int2(0, 0);
-                    double clo[kBlock];
-                    int fin = 0;
-                    if (have) {
-                        e = queue[h + lane];
-                        const int u = e.y & 0xffff, mask = e.y >> 16;
-                        const WidthRec wr = rec[u];
-                        const double EB = wr.eb * eb_scale;
-                        const float EB2f = __double2float_ru(2.000001 * EB);
-                        float B[kBlock];
-                        double diff[kBlock];
-                        th.refresh(fs, T);
-                        if (wr.X == 1) {
-                            tap_block32<kBlock, true>(wr, a.tq32, wd32, e.x, B);
-                            const int keep = block_screen<kBlock, true>(wr, cs, a.w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
-                            if (keep) fin = block_bounds<kBlock, true>(wr, wd32, a.w0, T, EB, e.x, keep, B, diff, th, fs, clo);
-                        } else {
-                            tap_block32<kBlock, false>(wr, a.tq32, wd32, e.x, B);
-                            const int keep = block_screen<kBlock, false>(wr, cs, a.w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
-                            if (keep) fin = block_bounds<kBlock, false>(wr, wd32, a.w0, T, EB, e.x, keep, B, diff, th, fs, clo);
-                        }
-                        if (a.stats) atomicAdd(a.stats, (unsigned long long)__popc(mask));
-                    }
-                    if (first) {
-                        __syncthreads();
-                        first = false;
-                        th.refresh(fs, T);
-                        if (fin) {  // the bounds were taken against a threshold that was still settling
-                            int still = 0;
-#pragma unroll
-                            for (int rr = 0; rr < kBlock; ++rr) still |= (((fin >> rr) & 1) && !(clo[rr] > th.U) ? 1 : 0) << rr;
-                            fin = still;
-                        }
-                    }
-                    if (fin) block_push<kBlock>(e.x, fin, e.y & 0xffff, clo, fs, fq, fq_lo, a.fq_cap, &queue[h + lane]);
-                }
-                __syncthreads();  // every finalist of this round is in the queue
-                drain_finalists<kT, kBlock, true>(rec, fs, fq, fq_lo, a.fq_cap, queue, qfill, view, best, a.stats);
+                filter_round<kT, kBlock, true>(queue, qfill, &s_next[3], round == 0, rec, cs, wd32, a.tq32, a.w0, T, eb_scale, fs,
+                                               fq, fq_lo, a.fq_cap, view, best, a.stats);
+                ++round;
                 if (!more) break;
                 __syncthreads();  // everyone has left the queues before they are reused
                 if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; fs->fq_fill = 0; }

@@ -25,7 +25,7 @@ namespace {
 // strongly clustered phases - and the caller then sorts in global scratch instead.
 template <int kT, bool kUniformW>
 __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsigned char *area, int *cnt,
-                                             double *gkey, unsigned *gid, double *cs1, double *w, double *wd,
+                                             double *gkey, unsigned *gid, double *cs1, double *w, double *wd, float *wd32,
                                              int nmp_even, double *red_d, double &tpart_out)
 {
     constexpr int kU = 4;                  // independent chains of the rank / gather loop
@@ -167,6 +167,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
             const double wv = kUniformW ? a.w0 : wv_s[q];
             const double x = wv * d;
             wd[pos] = x;
+            if (kUniformW) wd32[pos] = (float)x;  // the filter pass's samples
             tpart = fma(x, d, tpart);
             if (!kUniformW) w[pos] = wv;
             if (pos < M) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         __syncthreads();
     }
     // positions N .. NM-1 hold the wrapped d: continue the cumulative sum, weight them, zero the slack
-    wrap_weight_scan<kT, kUniformW, kSegScanItems>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry);
+    wrap_weight_scan<kT, kUniformW, kSegScanItems, true, kUniformW>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry, wd32);
     tpart_out = tpart;
     return true;
 }
@@ -206,18 +207,25 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     double *cs = reinterpret_cast<double *>(g);
     double *w = cs + cs_elems;
     double *wd = kUniformW ? w : w + nmp_even;
-    unsigned *sid = reinterpret_cast<unsigned *>(wd + nmp_even);
+    const size_t nmp4 = ((size_t)NMP + 3) & ~(size_t)3;
+    float *wd32 = reinterpret_cast<float *>(wd + nmp_even);  // equal weights: w*d rounded to fp32 (the filter pass)
+    unsigned *sid = kUniformW ? reinterpret_cast<unsigned *>(wd32 + nmp4) : reinterpret_cast<unsigned *>(wd + nmp_even);
     double *skey = wd;  // the sort keys borrow the wd area; the sorted d go straight to cs[1..N]
 
-    // ---- shared: queue | chunk of cs | [chunk of w] | chunk of wd | records, tables, scratch ----
+    // ---- shared: queue | finalist queue | chunk of cs | chunk of w*d in fp32 (equal weights) or chunks of w and w*d
+    //              | records, tables, scratch ----
     int2 *queue = reinterpret_cast<int2 *>(smem_raw);
-    double *cs_s = reinterpret_cast<double *>(queue + a.qcap);
+    int2 *fq = queue + a.qcap;
+    float *fq_lo = reinterpret_cast<float *>(fq + a.fq_cap);
+    double *cs_s = reinterpret_cast<double *>(fq_lo + a.fq_cap);
     double *w_s = cs_s + C;
     double *wd_s = kUniformW ? w_s : w_s + C;
+    float *wd32_s = reinterpret_cast<float *>(cs_s + C);
     int *H = reinterpret_cast<int *>(cs_s);  // phase A only: the histogram borrows the chunk area
-    WidthRec *rec = reinterpret_cast<WidthRec *>(wd_s + C);                   // [nU]
+    WidthRec *rec = kUniformW ? reinterpret_cast<WidthRec *>(wd32_s + C) : reinterpret_cast<WidthRec *>(wd_s + C);  // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(red_d + 2 * kW + 2);
+    FilterShared *fs = reinterpret_cast<FilterShared *>(red_d + 2 * kW + 2);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(fs + 1);
     int *red_i = reinterpret_cast<int *>(bar + 1);                            // [2*kW]
     int *s_next = red_i + 2 * kW;  // [8] period slot, "tiles left" flag, queue fill, queue head, chunk tiles
     int *ch_lo = s_next + 8;       // [nU] first candidate of the chunk, per width
@@ -239,9 +247,17 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     const unsigned lt_mask = (1u << lane) - 1u;
     const double depth_min = a.depth_min;
     const int qstop = a.qcap - kW * 32 * kSub;
+    double eb_scale = 0.0;  // filter pass: scale of the error bound = max |w d| over the light curve
+    if (kUniformW) eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
 
     for (;;) {
-        if (tid == 0) s_next[0] = atomicAdd(a.counter, 1);
+        if (tid == 0) {
+            s_next[0] = atomicAdd(a.counter, 1);
+            if (kUniformW) {
+                fs->U = (unsigned long long)__double_as_longlong((double)N);  // core.py:46: a model must beat N to count
+                fs->fq_fill = 0;
+            }
+        }
         __syncthreads();
         const int slot_p = s_next[0];
         if (slot_p >= a.P) break;
@@ -266,13 +282,14 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         bool on_chip = false;
         if (a.seg_cap > 0)
             on_chip = sort_on_chip<kT, kUniformW>(a, r, reinterpret_cast<unsigned char *>(cs_s), seg_cnt, gkey, gid,
-                                                  cs + 1, w, wd, (int)nmp_even, red_d, tpart);
+                                                  cs + 1, w, wd, wd32, (int)nmp_even, red_d, tpart);
         if (!on_chip) {  // clustered phases (or no room for segments): sort in the global scratch
             if (tid == 0 && a.seg_cap > 0) atomicAdd(a.counter + 4, 1);
             fold_sort_gather<kT, unsigned, !kUniformW, false, 8>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval,
                                                                  cs + 1, w, reinterpret_cast<int *>(red_d));
             __syncthreads();
-            tpart = wrap_weight_scan<kT, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d);
+            tpart = wrap_weight_scan<kT, kUniformW, kScanItems, true, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d, 0,
+                                                                                 0.0, wd32);
         }
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
@@ -321,7 +338,10 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         };
 
         // gate + taps over the tables' tiles, widths ub-1 downwards; csb / wb / wdb are indexable by global offsets
-        auto sweep = [&](const double *csb, const double *wb, const double *wdb, int ub) {
+        ExactView<false> view;
+        view.cs = cs; view.wd = wd; view.dval = nullptr; view.sid = nullptr; view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
+        int round = 0;  // rounds of the survivor queue in this period (the first one settles the filter's threshold)
+        auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *wd32b, int ub) {
             const int tile_end = s_next[4];
             int g_next = wid;
             int cur_u = ub - 1;
@@ -378,46 +398,60 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 const int qfill = s_next[2];
                 const bool more = s_next[1] != 0;
                 // B2: taps
-                for (;;) {
-                    int h = 0;
-                    if (lane == 0) h = atomicAdd(&s_next[3], 32);
-                    h = __shfl_sync(kFull, h, 0);
-                    if (h >= qfill) break;
-                    if (h + lane < qfill) {
-                        const int2 e = queue[h + lane];
-                        const int u = e.y & 0xffff, mask = e.y >> 16;
-                        const WidthRec wr = rec[u];
-                        const int i0 = e.x * wr.X;
-                        double A[kBlock], B[kBlock];
-                        if (wr.X == 1) {
-                            tap_block<kBlock, true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
-                            block_min<kBlock, true, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
-                        } else {
-                            tap_block<kBlock, false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
-                            block_min<kBlock, false, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
+                if constexpr (kUniformW) {
+                    filter_round<kT, kBlock, false>(queue, qfill, &s_next[3], round == 0, rec, csb, wd32b, a.tq32, a.w0, T, eb_scale,
+                                                    fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
+                    ++round;
+                } else {
+                    for (;;) {
+                        int h = 0;
+                        if (lane == 0) h = atomicAdd(&s_next[3], 32);
+                        h = __shfl_sync(kFull, h, 0);
+                        if (h >= qfill) break;
+                        if (h + lane < qfill) {
+                            const int2 e = queue[h + lane];
+                            const int u = e.y & 0xffff, mask = e.y >> 16;
+                            const WidthRec wr = rec[u];
+                            const int i0 = e.x * wr.X;
+                            double A[kBlock], B[kBlock];
+                            if (wr.X == 1) {
+                                tap_block<kBlock, true, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
+                                block_min<kBlock, true, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
+                            } else {
+                                tap_block<kBlock, false, kUniformW>(wr, a.tq, wb, wdb, e.x, A, B);
+                                block_min<kBlock, false, kUniformW>(wr, csb, wb, wdb, a.w0, T, i0, mask, u, A, B, best);
+                            }
                         }
                     }
                 }
                 if (!more) break;
                 __syncthreads();
-                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
+                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; if (kUniformW) fs->fq_fill = 0; }
                 __syncthreads();
             }
         };
 
         if (ulo < uT) {
-            const int TP = (C - window_need(rec[uT - 1].W, rec[uT - 1].X, kBlock)) & ~1;
+            const int TP = (C - window_need(rec[uT - 1].W, rec[uT - 1].X, kBlock)) & ~3;  // 16-byte aligned fp32 chunks
             const int i_last = NM - rec[ulo].W;  // the narrowest admissible width has the most offsets
             for (int a0 = 0; a0 <= i_last; a0 += TP) {
                 fence_proxy_async();
                 __syncthreads();  // phase A / the previous chunk are done with the staging area and the tables
                 if (tid == 0) {
                     const int len_cs = min(C, (int)cs_elems - a0);
-                    const int len_wd = min(C, (int)nmp_even - a0);
-                    mbar_expect_tx(bar, 8u * (unsigned)(len_cs + (kUniformW ? 1 : 2) * len_wd));
-                    bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
-                    if (!kUniformW) bulk_copy_g2s(w_s, w + a0, 8u * (unsigned)len_wd, bar);
-                    bulk_copy_g2s(wd_s, wd + a0, 8u * (unsigned)len_wd, bar);
+                    if (kUniformW) {
+                        const int len_32 = min(C, (int)nmp4 - a0);
+                        mbar_expect_tx(bar, 8u * (unsigned)len_cs + 4u * (unsigned)len_32);
+                        bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
+                        bulk_copy_g2s(wd32_s, wd32 + a0, 4u * (unsigned)len_32, bar);
+                        fs->fq_fill = 0;
+                    } else {
+                        const int len_wd = min(C, (int)nmp_even - a0);
+                        mbar_expect_tx(bar, 8u * (unsigned)(len_cs + 2 * len_wd));
+                        bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
+                        bulk_copy_g2s(w_s, w + a0, 8u * (unsigned)len_wd, bar);
+                        bulk_copy_g2s(wd_s, wd + a0, 8u * (unsigned)len_wd, bar);
+                    }
                     s_next[1] = 0;
                     s_next[2] = 0;
                     s_next[3] = 0;
@@ -426,15 +460,15 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 __syncthreads();
                 mbar_wait(bar, parity);
                 parity ^= 1u;
-                sweep(cs_s - a0, w_s - a0, wd_s - a0, uT);
+                sweep(cs_s - a0, w_s - a0, wd_s - a0, wd32_s - a0, uT);
             }
         }
         if (uT < uhi) {  // the widest widths: gate and taps read the scratch through L1/L2
             __syncthreads();  // the last chunk's sweep is done with the queue and the tables
-            if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
+            if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; if (kUniformW) fs->fq_fill = 0; }
             build_tables(0, 1 << 30, max(ulo, uT), uhi);
             __syncthreads();
-            sweep(cs, w, wd, uhi);
+            sweep(cs, w, wd, wd32, uhi);
         }
 
         // ---- C. block arg-min with the reference's tie order ---------------------------
