@@ -614,8 +614,8 @@ struct ExactView {
 // This is the ONLY place the equal-weights paths evaluate chi2 in fp64, so results do not depend on what the
 // filter let through.
 template <bool kGather>
-__device__ __forceinline__ void eval_exact_warp(const ExactView<kGather> &v, const WidthRec *rec, int c0, int rr, int u,
-                                                Best &best)
+__device__ __noinline__ void eval_exact_warp(const ExactView<kGather> &v, const WidthRec *rec, int c0, int rr, int u,
+                                             Best &best)
 {
     const int lane = threadIdx.x & 31;
     const WidthRec wr = rec[u];
@@ -665,8 +665,6 @@ struct Threshold {
     }
 };
 
-constexpr int kRedoFlag = 1 << 30;  // survivor-queue entry: the finalist queue was full, evaluate the whole block exactly
-
 // After tap_block32, cheap screen in fp32.  chi2 = T - R with the reduction R = D (2 B - D Aq); a candidate can only
 // matter if R + (error bounds) >= G = T - U.  R is evaluated in fp32 from D rounded to fp32: against the exact
 // R(B32) that costs less than 16 u relative to the magnitude of its terms (D: 3 roundings, Aq: 1, three
@@ -701,180 +699,343 @@ __device__ __forceinline__ int block_screen(const WidthRec &wr, const double *cs
     return keep & mask;
 }
 
-// Exact fp64 bounds of the candidates in `keep` (clo; +inf for the others) and update of the threshold with their
-// upper bounds.
-template <int kBlock, bool kUnit>
-__device__ __forceinline__ int block_bounds(const WidthRec &wr, const float *wd32, double w0, double T, double EB, int c0,
-                                            int keep, const float (&B)[kBlock], const double (&diff)[kBlock],
-                                            Threshold &th, FilterShared *fs, double (&clo)[kBlock])
+// Exact fp64 bounds of ONE candidate the screen did not rule out (rare: kept out of line, scalars only, so that the
+// hot loop keeps its registers and its instruction-cache footprint): returns the lower bound of chi2 rounded down
+// to fp32 and lowers the CTA-wide threshold to the upper bound if that is smaller.
+//   diff = cs[i+W] - cs[i], B = the fp32 correlation, EB = the bound on |B32 - B64|;
+//   n_tail > 0: the template was trimmed (L < W) and wd32 + k_tail are the n_tail window samples it does not cover.
+__device__ __noinline__ float bound_one(double diff, float B, double invW, double os, double Aq, double EB, double T,
+                                        double w0, const float *wd32, int k_tail, int n_tail, FilterShared *fs)
 {
-    const int X = kUnit ? 1 : wr.X;
-    const int i0 = c0 * X;
-    const double Aq = w0 * wr.sq2;
-    double U_new = th.U;
-#pragma unroll
-    for (int rr = 0; rr < kBlock; ++rr) {
-        clo[rr] = INFINITY;
-        if (!((keep >> rr) & 1)) continue;
-        const double D = diff[rr] * wr.invW * wr.os;
-        const double Bd = (double)B[rr];
-        const double chi = chi2_value(T, D, Aq, Bd);
-        // |chi32 - chi64| <= 2 |D| EB + the roundings of two fp64 evaluations of the same expression
-        const double E = 2.0 * fabs(D) * EB + 1e-14 * (fabs(T) + fabs(D) * (fabs(D) * Aq + 2.0 * fabs(Bd)));
-        double l = chi - E, h = chi + E;
-        if (wr.L < wr.W) {  // the untouched tail only lowers chi2: [tail (1 - e), tail (1 + e)] from the fp32 samples
-            float rest = 0.f;
-            for (int k = i0 + rr * X + wr.L; k < i0 + rr * X + wr.W; ++k) rest = fmaf(wd32[k], wd32[k], rest);
-            const double tail = (double)rest / w0, e = (double)(wr.W - wr.L + 4) * 1.2e-7;
-            l -= tail * (1.0 + e);
-            h -= tail * (1.0 - e);
-        }
-        clo[rr] = l;
-        if (h < U_new) U_new = h;
+    const double D = diff * invW * os;
+    const double Bd = (double)B;
+    const double chi = chi2_value(T, D, Aq, Bd);
+    // |chi32 - chi64| <= 2 |D| EB + the roundings of two fp64 evaluations of the same expression
+    const double E = 2.0 * fabs(D) * EB + 1e-14 * (fabs(T) + fabs(D) * (fabs(D) * Aq + 2.0 * fabs(Bd)));
+    double l = chi - E, h = chi + E;
+    if (n_tail > 0) {  // the untouched tail only lowers chi2: [tail (1 - e), tail (1 + e)] from the fp32 samples
+        float rest = 0.f;
+        for (int k = k_tail; k < k_tail + n_tail; ++k) rest = fmaf(wd32[k], wd32[k], rest);
+        const double tail = (double)rest / w0, e = (double)(n_tail + 4) * 1.2e-7;
+        l -= tail * (1.0 + e);
+        h -= tail * (1.0 - e);
     }
-    if (U_new < th.U) {
-        th.set(U_new, T);
-        if (U_new > 0.0) atomicMin(&fs->U, (unsigned long long)__double_as_longlong(U_new));
-    }
-    int fin = 0;
-#pragma unroll
-    for (int rr = 0; rr < kBlock; ++rr) fin |= (((keep >> rr) & 1) && !(clo[rr] > th.U) ? 1 : 0) << rr;
-    return fin;
+    if (h > 0.0) atomicMin(&fs->U, (unsigned long long)__double_as_longlong(h));  // NaN compares false: no update
+    return __double2float_rd(l);
 }
 
-// Finalists (bit rr of `fin`) go to the finalist queue together with their lower bound (rounded down to fp32; it is
-// checked again against the final threshold before the exact evaluation).  Queue full: the block's entry in the
-// survivor queue is flagged and drain_finalists evaluates all of its candidates.
-template <int kBlock>
-__device__ __forceinline__ void block_push(int c0, int fin, int u, const double (&clo)[kBlock], FilterShared *fs, int2 *fq,
-                                           float *fq_lo, int fq_cap, int2 *entry)
+// What the cold paths of a sweep need, gathered once per sweep (lives in local memory)
+template <bool kGather>
+struct FilterCtx {
+    ExactView<kGather> view;
+    const WidthRec *rec;
+    FilterShared *fs;
+    int2 *fq;
+    float *fq_lo;
+    int fq_cap;
+    unsigned long long *stats;
+};
+
+// Finalists of one batch (bit rr of `fin`, lower bounds rounded down to fp32) go to the finalist queue once more
+// checked against the threshold as it is NOW; the bound travels with them and is checked a last time before the
+// exact evaluation.  All 32 lanes must call.  Queue full (rare): the warp evaluates the leftovers on the spot.
+template <int kBlock, bool kGather>
+__device__ __noinline__ void warp_push(const FilterCtx<kGather> &cx, int fin, int c0, int u, float l0, float l1, float l2,
+                                       float l3, float l4, float l5, float l6, Best &best)
 {
+    static_assert(kBlock <= 7, "warp_push carries seven bounds");
+    const float lo[7] = {l0, l1, l2, l3, l4, l5, l6};
+    const double U = __longlong_as_double((long long)*(volatile unsigned long long *)&cx.fs->U);
+    int over = 0;
 #pragma unroll
     for (int rr = 0; rr < kBlock; ++rr) {
-        if ((fin >> rr) & 1) {
-            const int slot = atomicAdd(&fs->fq_fill, 1);
-            if (slot < fq_cap) {
-                fq[slot] = make_int2(c0, u | (rr << 16));
-                fq_lo[slot] = __double2float_rd(clo[rr]);
+        if (((fin >> rr) & 1) && !((double)lo[rr] > U)) {
+            const int slot = atomicAdd(&cx.fs->fq_fill, 1);
+            if (slot < cx.fq_cap) {
+                cx.fq[slot] = make_int2(c0, u | (rr << 16));
+                cx.fq_lo[slot] = lo[rr];
             } else {
-                entry->y |= kRedoFlag;
+                over |= 1 << rr;
             }
         }
+    }
+    unsigned any = __ballot_sync(kFull, over != 0);
+    while (any) {
+        const int src = __ffs(any) - 1;
+        const int oc0 = __shfl_sync(kFull, c0, src), ou = __shfl_sync(kFull, u, src), oo = __shfl_sync(kFull, over, src);
+        for (int rr = 0; rr < kBlock; ++rr)
+            if ((oo >> rr) & 1) {
+                eval_exact_warp<kGather>(cx.view, cx.rec, oc0, rr, ou, best);
+                if (cx.stats && (threadIdx.x & 31) == 0) atomicAdd(cx.stats + 2, 1ull);
+            }
+        any &= any - 1;
     }
 }
 
 // The queued finalists, one per warp at a time (call after a barrier, all threads of the CTA): each is checked
 // against the current threshold once more (most were queued while it was still settling), evaluated in fp64, and
 // its exact chi2 tightens the threshold for the rest.
-template <int kT, int kBlock, bool kGather>
-__device__ __forceinline__ void drain_finalists(const WidthRec *rec, FilterShared *fs, const int2 *fq, const float *fq_lo,
-                                                int fq_cap, const int2 *queue, int qfill, const ExactView<kGather> &view,
-                                                Best &best, unsigned long long *stats)
+template <int kT, bool kGather>
+__device__ __forceinline__ void drain_finalists(const FilterCtx<kGather> &cx, Best &best)
 {
     constexpr int kW = kT / 32;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int filled = fs->fq_fill;
-    const int nf = min(filled, fq_cap);
+    const int nf = min(cx.fs->fq_fill, cx.fq_cap);
     for (int k = wid; k < nf; k += kW) {
-        const double U = __longlong_as_double((long long)*(volatile unsigned long long *)&fs->U);
-        if ((double)fq_lo[k] > U) continue;
-        const int2 e = fq[k];
+        const double U = __longlong_as_double((long long)*(volatile unsigned long long *)&cx.fs->U);
+        if ((double)cx.fq_lo[k] > U) continue;
+        const int2 e = cx.fq[k];
         const double before = best.chi2;
-        eval_exact_warp<kGather>(view, rec, e.x, e.y >> 16, e.y & 0xffff, best);
+        eval_exact_warp<kGather>(cx.view, cx.rec, e.x, e.y >> 16, e.y & 0xffff, best);
         if (lane == 0 && best.chi2 < before && best.chi2 > 0.0)
-            atomicMin(&fs->U, (unsigned long long)__double_as_longlong(best.chi2));
-        if (stats && lane == 0) atomicAdd(stats + 1, 1ull);
-    }
-    if (filled > fq_cap) {  // the finalist queue overflowed: every candidate of the flagged blocks, exactly
-        for (int k = wid; k < qfill; k += kW) {
-            const int2 e = queue[k];
-            if (!(e.y & kRedoFlag)) continue;
-            const int u = e.y & 0xffff, mask = (e.y >> 16) & 0x3fff;
-            for (int rr = 0; rr < kBlock; ++rr)
-                if ((mask >> rr) & 1) {
-                    eval_exact_warp<kGather>(view, rec, e.x, rr, u, best);
-                    if (stats && lane == 0) atomicAdd(stats + 2, 1ull);
-                }
-        }
+            atomicMin(&cx.fs->U, (unsigned long long)__double_as_longlong(best.chi2));
+        if (cx.stats && lane == 0) atomicAdd(cx.stats + 1, 1ull);
     }
 }
 
-// Phase B2 with the filter, one round of the survivor queue (all threads of the CTA must call; contains barriers).
-// Warps grab batches of 32 queue entries, run the fp32 correlation, the fp32 screen and - for what the screen lets
-// through - the exact bounds, and queue the finalists; then everybody drains the finalist queue.  `settle` (the
-// first round of a period): the threshold is still at its start value N, so every warp first takes ONE batch from
-// the TAIL of the queue (the narrowest widths: short templates, so the barrier behind them is cheap) and the
-// finalists of that batch are picked only after all warps have posted their upper bounds.
-// cs / wd32 must be indexable by the global offsets of the queue entries.
+// Finalists of a warp's previous batch: pushed one batch late, so that their bounds meet a threshold every active
+// warp has contributed to (most candidates qualify while the threshold is still at its start value).
+template <int kBlock>
+struct Pending {
+    int fin, c0, u;
+    float lo[kBlock];
+    __device__ __forceinline__ void clear()
+    {
+        fin = 0; c0 = 0; u = 0;
+#pragma unroll
+        for (int rr = 0; rr < kBlock; ++rr) lo[rr] = 0.f;
+    }
+    template <bool kGather>
+    __device__ __forceinline__ void push(const FilterCtx<kGather> &cx, Best &best)  // all 32 lanes must call
+    {
+        if (__any_sync(kFull, fin != 0))
+            warp_push<kBlock, kGather>(cx, fin, c0, u, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], best);
+        fin = 0;
+    }
+};
+
+// One batch of survivor blocks (one per lane, `have`): fp32 correlation, fp32 screen, exact bounds for what the
+// screen lets through; then the PREVIOUS batch's finalists are pushed and this batch's become pending.
+template <int kBlock, bool kGather>
+__device__ __forceinline__ void tap_batch(bool have, int2 e, const FilterCtx<kGather> &cx, const double *cs, const float *wd32,
+                                          const float *__restrict__ tq32, double w0, double T, double eb_scale, float slopTf,
+                                          Threshold &th, Pending<kBlock> &pend, Best &best)
+{
+    int fin = 0;
+    float lo_now[kBlock];
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) lo_now[rr] = 0.f;
+    if (have) {
+        const int u = e.y & 0xffff, mask = e.y >> 16;
+        const WidthRec wr = cx.rec[u];
+        const double EB = wr.eb * eb_scale;
+        const float EB2f = __double2float_ru(2.000001 * EB);
+        float B[kBlock];
+        double diff[kBlock];
+        th.refresh(cx.fs, T);
+        int keep;
+        if (wr.X == 1) {
+            tap_block32<kBlock, true>(wr, tq32, wd32, e.x, B);
+            keep = block_screen<kBlock, true>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+        } else {
+            tap_block32<kBlock, false>(wr, tq32, wd32, e.x, B);
+            keep = block_screen<kBlock, false>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+        }
+        if (keep) {  // rare
+            const double Aq = w0 * wr.sq2;
+#pragma unroll
+            for (int rr = 0; rr < kBlock; ++rr)
+                if ((keep >> rr) & 1)
+                    lo_now[rr] = bound_one(diff[rr], B[rr], wr.invW, wr.os, Aq, EB, T, w0, wd32, (e.x + rr) * wr.X + wr.L,
+                                           wr.W - wr.L, cx.fs);
+            th.refresh(cx.fs, T);
+#pragma unroll
+            for (int rr = 0; rr < kBlock; ++rr) fin |= (((keep >> rr) & 1) && !((double)lo_now[rr] > th.U) ? 1 : 0) << rr;
+        }
+        if (cx.stats) atomicAdd(cx.stats, (unsigned long long)__popc(mask));
+    }
+    pend.push(cx, best);  // the previous batch's finalists, against the threshold as it is now
+    pend.fin = fin;
+    pend.c0 = e.x;
+    pend.u = e.y & 0xffff;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) pend.lo[rr] = lo_now[rr];
+}
+
+// Scheduler words of one sweep in shared memory (all zero before a sweep starts)
+struct SweepShared {
+    int tile_next;   // next gate tile to hand out
+    int tiles_done;  // tiles whose survivors are in the ring
+    int q_tail;      // ring entries reserved by gating warps
+    int q_head;      // ring entries taken by tap warps
+    int q_done;      // ring entries read and cleared (their slots may be reused)
+    int pad_[3];
+};
+
+// Phases B1 + B2 of one sweep (equal weights) without a barrier between them: every warp switches roles as the
+// work demands.  A warp that finds a batch of 32 survivor blocks in the ring takes it (fp32 correlation, screen,
+// exact bounds, finalists); otherwise, if gate tiles are left and the ring has room, it gates the next tile and
+// appends the surviving blocks; it leaves when all tiles are gated and the ring is empty.  The ring is a
+// power-of-two array of int2 entries, (first candidate, width index | mask << 16); a slot is valid when its second
+// word is non-zero, readers clear it.  Tiles are numbered wide -> narrow: tile ids [0, t_tiles[ub-1]) belong to width
+// ub-1 and cover its candidates [t_lo, t_hi), and so on downwards.  Finalists are pushed one batch late, so that
+// their bounds meet a threshold every active warp has contributed to.  Ends with the finalist queue drained
+// (contains barriers: all threads of the CTA must call).  cs / wd32 must be indexable by global offsets.
 template <int kT, int kBlock, bool kGather>
-__device__ __forceinline__ void filter_round(int2 *queue, int qfill, int *q_head, bool settle, const WidthRec *rec,
-                                             const double *cs, const float *wd32, const float *__restrict__ tq32, double w0,
-                                             double T, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo, int fq_cap,
-                                             const ExactView<kGather> &view, Best &best, unsigned long long *stats)
+__device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int qmask, int tile_end, int ub, const int *t_lo,
+                                             const int *t_hi, const int *t_tiles, const WidthRec *rec, const double *cs,
+                                             const float *wd32, const float *__restrict__ tq32, double w0, double T,
+                                             double depth_min, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo,
+                                             int fq_cap, const ExactView<kGather> &view, Best &best,
+                                             unsigned long long *stats)
 {
     constexpr int kW = kT / 32;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int kTile = tile_size(kBlock);
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int qroom = qmask + 1 - kW * 32 * kSub;  // gating pauses above this fill: every warp can still add one tile
+    FilterCtx<kGather> cx;
+    cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats;
     Threshold th;
     th.set(INFINITY, T);
     th.refresh(fs, T);
     const float slopTf = __double2float_ru(4e-14 * fabs(T));
-    const int nbatch = (qfill + 31) / 32;
-    const int reserved = settle ? min(kW, nbatch) : 0;  // batches at the tail, one per warp, taken first
-    const int qlimit = 32 * (nbatch - reserved);
-    int stage = settle ? 0 : 1;
+    int cur_u = ub - 1, u_begin = 0, u_end = tile_end > 0 ? t_tiles[cur_u] : 0;
+    Pending<kBlock> pend;  // the previous batch's finalists, not pushed yet
+    pend.clear();
+    int idle = 0;
+    bool gating = true;  // the role this warp prefers; it keeps a role while there is work for it (instruction cache)
+    for (;;) {
+        const int head = *(volatile int *)&ss->q_head, tail = *(volatile int *)&ss->q_tail;
+        const int avail = tail - head;
+        const bool gate_done = *(volatile int *)&ss->tiles_done >= tile_end;
+        const bool can_tap = avail >= 32 || (gate_done && avail > 0);
+        const bool can_gate = !gate_done && *(volatile int *)&ss->tile_next < tile_end &&
+                              tail - *(volatile int *)&ss->q_done <= qroom;
+        if (gating) {
+            if (!can_gate || avail >= 32 * kW) gating = false;  // a batch for every warp is waiting
+        } else if (!can_tap) {
+            gating = true;
+        }
+        const bool do_tap = can_tap && (!gating || !can_gate);
+        const bool do_gate = !do_tap && can_gate;
+        if (do_tap) {
+            // ---- B2: one batch of survivor blocks ----
+            const int n = min(32, avail);
+            int ok = 0;
+            if (lane == 0) ok = atomicCAS(&ss->q_head, head, head + n) == head;
+            if (!__shfl_sync(kFull, ok, 0)) continue;
+            idle = 0;
+            const bool have = lane < n;
+            int2 e = make_int2(0, 0);
+            if (have) {
+                volatile unsigned long long *slot = reinterpret_cast<volatile unsigned long long *>(queue + ((head + lane) & qmask));
+                int spins = 0;
+                for (;;) {  // reserved before we took it, written in a moment
+                    const unsigned long long raw = *slot;
+                    e.x = (int)(unsigned)(raw & 0xffffffffull);
+                    e.y = (int)(unsigned)(raw >> 32);
+                    if (e.y != 0) break;
+                    if (++spins > (1 << 24)) __trap();
+                }
+                *slot = 0ull;
+            }
+            __syncwarp();
+            if (lane == 0) atomicAdd(&ss->q_done, n);
+            tap_batch<kBlock, kGather>(have, e, cx, cs, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
+            continue;
+        }
+        if (do_gate) {
+            // ---- B1: gate one tile ----
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&ss->tile_next, 1);
+            g = __shfl_sync(kFull, g, 0);
+            if (g >= tile_end) continue;
+            idle = 0;
+            while (g >= u_end) {
+                --cur_u;
+                u_begin = u_end;
+                u_end = u_begin + t_tiles[cur_u];
+            }
+            const int u = cur_u;
+            const int W = rec[u].W, X = rec[u].X, c_end = t_hi[u];
+            const double invW = rec[u].invW;
+            const int c_tile = t_lo[u] + (g - u_begin) * kTile + lane * kBlock;
+            int masks[kSub];
+            unsigned votes[kSub];
+            int total = 0;
+            if (X == 1) {
+#pragma unroll
+                for (int sb = 0; sb < kSub; ++sb)
+                    masks[sb] = gate_block<kBlock, true>(cs, c_tile + sb * 32 * kBlock, c_end, W, 1, invW, depth_min);
+            } else {
+#pragma unroll
+                for (int sb = 0; sb < kSub; ++sb)
+                    masks[sb] = gate_block<kBlock, false>(cs, c_tile + sb * 32 * kBlock, c_end, W, X, invW, depth_min);
+            }
+#pragma unroll
+            for (int sb = 0; sb < kSub; ++sb) {
+                votes[sb] = __ballot_sync(kFull, masks[sb] != 0);
+                total += __popc(votes[sb]);
+            }
+            if (total) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&ss->q_tail, total);
+                base = __shfl_sync(kFull, base, 0);
+#pragma unroll
+                for (int sb = 0; sb < kSub; ++sb) {
+                    if (masks[sb])
+                        queue[(base + __popc(votes[sb] & lt_mask)) & qmask] =
+                            make_int2(c_tile + sb * 32 * kBlock, u | (masks[sb] << 16));
+                    base += __popc(votes[sb]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&ss->tiles_done, 1);
+            }
+            continue;
+        }
+        if (gate_done && avail == 0) break;
+        if (++idle > (1 << 24)) __trap();  // never seen; a hang here would take the GPU with it
+        __nanosleep(20);
+    }
+    pend.push(cx, best);
+    __syncthreads();  // every finalist of this sweep is in the queue
+    drain_finalists<kT, kGather>(cx, best);
+}
+
+// The same work with the classic schedule, for layouts with two CTAs per SM (the other CTA fills this one's barrier
+// waits, and short batches make the ring's bookkeeping the larger cost): one ROUND of the survivor queue, filled by
+// the gate before a barrier; warps take batches of 32 entries until the queue is empty, then drain the finalists.
+template <int kT, int kBlock, bool kGather>
+__device__ __forceinline__ void filter_round(const int2 *queue, int qfill, int *q_head, const WidthRec *rec, const double *cs,
+                                             const float *wd32, const float *__restrict__ tq32, double w0, double T,
+                                             double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo, int fq_cap,
+                                             const ExactView<kGather> &view, Best &best, unsigned long long *stats)
+{
+    const int lane = threadIdx.x & 31;
+    FilterCtx<kGather> cx;
+    cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats;
+    Threshold th;
+    th.set(INFINITY, T);
+    th.refresh(fs, T);
+    const float slopTf = __double2float_ru(4e-14 * fabs(T));
+    Pending<kBlock> pend;
+    pend.clear();
     for (;;) {
         int h = 0;
-        if (stage == 0) {
-            h = 32 * (nbatch - 1 - wid);
-            if (h < 0) {  // fewer batches than warps: nothing to take, but the barrier is for everybody
-                __syncthreads();
-                stage = 1;
-                continue;
-            }
-        } else {
-            if (lane == 0) h = atomicAdd(q_head, 32);
-            h = __shfl_sync(kFull, h, 0);
-            if (h >= qlimit) break;
-        }
+        if (lane == 0) h = atomicAdd(q_head, 32);
+        h = __shfl_sync(kFull, h, 0);
+        if (h >= qfill) break;
         const bool have = h + lane < qfill;
-        int2 e = make_int2(0, 0);
-        double clo[kBlock];
-        int fin = 0;
-        if (have) {
-            e = queue[h + lane];
-            const int u = e.y & 0xffff, mask = e.y >> 16;
-            const WidthRec wr = rec[u];
-            const double EB = wr.eb * eb_scale;
-            const float EB2f = __double2float_ru(2.000001 * EB);
-            float B[kBlock];
-            double diff[kBlock];
-            th.refresh(fs, T);
-            if (wr.X == 1) {
-                tap_block32<kBlock, true>(wr, tq32, wd32, e.x, B);
-                const int keep = block_screen<kBlock, true>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
-                if (keep) fin = block_bounds<kBlock, true>(wr, wd32, w0, T, EB, e.x, keep, B, diff, th, fs, clo);
-            } else {
-                tap_block32<kBlock, false>(wr, tq32, wd32, e.x, B);
-                const int keep = block_screen<kBlock, false>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
-                if (keep) fin = block_bounds<kBlock, false>(wr, wd32, w0, T, EB, e.x, keep, B, diff, th, fs, clo);
-            }
-            if (stats) atomicAdd(stats, (unsigned long long)__popc(mask));
-        }
-        if (stage == 0) {
-            __syncthreads();
-            stage = 1;
-            th.refresh(fs, T);
-            if (fin) {  // the bounds were taken against a threshold that was still settling
-                int still = 0;
-#pragma unroll
-                for (int rr = 0; rr < kBlock; ++rr) still |= (((fin >> rr) & 1) && !(clo[rr] > th.U) ? 1 : 0) << rr;
-                fin = still;
-            }
-        }
-        if (fin) block_push<kBlock>(e.x, fin, e.y & 0xffff, clo, fs, fq, fq_lo, fq_cap, &queue[h + lane]);
+        const int2 e = have ? queue[h + lane] : make_int2(0, 0);
+        tap_batch<kBlock, kGather>(have, e, cx, cs, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
     }
+    pend.push(cx, best);
     __syncthreads();  // every finalist of this round is in the queue
-    drain_finalists<kT, kBlock, kGather>(rec, fs, fq, fq_lo, fq_cap, queue, qfill, view, best, stats);
+    drain_finalists<kT, kGather>(cx, best);
 }
 
 // max |x_k| over k < n, the same value in every thread (all threads must call; scratch: kT/32 doubles, shared)

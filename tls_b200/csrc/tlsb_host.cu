@@ -258,6 +258,7 @@ Layout choose_layout(const tlsb_handle *h)
     if (N < 65536 && h->path_mode <= 1 && h->uniform_w && kb_pref == 7) {
         // equal weights: fp32 filter pass; the folded curve costs 8 (cs) + 4 (w*d in fp32) + 2 (ids) bytes per sample
         // threads, CTAs per SM, survivor queue, finalist queue, phase buckets of the sort as a divisor of N
+        // (512 threads: the survivor queue is a ring, a power of two, at least twice what all warps can append at once)
         const int tries[7][5] = {{256, 2, 3584, 1024, 1}, {256, 2, 3072, 1024, 1}, {256, 2, 3072, 1024, 2}, {256, 2, 3072, 512, 3},
                                  {256, 2, 2560, 512, 4}, {512, 1, 8192, 2048, 1}, {512, 1, 4096, 1024, 1}};
         for (const auto &t : tries) {
@@ -317,7 +318,8 @@ Layout choose_layout(const tlsb_handle *h)
     const char *force = std::getenv("TLSB_TILED");  // "0": never, "256"/"512": force that CTA size (experiments)
     const int forced = force ? std::atoi(force) : -1;
     if (forced != 0 && h->path_mode != 3) {
-        const int tries[2][3] = {{256, 2, 3072}, {512, 1, 4096}};  // threads, CTAs per SM, queue entries
+        // threads, CTAs per SM, queue entries (equal weights: a ring, power of two)
+        const int tries[2][3] = {{256, 2, h->uniform_w ? 2048 : 3072}, {512, 1, 4096}};
         for (const auto &t : tries) {
             if (forced > 0 && forced != t[0]) continue;
             size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);

@@ -163,7 +163,8 @@ __host__ __device__ inline double t14_fraction(double R_s, double M_s, double P,
 __host__ __device__ inline size_t filter_tail_bytes(int nU, int threads)
 {
     const int kW = threads / 32;
-    return ((size_t)nU * sizeof(WidthRec) + (size_t)(2 * kW + 2) * 8 + 16 + (size_t)2 * kW * 4 + 16 + 15) & ~(size_t)15;
+    // records, reduction doubles, filter state (16), sweep scheduler (32), reduction ints, period scheduler (16), tile tables
+    return ((size_t)nU * sizeof(WidthRec) + (size_t)(2 * kW + 2) * 8 + 16 + 32 + (size_t)2 * kW * 4 + 16 + (size_t)nU * 12 + 15) & ~(size_t)15;
 }
 
 // what a candidate block of width record wr may read behind its start offset

@@ -73,11 +73,21 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     WidthRec *rec = reinterpret_cast<WidthRec *>(tail);                       // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
     FilterShared *fs = reinterpret_cast<FilterShared *>(red_d + 2 * kW + 2);  // (kFilter)
-    int *red_i = reinterpret_cast<int *>(fs + 1);                             // [2*kW]
+    SweepShared *ss = reinterpret_cast<SweepShared *>(fs + 1);                // (kFilter)
+    int *red_i = reinterpret_cast<int *>(ss + 1);                             // [2*kW]
     int *s_next = red_i + 2 * kW;  // [4] period slot, "tiles left" flag, queue fill, queue head
+    int *t_lo = s_next + 4;        // (kFilter) [nU] per width: first candidate, one past the last, gate tiles
+    int *t_hi = t_lo + nU;
+    int *t_tiles = t_hi + nU;
 
     for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
         reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
+    if (kFilter)
+        for (int u = tid; u < nU; u += kT) {
+            t_lo[u] = 0;
+            t_hi[u] = a.rec[u].ncand;
+            t_tiles[u] = a.rec[u].tiles;
+        }
 
     const unsigned lt_mask = (1u << lane) - 1u;
     const double depth_min = a.depth_min;
@@ -95,6 +105,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             if (kFilter) {
                 fs->U = (unsigned long long)__double_as_longlong((double)N);  // core.py:46: a model must beat N to count
                 fs->fq_fill = 0;
+                *ss = SweepShared{};
             }
         }
         __syncthreads();
@@ -120,6 +131,8 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w, reinterpret_cast<int *>(red_d), sid_sorted);
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
+        if (kFilter && kT > 256)  // the survivor ring shares its memory with the sort: a slot is valid when it is non-zero
+            for (int k = tid; k < a.qcap; k += kT) reinterpret_cast<unsigned long long *>(queue)[k] = 0ull;
         double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems), !kFilter, kFilter>(
             cs + 1, w, wd, a.w0, N, NM, NMP, red_d, 0, 0.0, wd32);
 #pragma unroll
@@ -143,101 +156,103 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         best.u = -1;  // "no model yet": loses every tie, so a candidate must be strictly below N
         best.i = -1;
 
-        const int tile_end = rec[ulo].cum + rec[ulo].tiles;
-        int g_next = rec[uhi - 1].cum + wid;
-        int cur_u = uhi - 1;
-        int u_begin = rec[cur_u].cum, u_end = u_begin + rec[cur_u].tiles;  // tile range of width cur_u
-        int round = 0;
-        for (;;) {
-            // B1
-            while (g_next < tile_end) {
-                int fill = 0;
-                if (lane == 0) fill = *(volatile int *)&s_next[2];
-                if (__shfl_sync(kFull, fill, 0) >= qstop) break;
-                const int g = g_next;
-                g_next += kW;
-                while (g >= u_end) {
-                    --cur_u;
-                    u_begin = u_end;
-                    u_end = u_begin + rec[cur_u].tiles;
-                }
-                const int u = cur_u;
-                const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
-                const double invW = rec[u].invW;
-                const int c_tile = (g - u_begin) * kTile + lane * kBlock;
-                int masks[kSub];
-                unsigned votes[kSub];
-                int total = 0;
-                if (X == 1) {
-#pragma unroll
-                    for (int sb = 0; sb < kSub; ++sb)
-                        masks[sb] = gate_block<kBlock, true>(cs, c_tile + sb * 32 * kBlock, ncand, W, 1, invW, depth_min);
-                } else {
-#pragma unroll
-                    for (int sb = 0; sb < kSub; ++sb)
-                        masks[sb] = gate_block<kBlock, false>(cs, c_tile + sb * 32 * kBlock, ncand, W, X, invW, depth_min);
-                }
-#pragma unroll
-                for (int sb = 0; sb < kSub; ++sb) {
-                    votes[sb] = __ballot_sync(kFull, masks[sb] != 0);
-                    total += __popc(votes[sb]);
-                }
-                if (total) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_next[2], total);
-                    base = __shfl_sync(kFull, base, 0);
-#pragma unroll
-                    for (int sb = 0; sb < kSub; ++sb) {
-                        if (masks[sb])
-                            queue[base + __popc(votes[sb] & lt_mask)] =
-                                make_int2(c_tile + sb * 32 * kBlock, u | (masks[sb] << 16));
-                        base += __popc(votes[sb]);
-                    }
-                }
-            }
-            if (lane == 0 && g_next < tile_end) s_next[1] = 1;  // this warp has tiles left
-            __syncthreads();
-            const int qfill = s_next[2];
-            const bool more = s_next[1] != 0;
-            // B2
-            if constexpr (kFilter) {
-                // fp32 correlation + rigorous bounds for every survivor; the few candidates that can still be the minimum
-                // go to the finalist queue and are evaluated in fp64 by all lanes afterwards
-                ExactView<true> view;
-                view.cs = cs; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
-                view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
-                filter_round<kT, kBlock, true>(queue, qfill, &s_next[3], round == 0, rec, cs, wd32, a.tq32, a.w0, T, eb_scale, fs,
-                                               fq, fq_lo, a.fq_cap, view, best, a.stats);
-                ++round;
-                if (!more) break;
-                __syncthreads();  // everyone has left the queues before they are reused
-                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; fs->fq_fill = 0; }
-                __syncthreads();
-            } else {
+        constexpr bool kDynamic = kFilter && kT > 256;  // one big CTA per SM: nothing else would fill a barrier wait
+        ExactView<true> view;
+        if (kFilter) {
+            view.cs = cs; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
+            view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
+        }
+        if constexpr (kDynamic) {
+            // B1 + B2 as one barrier-free sweep: warps switch between gating tiles and taking batches of survivors
+            // (fp32 correlation, screen, bounds); finalists are evaluated in fp64 by whole warps at the end
+            const int tile_total = rec[ulo].cum + rec[ulo].tiles - rec[uhi - 1].cum;
+            sweep_filter<kT, kBlock, true>(ss, queue, a.qcap - 1, tile_total, uhi, t_lo, t_hi, t_tiles, rec, cs, wd32, a.tq32, a.w0, T,
+                                           depth_min, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
+        } else {
+            const int tile_end = rec[ulo].cum + rec[ulo].tiles;
+            int g_next = rec[uhi - 1].cum + wid;
+            int cur_u = uhi - 1;
+            int u_begin = rec[cur_u].cum, u_end = u_begin + rec[cur_u].tiles;  // tile range of width cur_u
             for (;;) {
-                int h = 0;
-                if (lane == 0) h = atomicAdd(&s_next[3], 32);
-                h = __shfl_sync(kFull, h, 0);
-                if (h >= qfill) break;
-                if (h + lane < qfill) {
-                    const int2 e = queue[h + lane];
-                    const int u = e.y & 0xffff, mask = e.y >> 16;
-                    const WidthRec wr = rec[u];
-                    const int i0 = e.x * wr.X;
-                    double A[kBlock], B[kBlock];
-                    if (wr.X == 1) {
-                        tap_block<kBlock, true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
-                        block_min<kBlock, true, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
+                // B1
+                while (g_next < tile_end) {
+                    int fill = 0;
+                    if (lane == 0) fill = *(volatile int *)&s_next[2];
+                    if (__shfl_sync(kFull, fill, 0) >= qstop) break;
+                    const int g = g_next;
+                    g_next += kW;
+                    while (g >= u_end) {
+                        --cur_u;
+                        u_begin = u_end;
+                        u_end = u_begin + rec[cur_u].tiles;
+                    }
+                    const int u = cur_u;
+                    const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
+                    const double invW = rec[u].invW;
+                    const int c_tile = (g - u_begin) * kTile + lane * kBlock;
+                    int masks[kSub];
+                    unsigned votes[kSub];
+                    int total = 0;
+                    if (X == 1) {
+    #pragma unroll
+                        for (int sb = 0; sb < kSub; ++sb)
+                            masks[sb] = gate_block<kBlock, true>(cs, c_tile + sb * 32 * kBlock, ncand, W, 1, invW, depth_min);
                     } else {
-                        tap_block<kBlock, false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
-                        block_min<kBlock, false, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
+    #pragma unroll
+                        for (int sb = 0; sb < kSub; ++sb)
+                            masks[sb] = gate_block<kBlock, false>(cs, c_tile + sb * 32 * kBlock, ncand, W, X, invW, depth_min);
+                    }
+    #pragma unroll
+                    for (int sb = 0; sb < kSub; ++sb) {
+                        votes[sb] = __ballot_sync(kFull, masks[sb] != 0);
+                        total += __popc(votes[sb]);
+                    }
+                    if (total) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_next[2], total);
+                        base = __shfl_sync(kFull, base, 0);
+    #pragma unroll
+                        for (int sb = 0; sb < kSub; ++sb) {
+                            if (masks[sb])
+                                queue[base + __popc(votes[sb] & lt_mask)] =
+                                    make_int2(c_tile + sb * 32 * kBlock, u | (masks[sb] << 16));
+                            base += __popc(votes[sb]);
+                        }
                     }
                 }
-            }
-            if (!more) break;
-            __syncthreads();  // everyone has left B2 before the queue is reused
-            if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
-            __syncthreads();
+                if (lane == 0 && g_next < tile_end) s_next[1] = 1;  // this warp has tiles left
+                __syncthreads();
+                const int qfill = s_next[2];
+                const bool more = s_next[1] != 0;
+                // B2
+                if constexpr (kFilter) {
+                    filter_round<kT, kBlock, true>(queue, qfill, &s_next[3], rec, cs, wd32, a.tq32, a.w0, T, eb_scale, fs, fq, fq_lo,
+                                                   a.fq_cap, view, best, a.stats);
+                } else
+                for (;;) {
+                    int h = 0;
+                    if (lane == 0) h = atomicAdd(&s_next[3], 32);
+                    h = __shfl_sync(kFull, h, 0);
+                    if (h >= qfill) break;
+                    if (h + lane < qfill) {
+                        const int2 e = queue[h + lane];
+                        const int u = e.y & 0xffff, mask = e.y >> 16;
+                        const WidthRec wr = rec[u];
+                        const int i0 = e.x * wr.X;
+                        double A[kBlock], B[kBlock];
+                        if (wr.X == 1) {
+                            tap_block<kBlock, true, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
+                            block_min<kBlock, true, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
+                        } else {
+                            tap_block<kBlock, false, kUniformW>(wr, a.tq, w, wd, e.x, A, B);
+                            block_min<kBlock, false, kUniformW>(wr, cs, w, wd, a.w0, T, i0, mask, u, A, B, best);
+                        }
+                    }
+                }
+                if (!more) break;
+                __syncthreads();  // everyone has left B2 before the queue is reused
+                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; if (kFilter) fs->fq_fill = 0; }
+                __syncthreads();
             }
         }
 

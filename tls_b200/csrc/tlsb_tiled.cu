@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     WidthRec *rec = kUniformW ? reinterpret_cast<WidthRec *>(wd32_s + C) : reinterpret_cast<WidthRec *>(wd_s + C);  // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
     FilterShared *fs = reinterpret_cast<FilterShared *>(red_d + 2 * kW + 2);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(fs + 1);
+    SweepShared *ss = reinterpret_cast<SweepShared *>(fs + 1);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(ss + 1);
     int *red_i = reinterpret_cast<int *>(bar + 1);                            // [2*kW]
     int *s_next = red_i + 2 * kW;  // [8] period slot, "tiles left" flag, queue fill, queue head, chunk tiles
     int *ch_lo = s_next + 8;       // [nU] first candidate of the chunk, per width
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
 
     for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
         reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
+    if (kUniformW)  // the survivor ring: a slot is valid when it is non-zero, readers clear it
+        for (int k = tid; k < a.qcap; k += kT) reinterpret_cast<unsigned long long *>(queue)[k] = 0ull;
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -340,9 +343,13 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         // gate + taps over the tables' tiles, widths ub-1 downwards; csb / wb / wdb are indexable by global offsets
         ExactView<false> view;
         view.cs = cs; view.wd = wd; view.dval = nullptr; view.sid = nullptr; view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
-        int round = 0;  // rounds of the survivor queue in this period (the first one settles the filter's threshold)
         auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *wd32b, int ub) {
             const int tile_end = s_next[4];
+            if constexpr (kUniformW) {  // barrier-free gate + filter sweep (tlsb_device.cuh)
+                sweep_filter<kT, kBlock, false>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, csb, wd32b, a.tq32,
+                                                a.w0, T, depth_min, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
+                return;
+            }
             int g_next = wid;
             int cur_u = ub - 1;
             int u_begin = 0, u_end = ch_tiles[cur_u];
@@ -398,11 +405,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 const int qfill = s_next[2];
                 const bool more = s_next[1] != 0;
                 // B2: taps
-                if constexpr (kUniformW) {
-                    filter_round<kT, kBlock, false>(queue, qfill, &s_next[3], round == 0, rec, csb, wd32b, a.tq32, a.w0, T, eb_scale,
-                                                    fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
-                    ++round;
-                } else {
+                {
                     for (;;) {
                         int h = 0;
                         if (lane == 0) h = atomicAdd(&s_next[3], 32);
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 }
                 if (!more) break;
                 __syncthreads();
-                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; if (kUniformW) fs->fq_fill = 0; }
+                if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; }
                 __syncthreads();
             }
         };
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                         bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
                         bulk_copy_g2s(wd32_s, wd32 + a0, 4u * (unsigned)len_32, bar);
                         fs->fq_fill = 0;
+                        *ss = SweepShared{};
                     } else {
                         const int len_wd = min(C, (int)nmp_even - a0);
                         mbar_expect_tx(bar, 8u * (unsigned)(len_cs + 2 * len_wd));
@@ -465,7 +469,10 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         }
         if (uT < uhi) {  // the widest widths: gate and taps read the scratch through L1/L2
             __syncthreads();  // the last chunk's sweep is done with the queue and the tables
-            if (tid == 0) { s_next[1] = 0; s_next[2] = 0; s_next[3] = 0; if (kUniformW) fs->fq_fill = 0; }
+            if (tid == 0) {
+                s_next[1] = 0; s_next[2] = 0; s_next[3] = 0;
+                if (kUniformW) { fs->fq_fill = 0; *ss = SweepShared{}; }
+            }
             build_tables(0, 1 << 30, max(ulo, uT), uhi);
             __syncthreads();
             sweep(cs, w, wd, wd32, uhi);
