@@ -18,8 +18,10 @@ trial period of the grid) over one synthetic light curve:
   job's grid is the reference's period grid oversampled N x (``oversampling_factor = 3 N``),
   dealt to the ranks round-robin (period k -> rank k mod N), one all-gather at the end of
   each step.  value = all ranks' periods / max-over-ranks time.
-* ``--impl reference`` — the CPU implementation of the same path (the C restatement of the
-  reference under ``oracle/``, all host threads) on a bounded sample of the same workload.
+* ``--impl reference`` — the reference's own CPU implementation of the same path: the unmodified numba
+  ``core.search_period`` behind a warmed ``multiprocessing.Pool`` over all host cores (``oracle/_ref``, vendored
+  by ``oracle/vendor_ref.py``), on a bounded sample of the same workload; the C restatement under ``oracle/``
+  is reported beside it as ``cpu_baseline.port``.
 
 One JSON line on stdout (rank 0).
 """
@@ -227,6 +229,31 @@ def cpu_sample(inp, periods, seconds, threads=0):
     return n / dt, n, cores
 
 
+def numba_reference(workload, oversampling, seconds, steps=1, max_periods=0, serial_seconds=3.0):
+    """The reference's own numba ``core.search_period`` on this box's host cores (``oracle/time_reference.py``, its own
+    process: a warmed fork Pool must not inherit a CUDA context or torchrun's OMP_NUM_THREADS).  Returns the
+    script's JSON object, or {"unavailable": why}."""
+    import subprocess
+
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+        env.pop(k, None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.join(REPO, "oracle", "time_reference.py"), "--workload", workload,
+           "--oversampling", str(oversampling), "--seconds", "%.3f" % seconds, "--steps", str(steps),
+           "--serial-seconds", "%.3f" % serial_seconds]
+    if max_periods:
+        cmd += ["--max-periods", str(max_periods)]
+    try:
+        proc = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+        lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+        if proc.returncode != 0 or not lines:
+            return {"unavailable": "oracle/time_reference.py failed: " + (proc.stderr or proc.stdout)[-300:]}
+        return json.loads(lines[-1])
+    except Exception as exc:
+        return {"unavailable": str(exc)[:300]}
+
+
 def workload_config(args, inp, n_gpus, P_rank, P_total, oversampling):
     return {
         "workload": "%s: %s" % (args.workload, WORKLOAD_NOTES.get(args.workload, "")),
@@ -251,6 +278,11 @@ WORKLOAD_NOTES = {
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores: the unmodified numba
+    ``core.search_period`` behind a warmed ``multiprocessing.Pool(os.cpu_count()).imap_unordered`` (main.py:141-163),
+    imported from the copy ``oracle/vendor_ref.py`` ships under ``oracle/_ref``; each step is a bounded, evenly spread
+    sample of the same period grid.  The C restatement under ``oracle/`` (OpenMP) is timed beside it as
+    ``cpu_baseline.port``; it becomes the line's value only if the reference package is not there."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -259,28 +291,38 @@ def run_reference(args):
     periods = inp.periods
     if args.max_periods and args.max_periods * args.gpus < len(periods):
         periods = periods[np.linspace(0, len(periods) - 1, args.max_periods * args.gpus).astype(int)]
-    from oracle import oracle
-
     cores = os.cpu_count() or 1
-    # size one step for a few seconds of CPU work
-    rate, n0, _ = cpu_sample(inp, periods, 2.0)
-    per_step = int(min(len(periods), max(cores * 8, rate * 3.0)))
-    sample = periods[np.linspace(0, len(periods) - 1, per_step).astype(int)]
-    for _ in range(max(1, min(args.warmup, 3))):
-        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample[: max(cores * 4, per_step // 8)], inp.templates, inp.params, threads=cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.search_periods_c(inp.t, inp.y, inp.dy, sample, inp.templates, inp.params, threads=cores)
-    dt = time.perf_counter() - t0
-    value = per_step * args.steps / dt
-    what = "%d of %d periods per step (evenly spread), C restatement of core.search_period, OpenMP" % (per_step, len(periods))
+    steps = max(1, args.steps)
+    per_step_s = float(min(8.0, max(1.5, 120.0 / steps)))  # the whole run stays within a few minutes
+    port_rate, port_n, _ = cpu_sample(inp, periods, min(6.0, args.cpu_seconds))
+    port = {"value": port_rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d periods (evenly spread), C restatement of core.search_period under oracle/, OpenMP" % (port_n, len(periods))}
+    ref = numba_reference(args.workload, oversampling, per_step_s, steps=steps,
+                          max_periods=len(periods) if len(periods) < len(inp.periods) else 0)
+    if "pool" in ref:
+        value, ms = float(ref["pool"]["value"]), float(ref["pool"]["ms_per_step"])
+        what = "%d of %d periods per step (evenly spread), %s; %s" % (
+            ref["pool"]["periods_per_step"], len(periods), ref["impl"], ref["pool"]["how"])
+        cpu = {"value": value, "unit": UNIT, "cores": int(ref["pool"]["cores"]), "kind": "reference", "sample": what,
+               "serial": ref["serial"], "imported_from": ref.get("imported_from"), "port": port}
+    else:  # no reference package on this machine: the port stands in, and says so
+        from oracle import oracle
+
+        per_step = int(min(len(periods), max(cores * 8, port_rate * 3.0)))
+        sample = periods[np.linspace(0, len(periods) - 1, per_step).astype(int)]
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            oracle.search_periods_c(inp.t, inp.y, inp.dy, sample, inp.templates, inp.params, threads=cores)
+        dt = time.perf_counter() - t0
+        value, ms = per_step * steps / dt, 1e3 * dt / steps
+        cpu = dict(port, value=value, reference_unavailable=ref.get("unavailable"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(args, inp, args.gpus, len(periods) // args.gpus, len(periods), oversampling),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": what},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -453,14 +495,26 @@ def run_b200(args):
                 pass
         if not args.no_cpu_baseline:
             rate, n, cores = cpu_sample(inp, job.local_periods, args.cpu_seconds)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d of %d periods (evenly spread) of the same workload, C restatement of "
-                             "core.search_period under oracle/, OpenMP over periods" % (n, P_rank)}
+            port = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "%d of %d periods (evenly spread) of the same workload, C restatement of "
+                              "core.search_period under oracle/, OpenMP over periods" % (n, P_rank)}
             try:  # the 1-core figure beside the all-cores one (about 3 s more)
                 rate1, n1, _ = cpu_sample(inp, job.local_periods, min(3.0, args.cpu_seconds), threads=1)
-                cpu["serial"] = {"value": rate1, "unit": UNIT, "cores": 1, "sample": "%d periods" % n1}
+                port["serial"] = {"value": rate1, "unit": UNIT, "cores": 1, "sample": "%d periods" % n1}
             except Exception as exc:
-                cpu["serial"] = {"error": str(exc)[:200]}
+                port["serial"] = {"error": str(exc)[:200]}
+            cpu = port
+            if n_gpus == 1:  # the reference's own numba path, timed on this box's host cores in the same run
+                ref = numba_reference(args.workload, oversampling, args.cpu_seconds, max_periods=args.max_periods,
+                                      serial_seconds=min(3.0, args.cpu_seconds))
+                if "pool" in ref:
+                    cpu = {"value": float(ref["pool"]["value"]), "unit": UNIT, "cores": int(ref["pool"]["cores"]),
+                           "kind": "reference",
+                           "sample": "%d of %d periods (evenly spread), %s; %s" % (
+                               ref["pool"]["periods_per_step"], ref["periods_in_grid"], ref["impl"], ref["pool"]["how"]),
+                           "serial": ref["serial"], "imported_from": ref.get("imported_from"), "port": port}
+                else:
+                    cpu = dict(port, reference_unavailable=ref.get("unavailable"))
 
     secondary = None
     if rank == 0 and n_gpus == 1 and not args.no_secondary and not args.max_periods:

@@ -14,7 +14,7 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ref_shim  # noqa: E402
 
-pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="needs /root/reference (build container only)")
+pytestmark = pytest.mark.skipif(not ref_shim.source_tree_available(), reason="needs /root/reference (build container only)")
 
 
 @pytest.fixture(scope="module")
