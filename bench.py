@@ -413,21 +413,40 @@ def run_b200(args):
             "chi2_max_rel_err": float(np.max(np.abs(chi2[sel][fin] - w[0][fin]) / np.abs(w[0][fin]))) if fin.any() else 0.0,
         }
 
+    # N > 1: what every rank ends up with after the all-gather and the device-side un-interleave, checked on rank 0
+    # against the CPU oracle on periods spread over ALL shards (collective: every rank calls results())
+    if dist is not None:
+        g_chi2, g_row, g_depth, _g_t0 = job.results()
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import oracle
+
+            sel = np.unique(np.linspace(0, P_total - 1, min(P_total, 16 * world + 64)).astype(int))
+            w = oracle.search_periods_c(inp.t, inp.y, inp.dy, all_periods[sel], inp.templates, inp.params)
+            fin = np.isfinite(w[0])
+            shards = sorted(set(int(k) % world for k in sel))
+            parity["gathered"] = {
+                "periods_checked": int(len(sel)), "shards_covered": len(shards), "world": world,
+                "rows_equal": bool(np.array_equal(g_row[sel], w[1])),
+                "chi2_max_rel_err": float(np.max(np.abs(g_chi2[sel][fin] - w[0][fin]) / np.abs(w[0][fin]))) if fin.any() else 0.0,
+                "depth_max_rel_err": float(np.max(np.abs(g_depth[sel] - w[2]) / np.maximum(np.abs(w[2]), 1e-300))),
+                "local_shard_identical": bool(np.array_equal(g_chi2[rank::world], chi2) and np.array_equal(g_row[rank::world], row)),
+            }
+
     # ---- e2e: the C-ABI one-shot call with pinned host buffers ------------------------------
     pin = {}
     for name, arr in (("t", inp.t), ("y", inp.y), ("dy", inp.dy), ("periods", job.local_periods)):
         tt = torch.from_numpy(np.ascontiguousarray(arr, np.float64).copy()).pin_memory()
         pin[name] = (tt, tt.numpy())
     h2d = 8 * (3 * len(inp.y) + P_rank) + sum(int(np.asarray(v).nbytes) for v in inp.templates.values())
-    d2h = 24 * P_rank if dist is None else 8 * world * (3 * job.capacity + 1)
+    d2h = 24 * P_rank if dist is None else 8 * (3 * P_total + 1)
 
     def e2e_step():
         if dist is None:
             return native.search_periods(pin["t"][1], pin["y"][1], pin["dy"][1], pin["periods"][1], inp.templates,
                                          inp.params, devices=[local])
-        # N > 1: the same host buffers go up through the handle API (tlsb_set_lightcurve / _templates /
-        # _periods), the records are all-gathered on the device and come back in ONE copy
-        job.reload(pin["t"][1], pin["y"][1], pin["dy"][1], inp.templates, inp.params)
+        # N > 1: the same host buffers go up through the handle API in one asynchronous call (tlsb_set_inputs_async),
+        # the records are all-gathered and un-interleaved on the device and come back in ONE copy of 24 B per period
+        job.reload(pin["t"][1], pin["y"][1], pin["dy"][1], inp.templates, inp.params, stream=stream)
         job.step(stream)
         return job.results()
 
@@ -529,7 +548,8 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "call": "tlsb_search_periods (C ABI, host buffers)" if dist is None else
-                            "ShardedSearch.reload/step/results: C ABI setters with host buffers, device all-gather, one copy back"},
+                            "ShardedSearch.reload/step/results: tlsb_set_inputs_async with host buffers, device all-gather + "
+                            "tlsb_unshard_records, one copy back"},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "parity": parity,
         }

@@ -101,6 +101,18 @@ int tlsb_destroy(tlsb_handle *h);
 int tlsb_set_lightcurve(tlsb_handle *h, const tlsb_lightcurve *lc);
 int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_params *prm);
 int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods);
+/* The three setters in one call, every upload asynchronous on `cuda_stream` (the stream the following
+ * tlsb_search_async will use) and no synchronisation: the caller's buffers must stay valid and unchanged until that
+ * stream has passed the uploads (e.g. until the results of the search have been read).  Any of lc, tp (with prm),
+ * periods may be NULL to keep what the handle has.  This is the per-step upload of the multi-GPU end-to-end path
+ * (one process per GPU re-sends light curve, bank and its period shard: main.py:140-163 pickles the same per task). */
+int tlsb_set_inputs_async(tlsb_handle *h, void *cuda_stream, const tlsb_lightcurve *lc, const tlsb_templates *tp,
+                          const tlsb_params *prm, const double *periods, int64_t n_periods);
+/* Multi-GPU: undo the interleaved period partition ON THE DEVICE.  gathered_dev is the all-gathered record buffer,
+ * rank-major: world shards of 3 * ceil(n/world) + 1 words, shard r holding periods r, r + world, ... in the layout of
+ * tlsb_search_async.  out_dev receives 3 * n_periods + 1 words: chi2 | depth | packed in the job's period order
+ * (main.py:190-196) and the SUM of the shards' status words.  Asynchronous on `cuda_stream`; needs no handle. */
+int tlsb_unshard_records(const void *gathered_dev, int64_t n_periods, int32_t world, void *out_dev, void *cuda_stream);
 /* Launch the plan + search kernels on `cuda_stream` (a cudaStream_t, NULL = default
  * stream); asynchronous.  Results go to the handle's device buffer, or, when `records_dev`
  * is not NULL, to that device buffer of 3*n_periods + 1 8-byte words: three planes
@@ -125,7 +137,8 @@ int tlsb_resolve_plan(tlsb_handle *h, void *cuda_stream, void *records_dev);
  * than the plan kernel lists), and how many single periods were re-searched by the repair path. */
 int64_t tlsb_plan_fallback_count(const tlsb_handle *h);
 int64_t tlsb_plan_repair_count(const tlsb_handle *h);
-/* Wait for the stream and copy the handle's own result buffer to the host. */
+/* Wait for the stream and copy the handle's own result buffer to the host.  TLSB_ERR_STATE if the most recent
+ * tlsb_search_async was given its own records_dev (the handle's buffer would hold an older search). */
 int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_t *row_out,
                      double *depth_out, int64_t *t0_index_out);
 /* Number of kernels this library launched for the most recent tlsb_search_async. */

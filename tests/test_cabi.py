@@ -62,11 +62,9 @@ def test_null_arguments_are_rejected_without_touching_cuda():
     assert L.tlsb_last_launch_count(None) == 0
 
 
-def test_integration_md_stub_runs_as_written(has_cuda):
+def _integration_md_stub():
     """The ctypes stub INTEGRATION.md §1 shows a TLS maintainer, executed verbatim (only the library path is
-    made absolute): it must marshal the reference's own arguments (ragged lc_arr, structured overview) and, on a
-    machine without a GPU, surface the library's refusal as a RuntimeError; with a GPU it must return what
-    tls_b200.native returns."""
+    made absolute), and the reference's own arguments for it (ragged lc_arr, structured overview)."""
     text = open(os.path.join(REPO, "INTEGRATION.md")).read()
     block = re.search(r"```python\n(import ctypes, numpy\n.*?)```", text, flags=re.S).group(1)
     block = block.replace('ctypes.CDLL("libtlsb200.so")', "ctypes.CDLL(%r)" % native.library_path())
@@ -79,13 +77,29 @@ def test_integration_md_stub_runs_as_written(has_cuda):
         lc_arr[r] = np.array(tp["signal"][tp["offset"][r]: tp["offset"][r] + tp["length"][r]])
     overview = np.zeros(len(lc_arr), dtype=[("duration", "f8"), ("width_in_samples", "i8"), ("overshoot", "f8")])
     overview["width_in_samples"], overview["overshoot"] = tp["width"], tp["overshoot"]
-    call = lambda: ns["search_periods"](g["periods"], g["t"], g["y"], g["dy"], lc_arr, overview, **g["params"])
-    if not has_cuda:
-        with pytest.raises(RuntimeError, match="CUDA"):
-            call()
-        return
+    return g, (lambda: ns["search_periods"](g["periods"], g["t"], g["y"], g["dy"], lc_arr, overview, **g["params"]))
+
+
+def test_integration_md_stub_refuses_without_a_gpu(has_cuda):
+    """On a machine without a GPU the stub must marshal its arguments and surface the library's refusal as a
+    RuntimeError (there is no CPU fallback)."""
+    if has_cuda:
+        pytest.skip("a CUDA device is present: test_integration_md_stub_runs_as_written covers this machine")
+    _, call = _integration_md_stub()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        call()
+
+
+@pytest.mark.gpu
+def test_integration_md_stub_runs_as_written():
+    """With a GPU the stub, exactly as INTEGRATION.md prints it, returns what tls_b200.native returns and what the
+    reference's numba path returned for the same arguments (the golden)."""
+    g, call = _integration_md_stub()
     chi2, row, depth = call()
     want = native.search_periods(g["t"], g["y"], g["dy"], g["periods"], g["templates"], g["params"])
     np.testing.assert_array_equal(chi2, want[0])
     np.testing.assert_array_equal(row, want[1])
     np.testing.assert_array_equal(depth, want[2])
+    from conftest import assert_search_parity
+
+    assert_search_parity((chi2, row, depth), g, rtol=1e-5, label="INTEGRATION.md stub")

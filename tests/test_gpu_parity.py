@@ -287,3 +287,70 @@ def test_clustered_phases_fall_back_to_the_global_sort():
     np.testing.assert_array_equal(tiled[1], auto[1])
     np.testing.assert_array_equal(tiled[3], auto[3])
     np.testing.assert_allclose(tiled[0], auto[0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,world", [(9679, 2), (9679, 8), (77, 3), (5, 8), (64, 4)])
+def test_device_unshard_equals_the_host_unpack(n, world):
+    """tlsb_unshard_records (main.py:190-196 on the device): a rank-major all-gathered buffer of interleaved shards,
+    built here on one GPU exactly as ranks would write it, comes out in the job's period order; the host-side
+    unpack of the gloo tests (tls_b200.distributed.unpack_gathered) is the checker.  Bit for bit."""
+    import torch
+
+    native = _native()
+    from tls_b200 import distributed as D
+
+    rng = np.random.default_rng(n * 31 + world)
+    chi2 = rng.normal(4000, 10, n)
+    depth = rng.uniform(0.99, 1.0, n)
+    row = rng.integers(0, 60, n)
+    t0 = rng.integers(-1, 5000, n)
+    cap = D.shard_capacity(n, world)
+    shards = []
+    for r in range(world):
+        idx = D.shard_indices(n, r, world)
+        rec = D.pack_records(chi2[idx], row[idx], depth[idx], t0[idx], cap)
+        rec[3 * len(idx)] = r + 1  # status words: the sum must come through
+        shards.append(rec)
+    gathered = np.concatenate(shards)
+    want = D.unpack_gathered(gathered, n, world)
+    g_dev = torch.from_numpy(gathered).cuda()
+    out = torch.empty(3 * n + 1, dtype=torch.int64, device="cuda")
+    native.unshard_records(g_dev.data_ptr(), n, world, out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    host = out.cpu().numpy()
+    got = native.unpack_records(host, n)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    assert host[3 * n] == world * (world + 1) // 2
+    np.testing.assert_array_equal(got[0], chi2)
+    np.testing.assert_array_equal(got[3], t0)
+
+
+def test_one_call_async_upload_equals_the_three_setters_and_get_results_guards_its_buffer():
+    import torch
+
+    native = _native()
+    g = load_search_golden("small")
+    s = native.Searcher()
+    s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
+    s.set_periods(g["periods"])
+    s.search_async()
+    want = s.results()
+    s2 = native.Searcher()
+    stream = torch.cuda.current_stream()
+    for _ in range(3):  # repeated reloads: the staged template copy must not be rewritten under an upload in flight
+        s2.set_inputs_async(g["t"], g["y"], g["dy"], g["templates"], g["params"], g["periods"], stream=stream.cuda_stream)
+        s2.search_async(stream=stream.cuda_stream)
+        got = s2.results(stream=stream.cuda_stream)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    # a search into a caller-supplied buffer must not let tlsb_get_results hand back the OLDER search in the handle's buffer
+    mine = torch.zeros(3 * len(g["periods"]) + 1, dtype=torch.int64, device="cuda")
+    s2.search_async(stream=stream.cuda_stream, records_ptr=mine.data_ptr())
+    with pytest.raises(RuntimeError, match="records_dev|own buffer"):
+        s2.results(stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    got = native.unpack_records(mine.cpu().numpy(), len(g["periods"]))
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
+    s.close()
+    s2.close()

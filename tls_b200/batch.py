@@ -42,6 +42,8 @@ def _validate_batch(t, ys, dys):
         raise ValueError("t must be [n] (shared) or [curves, n]")
     if not (np.all(np.isfinite(ys)) and np.all(np.isfinite(t))):
         raise ValueError("batch inputs must be finite; run cleaned_array per curve first")
+    if np.any(ys <= 0):  # validate_inputs drops such samples (helpers.cleaned_array): the curves would lose their common length
+        raise ValueError("batch fluxes must be positive; run cleaned_array per curve first")
     if dys is None:  # validate.py:39-40: dy = std(y) everywhere, per curve
         dys = np.repeat(np.std(ys, axis=1)[:, None], ys.shape[1], axis=1)
         given = False
@@ -66,13 +68,20 @@ def shard_curves(n_curves, rank, world):
     return np.arange(rank, n_curves, world)
 
 
+def argmin_in_ascending_period_order(chi2_by_input, periods):
+    """Index (in INPUT order) of the chi2 minimum the reference picks: it sorts by ascending period first
+    (main.py:190-199), so among tied minima the SHORTEST period wins, not the first in input order."""
+    asc = np.argsort(periods, kind="stable")
+    return int(asc[int(np.argmin(np.asarray(chi2_by_input)[asc]))])
+
+
 def summarize_curve(model, t, y, chi2_by_input, rows_by_input, depths_by_input, SDE, SDE_raw, best_index,
                     inputs, T0):
     """The scalar part of main.py:198-455 for one curve (host, O(1) + one pass over t)."""
     periods = inputs.periods
     period = periods[best_index]
     depth = depths_by_input[best_index]
-    k_min = int(np.argmin(chi2_by_input))
+    k_min = argmin_in_ascending_period_order(chi2_by_input, periods)
     best_row = int(rows_by_input[k_min])
     duration = inputs.overview["duration"][best_row]
     transit_times = stats.all_transit_times(T0, t, period)
@@ -96,6 +105,8 @@ def batch_power(t, ys, dys=None, device=None, dist=None, return_power=False, **k
     mine = shard_curves(B, rank, world)
     t0_axis = t if t.ndim == 1 else t[0]
     model = transitleastsquares(t0_axis, ys[0], dys[0], verbose=False)
+    if len(model.t) != n:
+        raise ValueError("input validation removed samples from the first curve; clean the batch first")
     kwargs.setdefault("show_progress_bar", False)
     inputs = model.prepare(**kwargs)  # grids and bank depend on (span, n) only: shared by the batch
     no_detection = dict(SDE=0.0, SDE_raw=0.0, period=np.nan, T0=0.0, depth=1.0, duration=np.nan, rp_rs=np.nan,
@@ -117,7 +128,7 @@ def batch_power(t, ys, dys=None, device=None, dist=None, return_power=False, **k
                                best_row=int(out["row"][k][0]))
                 else:
                     best = int(out["best_index"][k])
-                    k_min = int(np.argmin(chi2))
+                    k_min = argmin_in_ascending_period_order(chi2, inputs.periods)
                     signal = inputs.lc_arr[int(out["row"][k][k_min])]
                     model_in, trials = stats.t0_fit_inputs(signal, out["depth"][k][best], tc, ys[c],
                                                            inputs.periods[best], model.T0_fit_margin)

@@ -196,9 +196,37 @@ __global__ void tlsb_gather_rows_kernel(const double *__restrict__ records, size
     if (k < P) out[c * P + k] = records[c * record_stride + order[k]];  // chi2 plane, ascending period
 }
 
+// Multi-GPU (main.py:190-196 wants one array per quantity in the job's period order): the all-gathered buffer is
+// rank-major, rank r holding periods r, r + world, ... as three planes of its own length n_r plus a status word.
+// One thread per period writes the final three planes; thread 0 adds up the shards' status words.
+__global__ void tlsb_unshard_kernel(const long long *__restrict__ g, int n, int world, int words_per_rank,
+                                    long long *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        const int r = k % world, j = k / world;
+        const int n_r = (n - r + world - 1) / world;
+        const long long *src = g + (size_t)r * words_per_rank;
+        out[k] = src[j];
+        out[(size_t)n + k] = src[n_r + j];
+        out[2 * (size_t)n + k] = src[2 * n_r + j];
+    }
+    if (k == 0) {
+        long long status = 0;
+        for (int r = 0; r < world; ++r) status += g[(size_t)r * words_per_rank + 3 * ((n - r + world - 1) / world)];
+        out[3 * (size_t)n] = status;
+    }
+}
+
 }  // namespace
 
 namespace tlsb {
+
+cudaError_t launch_unshard(const long long *gathered, int n, int world, int words_per_rank, long long *out, cudaStream_t s)
+{
+    tlsb_unshard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(gathered, n, world, words_per_rank, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_plan(const PlanArgs &a, int grid, cudaStream_t s)
 {

@@ -113,6 +113,8 @@ struct tlsb_handle {
     DevBuf asc_order, brec, bchi, bSR, bpr, bpw, bscal, bamax;  // batch pipeline
     std::vector<int> h_asc_order;
     bool asc_valid = false;        // asc_order matches the current periods (made on demand by the batch call)
+    cudaStream_t up_stream = nullptr;  // stream the setters upload on (tlsb_set_inputs_async: the search's stream)
+    bool out_is_current = false;   // the last search wrote the handle's own record buffer (tlsb_get_results reads it)
     bool defer_sync = false;       // one-shot call: the caller's buffers outlive the whole call, setters need not wait
     std::vector<double> h_tq;      // host copy of tq (keeps the upload source alive without a synchronisation)
     // templates
@@ -572,7 +574,7 @@ int resolve_records(tlsb_handle *h, cudaStream_t s, void *records_dev, long long
 extern "C" {
 
 const char *tlsb_last_error(void) { return g_error.c_str(); }
-const char *tlsb_version(void) { return "tlsb200 0.2 (sm_100a)"; }
+const char *tlsb_version(void) { return "tlsb200 0.3 (sm_100a)"; }
 
 int32_t tlsb_device_count(void)
 {
@@ -647,11 +649,11 @@ static int set_curves(tlsb_handle *h, const double *t, const double *y, const do
     const int n = (int)n64;
     const size_t total = (size_t)n * (size_t)n_curves, bytes = sizeof(double) * total;
     int rc;
-    if ((rc = upload(h->t, t, shared_t ? sizeof(double) * (size_t)n : bytes))) return rc;
-    if ((rc = upload(h->y, y, bytes))) return rc;
-    if ((rc = upload(h->dy, dy, bytes))) return rc;
+    if ((rc = upload(h->t, t, shared_t ? sizeof(double) * (size_t)n : bytes, h->up_stream))) return rc;
+    if ((rc = upload(h->y, y, bytes, h->up_stream))) return rc;
+    if ((rc = upload(h->dy, dy, bytes, h->up_stream))) return rc;
     if (h->dval.ensure(bytes) || h->wval.ensure(bytes)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
-    CUDA_TRY(launch_prepare(h->y.as<double>(), h->dy.as<double>(), h->dval.as<double>(), h->wval.as<double>(), total, nullptr));
+    CUDA_TRY(launch_prepare(h->y.as<double>(), h->dy.as<double>(), h->dval.as<double>(), h->wval.as<double>(), total, h->up_stream));
     h->c_span.assign((size_t)n_curves, 0.0);
     h->c_w0.assign((size_t)n_curves, 0.0);
     h->c_uniform.assign((size_t)n_curves, 0);
@@ -671,7 +673,7 @@ static int set_curves(tlsb_handle *h, const double *t, const double *y, const do
         h->c_uniform[c] = uniform ? 1 : 0;
         h->c_w0[c] = 1.0 / (dc[0] * dc[0]);
     }
-    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));
     h->n_curves = (int)n_curves;
     h->shared_t = shared_t;
     h->cur = 0;
@@ -778,11 +780,12 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
     int rc;
+    if (h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));  // an earlier asynchronous upload may still read h_tq
     h->h_tq.swap(tq);  // stays alive behind the asynchronous upload
     h->h_tq32.assign(h->h_tq.begin(), h->h_tq.end());
-    if ((rc = upload(h->tq, h->h_tq.data(), h->h_tq.size() * 8))) return rc;
-    if ((rc = upload(h->tq32, h->h_tq32.data(), h->h_tq32.size() * 4))) return rc;
-    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if ((rc = upload(h->tq, h->h_tq.data(), h->h_tq.size() * 8, h->up_stream))) return rc;
+    if ((rc = upload(h->tq32, h->h_tq32.data(), h->h_tq32.size() * 4, h->up_stream))) return rc;
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));
     h->recs.swap(recs);
     h->pad = kPadGroups * kBlockMax * xmax;
     h->nU = nU;
@@ -803,8 +806,8 @@ int tlsb_set_periods(tlsb_handle *h, const double *periods, int64_t n_periods)
     h->P = (int)n_periods;
     h->h_periods.assign(periods, periods + n_periods);
     int rc;
-    if ((rc = upload(h->periods, periods, sizeof(double) * (size_t)n_periods))) return rc;
-    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if ((rc = upload(h->periods, periods, sizeof(double) * (size_t)n_periods, h->up_stream))) return rc;
+    if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));
     h->asc_valid = false;
     h->have_periods = true;
     h->host_plan_valid = false;
@@ -824,6 +827,32 @@ int tlsb_set_path(tlsb_handle *h, int32_t path, int32_t chunk_doubles)
     if (!h || path < 0 || path > 3) return fail(TLSB_ERR_ARG, "tlsb_set_path: path must be 0..3");
     h->path_mode = path;
     h->chunk_cap = chunk_doubles;
+    return 0;
+}
+
+int tlsb_set_inputs_async(tlsb_handle *h, void *cuda_stream, const tlsb_lightcurve *lc, const tlsb_templates *tp,
+                          const tlsb_params *prm, const double *periods, int64_t n_periods)
+{
+    if (!h) return fail(TLSB_ERR_ARG, "tlsb_set_inputs_async: NULL handle");
+    h->up_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    h->defer_sync = true;
+    int rc = 0;
+    if (lc) rc = tlsb_set_lightcurve(h, lc);
+    if (!rc && tp) rc = prm ? tlsb_set_templates(h, tp, prm) : fail(TLSB_ERR_ARG, "tlsb_set_inputs_async: templates without params");
+    if (!rc && periods) rc = tlsb_set_periods(h, periods, n_periods);
+    h->defer_sync = false;
+    h->up_stream = nullptr;
+    return rc;
+}
+
+int tlsb_unshard_records(const void *gathered_dev, int64_t n_periods, int32_t world, void *out_dev, void *cuda_stream)
+{
+    if (!gathered_dev || !out_dev) return fail(TLSB_ERR_ARG, "tlsb_unshard_records: NULL argument");
+    if (n_periods < 1 || n_periods > (int64_t)1 << 30 || world < 1 || world > 65536)
+        return fail(TLSB_ERR_ARG, "tlsb_unshard_records: bad period count or world size");
+    const int64_t cap = (n_periods + world - 1) / world;
+    CUDA_TRY(launch_unshard(reinterpret_cast<const long long *>(gathered_dev), (int)n_periods, (int)world, (int)(3 * cap + 1),
+                            reinterpret_cast<long long *>(out_dev), reinterpret_cast<cudaStream_t>(cuda_stream)));
     return 0;
 }
 
@@ -860,6 +889,7 @@ int tlsb_search_async(tlsb_handle *h, void *cuda_stream, void *records_dev)
     h->timed = false;
     if (h->P == 0) return 0;
     if (h->M > h->N) return fail(TLSB_ERR_ARG, "widest template is longer than the light curve");
+    h->out_is_current = !records_dev;
     if (!records_dev) {
         if (h->out.ensure(((size_t)h->P * 3 + 1) * 8)) return fail(TLSB_ERR_ALLOC, "device allocation failed");
         records_dev = h->out.p;
@@ -875,7 +905,9 @@ int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_
     cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
     const size_t P = (size_t)h->P;
     if (P == 0) return 0;
-    if (!h->out.p) return fail(TLSB_ERR_STATE, "tlsb_get_results: no search has written the handle's buffer");
+    if (!h->out.p || !h->out_is_current)
+        return fail(TLSB_ERR_STATE, "tlsb_get_results: the most recent search did not write the handle's own buffer "
+                                    "(it was given records_dev; read that buffer instead)");
     std::vector<long long> packed(P + 1);
     for (int attempt = 0; attempt < 2; ++attempt) {
         CUDA_TRY(cudaMemcpyAsync(chi2_out, h->out.p, P * 8, cudaMemcpyDeviceToHost, s));

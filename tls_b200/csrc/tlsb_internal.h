@@ -193,6 +193,7 @@ cudaError_t launch_prepare(const double *y, const double *dy, double *dval, doub
 cudaError_t launch_t0fit(const T0Args &a, int threads, bool resident, int grid, size_t smem, cudaStream_t s);
 cudaError_t launch_gather_rows(const double *records, size_t record_stride, const int *order, double *out, int P,
                                int n_curves, cudaStream_t s);
+cudaError_t launch_unshard(const long long *gathered, int n, int world, int words_per_rank, long long *out, cudaStream_t s);
 // resident (folded curve in shared memory) or streaming (global scratch) layout           // tlsb_resident.cu
 cudaError_t launch_search_resident(const SearchArgs &a, int threads, bool resident, bool uniform_w, int kb, int grid,
                                    size_t smem, cudaStream_t s);

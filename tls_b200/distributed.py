@@ -109,16 +109,29 @@ class ShardedSearch(object):
         self.searcher.set_inputs(t, y, dy, templates, params)
         self.searcher.set_periods(self.local_periods)
         self.records = torch.zeros(record_words(self.capacity), dtype=torch.int64, device="cuda:%d" % device)
-        self.gathered = self._gathered_host = None
+        self.gathered = self.final = self._final_host = None
+        self._stream = None  # the stream of the most recent step(): what a read of the records has to wait for
         if world > 1:
             self.gathered = torch.empty(world * self.records.numel(), dtype=torch.int64, device=self.records.device)
-            self._gathered_host = torch.empty(self.gathered.numel(), dtype=torch.int64).pin_memory()
+            # the job's records in period order (3 planes + the summed status word), un-interleaved on the device
+            self.final = torch.empty(WORDS_PER_PERIOD * len(self.all_periods) + 1, dtype=torch.int64, device=self.records.device)
+            self._final_host = torch.empty(self.final.numel(), dtype=torch.int64).pin_memory()
 
     def step(self, stream=None):
         ptr = stream.cuda_stream if stream is not None else 0
+        self._stream = stream
         self.searcher.search_async(stream=ptr, records_ptr=self.records.data_ptr())
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.gathered, self.records)
+
+    def _wait(self):
+        """Order the host behind the stream the last step ran on (it need not be torch's current stream)."""
+        import torch
+
+        if self._stream is not None:
+            self._stream.synchronize()
+        else:
+            torch.cuda.default_stream(self.records.device).synchronize()
 
     @property
     def launch_count(self):
@@ -136,34 +149,49 @@ class ShardedSearch(object):
         """This rank's (chi2, row, depth, t0_index), in the order of ``local_periods``."""
         from . import native
 
+        self._wait()
         rec = self.records.cpu().numpy()
         if rec[WORDS_PER_PERIOD * self.n_local] != 0:
             rec = self._redo_exact(lambda: self.records.cpu().numpy())
         return native.unpack_records(rec, self.n_local)
 
     def results(self):
-        """All periods' (chi2, row, depth, t0_index) in the job's period order (every rank)."""
+        """All periods' (chi2, row, depth, t0_index) in the job's period order (every rank).  The gathered shards are
+        un-interleaved ON THE DEVICE (``tlsb_unshard_records``, main.py:190-196) and come back in one copy of
+        24 bytes per period + the summed status word."""
+        from . import native
+
         if self.world == 1:
             return self.local_results()
         n = len(self.all_periods)
-        g = self._fetch_gathered()
-        if gathered_status(g, n, self.world) != 0:  # every rank sees the same flags: a collective decision
-            g = self._redo_exact(self._fetch_gathered)
-        return unpack_gathered(g, n, self.world)
+        rec = self._fetch_final()
+        if rec[WORDS_PER_PERIOD * n] != 0:  # every rank sees the same sum of flags: a collective decision
+            rec = self._redo_exact(self._fetch_final)
+        return native.unpack_records(rec, n)
 
-    def _fetch_gathered(self):
-        """One device-to-host copy of every rank's records into pinned memory."""
+    def _fetch_final(self):
+        """Un-interleave on the device, then ONE device-to-host copy into pinned memory."""
         import torch
 
-        self._gathered_host.copy_(self.gathered, non_blocking=True)
-        torch.cuda.current_stream(self.records.device).synchronize()
-        return self._gathered_host.numpy()
+        from . import native
 
-    def reload(self, t, y, dy, templates, params):
-        """New inputs from HOST buffers for the next ``step`` (the end-to-end path: light curve,
-        template bank and this rank's periods are uploaded again through the C ABI setters)."""
-        self.searcher.set_inputs(t, y, dy, templates, params)
-        self.searcher.set_periods(self.local_periods)
+        dev = self.records.device
+        cur = torch.cuda.current_stream(dev)
+        if self._stream is not None and self._stream != cur:
+            cur.wait_stream(self._stream)
+        native.unshard_records(self.gathered.data_ptr(), len(self.all_periods), self.world, self.final.data_ptr(),
+                               stream=cur.cuda_stream)
+        with torch.cuda.stream(cur):
+            self._final_host.copy_(self.final, non_blocking=True)
+        cur.synchronize()
+        return self._final_host.numpy()
+
+    def reload(self, t, y, dy, templates, params, stream=None):
+        """New inputs from HOST buffers for the next ``step`` (the end-to-end path): light curve, template bank and this
+        rank's periods go up again in ONE call of the C ABI, asynchronously on the stream the step will use.  The
+        buffers must stay unchanged until the step's results have been read."""
+        ptr = stream.cuda_stream if stream is not None else 0
+        self.searcher.set_inputs_async(t, y, dy, templates, params, self.local_periods, stream=ptr)
 
     def _redo_exact(self, fetch):
         """The device plan flagged T14 limits too close to an integer: every rank settles its own

@@ -3,8 +3,9 @@
 Behaviour-matched restatement of ``/root/reference/transitleastsquares/grid.py``:
 ``T14`` (:9-32), ``duration_grid`` (:35-56), ``period_grid`` (:59-156).  These
 are the *inputs* of the GPU hot path, so their values are pinned by
-``tests/test_grid.py`` against the reference's own golden numbers
-(``tests/test_period_grid.py``, ``tests/test_duration_grid.py``).
+``tests/test_host.py`` against the reference's own golden numbers
+(its ``tests/test_period_grid.py``, ``tests/test_duration_grid.py``) and, in the
+build container, bit for bit against the reference itself (``tests/test_reference_diff.py``).
 """
 from __future__ import annotations
 

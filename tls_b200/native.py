@@ -12,6 +12,7 @@ import numpy as np
 from . import build as _build
 
 _LIB = None
+ABI_VERSION = "tlsb200 0.3"  # tlsb_version() must start with this (struct layouts and argtypes below)
 
 EXPORTS = (
     "tlsb_search_periods", "tlsb_create", "tlsb_destroy", "tlsb_set_lightcurve",
@@ -23,6 +24,7 @@ EXPORTS = (
     "tlsb_last_path", "tlsb_last_chunk", "tlsb_set_path", "tlsb_spectra", "tlsb_last_sort_info", "tlsb_last_block", "tlsb_resolve_plan", "tlsb_plan_repair_count",
     "tlsb_set_lightcurves", "tlsb_select_lightcurve", "tlsb_lightcurve_count", "tlsb_search_batch",
     "tlsb_current_device", "tlsb_last_tiled_widths", "tlsb_set_filter", "tlsb_last_filter_stats",
+    "tlsb_set_inputs_async", "tlsb_unshard_records",
 )
 
 _c_i64 = ctypes.c_int64
@@ -59,10 +61,18 @@ def lib():
     path = os.environ.get("TLSB200_LIB") or _build.LIB  # TLSB200_LIB: an experimental build (scripts/gpu_variants.sh)
     if path == _build.LIB and _build.is_stale():
         try:
-            _build.build()
-        except Exception as exc:  # no nvcc on this machine: use the shipped .so if there is one
-            if not os.path.exists(path):
-                raise RuntimeError("libtlsb200.so is missing and could not be built: %s" % exc)
+            _build.nvcc_path()
+            have_nvcc = True
+        except RuntimeError:
+            have_nvcc = False
+        if have_nvcc:
+            _build.build()  # a compile error in edited sources must surface, never a silently stale binary
+        elif not os.path.exists(path):
+            raise RuntimeError("libtlsb200.so is missing and there is no nvcc to build it")
+        else:
+            import warnings
+
+            warnings.warn("libtlsb200.so is older than its sources and there is no nvcc here to rebuild it: using the shipped binary")
     L = ctypes.CDLL(path)
     L.tlsb_last_error.restype = ctypes.c_char_p
     L.tlsb_version.restype = ctypes.c_char_p
@@ -105,6 +115,8 @@ def lib():
     L.tlsb_set_path.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
     L.tlsb_last_sort_info.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_set_filter.argtypes = [_c_vp, ctypes.c_int32, ctypes.c_int32]
+    L.tlsb_set_inputs_async.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_i64]
+    L.tlsb_unshard_records.argtypes = [_c_vp, _c_i64, ctypes.c_int32, _c_vp, _c_vp]
     L.tlsb_last_filter_stats.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_spectra.argtypes = [ctypes.c_int32, _c_vp, _c_i64, _c_i64, _c_i64, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
     L.tlsb_set_lightcurves.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_i64, ctypes.c_int32]
@@ -114,6 +126,9 @@ def lib():
     L.tlsb_search_batch.argtypes = [_c_vp, _c_vp, _c_i64] + [_c_vp] * 8
     L.tlsb_last_t0_fit_ms.restype = ctypes.c_double
     L.tlsb_last_t0_fit_ms.argtypes = [_c_vp]
+    version = L.tlsb_version().decode()
+    if not version.startswith(ABI_VERSION):
+        raise RuntimeError("libtlsb200.so reports %r but this binding was written for %r: rebuild the library" % (version, ABI_VERSION))
     _LIB = L
     return L
 
@@ -279,6 +294,17 @@ class Searcher(object):
         _check(lib().tlsb_set_templates(self._h, ctypes.byref(pk.tp), ctypes.byref(pk.prm)), "tlsb_set_templates")
         self._keep = pk
 
+    def set_inputs_async(self, t, y, dy, templates, params, periods, stream=None):
+        """``tlsb_set_inputs_async``: light curve, bank and periods in one call, uploads asynchronous on ``stream``, no
+        synchronisation.  The arrays are kept alive by this object; they must not be MODIFIED until the stream has
+        passed the uploads (e.g. until the next results have been read)."""
+        pk = _Packed(t, y, dy, templates, params)
+        periods = _f64(periods)
+        _check(lib().tlsb_set_inputs_async(self._h, _c_vp(stream or 0), ctypes.byref(pk.lc), ctypes.byref(pk.tp),
+                                           ctypes.byref(pk.prm), _ptr(periods), len(periods)), "tlsb_set_inputs_async")
+        self._keep = (pk, periods)
+        self.n_periods = len(periods)
+
     def set_lightcurve(self, t, y, dy):
         t, y, dy = _f64(t), _f64(y), _f64(dy)
         lc = LightCurve(_ptr(t), _ptr(y), _ptr(dy), len(t))
@@ -428,6 +454,13 @@ class Searcher(object):
     @property
     def resident(self):
         return bool(lib().tlsb_last_path_resident(self._h))
+
+
+def unshard_records(gathered_ptr, n_periods, world, out_ptr, stream=None):
+    """``tlsb_unshard_records``: rank-major all-gathered records -> 3 * n_periods + 1 words in the job's period order
+    (device pointers; asynchronous on ``stream``)."""
+    _check(lib().tlsb_unshard_records(_c_vp(gathered_ptr), int(n_periods), int(world), _c_vp(out_ptr), _c_vp(stream or 0)),
+           "tlsb_unshard_records")
 
 
 def unpack_records(records, n_periods):
