@@ -536,8 +536,8 @@ def run_b200(args):
                     cpu = dict(port, reference_unavailable=ref.get("unavailable"))
 
     secondary = None
-    if rank == 0 and n_gpus == 1 and not args.no_secondary and not args.max_periods:
-        secondary = secondary_records(args, peak_gbs, local)
+    if not args.no_secondary and not args.max_periods:  # collective at N > 1: every rank takes part, rank 0 reports
+        secondary = secondary_records(args, peak_gbs, local, dist, rank, world, stream)
 
     if rank == 0:
         line = {
@@ -562,59 +562,184 @@ def run_b200(args):
     return 0
 
 
-def secondary_records(args, peak_gbs, device):
-    """Extra context beside the headline (never part of `value`): the Kepler-long configuration
-    (cfg2, whole default grid, tiled kernel) and the wall clock of the drop-in ``.power()``."""
+def secondary_records(args, peak_gbs, device, dist, rank, world, stream):
+    """Extra context beside the headline (never part of `value`), measured at whatever N the line is for so that the
+    driver's 1/2/4/8 runs give STRONG-scaling series under its own clock:
+
+    * ``cfg2_strong``  the Kepler-long configuration (cfg-2), WHOLE default grid of 186,681 periods dealt to the N ranks
+      (period k -> rank k mod N), device-timed (max over ranks) and end to end (host buffers up, un-interleaved
+      records back);
+    * ``cfg4_batch``   1,000 independent K2-like curves through ``batch_power(dist=)`` (curve c -> rank c mod N);
+    * ``cfg5_multi_planet``  mask + rerun x3 on the 4-yr curve with three planets through ``search_planets(dist=)``
+      (tests/test_multi_planet.py:33-40), periods AND T0-fit trial epochs dealt to the ranks;
+    * ``power``        wall clock of the drop-in ``.power()`` on the headline workload, cold and warm (N = 1 only).
+
+    Each record carries its wall time and the shares of search / T0 fit / host work."""
     import warnings
 
     import torch
 
-    from tls_b200 import native, transitleastsquares, workloads
+    from tls_b200 import batch_power, search_planets, transitleastsquares, workloads
+    from tls_b200.distributed import ShardedSearch
 
     out = {}
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        tt = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- cfg-2, whole grid, strong scaling -----------------------------------------------------------------
     try:
-        if args.workload != "cfg2":
-            inp = build_inputs("cfg2", 3)
-            s = native.Searcher(device=device)
-            s.set_inputs(inp.t, inp.y, inp.dy, inp.templates, inp.params)
-            s.set_periods(inp.periods)
-            stream = torch.cuda.current_stream()
-            ms = []
-            for k in range(4):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                s.search_async(stream=stream.cuda_stream)
-                e1.record(stream)
-                torch.cuda.synchronize()
-                if k >= 2:
-                    ms.append(e0.elapsed_time(e1))
-            alg, _, _ = algorithmic_bytes(inp, inp.periods[:: max(1, len(inp.periods) // 2000)])
-            alg *= len(inp.periods) / len(inp.periods[:: max(1, len(inp.periods) // 2000)])
-            step = float(np.mean(ms))
-            out["cfg2"] = {
-                "workload": "cfg2: Kepler-long 4 yr @ 30 min, 50 ppm, whole default grid", "n_points": int(len(inp.y)),
-                "periods": int(len(inp.periods)), "value": len(inp.periods) / (step * 1e-3), "unit": UNIT,
-                "ms_per_step": step, "steps": len(ms), "layout": s.layout, "sort": s.sort_info,
-                "roofline_frac": alg / (step * 1e-3) / 1e9 / peak_gbs, "l2": "inputs larger than L2 per step (scratch 2.5 MB per CTA)",
-            }
-            s.close()
+        inp = build_inputs("cfg2", 3)
+        job = ShardedSearch(inp.t, inp.y, inp.dy, inp.templates, inp.params, inp.periods, rank=rank, world=world,
+                            device=device, dist=dist)
+        pin = {}
+        for name, arr in (("t", inp.t), ("y", inp.y), ("dy", inp.dy)):
+            tt = torch.from_numpy(np.ascontiguousarray(arr, np.float64).copy()).pin_memory()
+            pin[name] = (tt, tt.numpy())
+        ms = []
+        for k in range(4):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            job.step(stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if k >= 2:
+                ms.append(e0.elapsed_time(e1))
+        step = max_over_ranks(float(np.mean(ms)))
+        wall = []
+        for k in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            if dist is None:
+                got = native_search(inp, pin, device)
+            else:
+                job.reload(pin["t"][1], pin["y"][1], pin["dy"][1], inp.templates, inp.params, stream=stream)
+                job.step(stream)
+                got = job.results()
+            barrier()
+            if k >= 1:
+                wall.append(time.perf_counter() - t0)
+        e2e_s = max_over_ranks(float(np.mean(wall)))
+        P = len(inp.periods)
+        rec = {
+            "workload": "cfg2: Kepler-long 4 yr @ 30 min, 50 ppm, whole default grid, STRONG scaling (period k -> rank k mod N)",
+            "n_points": int(len(inp.y)), "periods": int(P), "n_gpus": world, "value": P / (step * 1e-3), "unit": UNIT,
+            "ms_per_step": step, "steps": len(ms), "e2e": {"value": P / e2e_s, "unit": UNIT, "ms_per_step": 1e3 * e2e_s},
+            "layout": job.searcher.layout, "sort": job.searcher.sort_info,
+            "l2": "inputs larger than L2 per step (scratch 2.5 MB per CTA)",
+        }
+        if rank == 0:
+            sub = inp.periods[:: max(1, P // 2000)]
+            alg, _, _ = algorithmic_bytes(inp, sub)
+            rec["roofline_frac_per_gpu"] = alg * (P / len(sub)) / world / (step * 1e-3) / 1e9 / peak_gbs
+            if not args.no_cpu_baseline:  # the gathered result against the CPU oracle, periods spread over all shards
+                from oracle import oracle
+
+                sel = np.unique(np.linspace(0, P - 1, 24).astype(int))
+                w = oracle.search_periods_c(inp.t, inp.y, inp.dy, inp.periods[sel], inp.templates, inp.params)
+                rec["parity"] = {"periods_checked": int(len(sel)), "rows_equal": bool(np.array_equal(got[1][sel], w[1])),
+                                 "chi2_max_rel_err": float(np.max(np.abs(got[0][sel] - w[0]) / np.abs(w[0])))}
+        out["cfg2_strong"] = rec
+        job.close()
     except Exception as exc:  # context only: never fail the headline
-        out["cfg2"] = {"error": str(exc)[:200]}
+        out["cfg2_strong"] = {"error": repr(exc)[:300]}
+
+    # ---- cfg-5: three planets on the 4-yr curve, mask + rerun x3 ---------------------------------------------
     try:
-        t, y, dy, kw = workloads.lightcurve(args.workload)
+        t, y, dy, kw = workloads.lightcurve("cfg2", planets=[7.1, 23.4, 101.7])
+        kw = dict(kw, device=device, verbose=False)
+        if dist is not None:
+            kw["dist"] = dist
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            model = transitleastsquares(t, y, dy, verbose=False)
-            best = 1e9
-            for _ in range(3):
-                t0 = time.perf_counter()
-                res = model.power(show_progress_bar=False, verbose=False, device=device, **kw)
-                best = min(best, time.perf_counter() - t0)
-        out["power"] = {"call": "transitleastsquares(t, y).power() end to end (grids, bank, search, spectra, T0 fit, statistics)",
-                        "workload": args.workload, "wall_s": best, "SDE": float(res.SDE), "period": float(res.period)}
+            search_planets(t, y, n_planets=1, **kw)  # warm-up (buffers, pinned staging)
+            barrier()
+            tm = []
+            t0 = time.perf_counter()
+            found = search_planets(t, y, n_planets=3, timings=tm, **kw)
+            barrier()
+            wall = max_over_ranks(time.perf_counter() - t0)
+        sums = {k: float(sum(d.get(k, 0.0) for d in tm)) for k in sorted(set(k for d in tm for k in d))}
+        host = sum(v for k, v in sums.items() if k not in ("search", "t0_fit", "spectra"))
+        out["cfg5_multi_planet"] = {
+            "workload": "cfg5: cfg2 curve with planets at 7.1 / 23.4 / 101.7 d; power() -> transit_mask -> cleaned_array, x3",
+            "n_gpus": world, "wall_s": wall, "runs": len(tm), "periods_found": [float(r.period) for r in found],
+            "SDE": [float(r.SDE) for r in found], "seconds": sums,
+            "shares": {"search": sums.get("search", 0.0) / wall, "t0_fit": sums.get("t0_fit", 0.0) / wall,
+                       "spectra": sums.get("spectra", 0.0) / wall, "host": host / wall},
+        }
     except Exception as exc:
-        out["power"] = {"error": str(exc)[:200]}
-    return out
+        out["cfg5_multi_planet"] = {"error": repr(exc)[:300]}
+
+    # ---- cfg-4: 1,000 K2-like curves ------------------------------------------------------------------------------
+    try:
+        B = 1000
+        t, ys = workloads.batch_lightcurves(B)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            batch_power(t, ys[: 2 * world], dist=dist, device=device)  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            res = batch_power(t, ys, dist=dist, device=device)
+            barrier()
+            wall = max_over_ranks(time.perf_counter() - t0)
+        P = len(res.periods)
+        tm = res.timings
+        out["cfg4_batch"] = {
+            "workload": "cfg4: %d curves shaped as cfg1 (own planet period ~U(1,40) d, noise ~logU(50,500) ppm), curve c -> rank c mod N" % B,
+            "n_gpus": world, "curves": B, "periods_per_curve": int(P), "wall_s": wall, "curves_per_s": B / wall,
+            "value": B * P / wall, "unit": UNIT, "median_SDE": float(np.median(res.SDE)), "seconds_rank0": tm,
+            "shares": {"search": tm["search"] / wall, "t0_fit": tm["t0_fit"] / wall,
+                       "host": (tm["prepare"] + tm["upload"] + tm["summaries"] + tm["gather"]) / wall},
+        }
+    except Exception as exc:
+        out["cfg4_batch"] = {"error": repr(exc)[:300]}
+
+    # ---- .power() wall clock, cold and warm (one GPU) ---------------------------------------------------------------
+    if dist is None:
+        try:
+            t, y, dy, kw = workloads.lightcurve(args.workload)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                from tls_b200 import transit as transit_mod
+
+                if hasattr(transit_mod, "clear_caches"):
+                    transit_mod.clear_caches()
+                t0 = time.perf_counter()
+                model = transitleastsquares(t, y, dy, verbose=False)
+                res = model.power(show_progress_bar=False, verbose=False, device=device, **kw)
+                cold = time.perf_counter() - t0
+                cold_sections = dict(model.timings)
+                warm = 1e9
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    res = model.power(show_progress_bar=False, verbose=False, device=device, **kw)
+                    warm = min(warm, time.perf_counter() - t0)
+            out["power"] = {"call": "transitleastsquares(t, y).power() end to end (grids, bank, search, spectra, T0 fit, statistics)",
+                            "workload": args.workload, "wall_s_cold": cold, "wall_s_warm": warm, "wall_s": warm,
+                            "cold_means": "first call of the process for this workload: template bank and quadrature nodes not cached, "
+                                          "device buffers of the pooled handle sized for another workload",
+                            "seconds_cold": cold_sections, "seconds_warm": dict(model.timings),
+                            "SDE": float(res.SDE), "period": float(res.period)}
+        except Exception as exc:
+            out["power"] = {"error": repr(exc)[:300]}
+    return out if rank == 0 else None
+
+
+def native_search(inp, pin, device):
+    from tls_b200 import native
+
+    return native.search_periods(pin["t"][1], pin["y"][1], pin["dy"][1], inp.periods, inp.templates, inp.params, devices=[device])
 
 
 def main():

@@ -112,3 +112,50 @@ def test_batch_summaries_all_gather_over_gloo(world, tmp_path):
     want = np.arange(21, dtype=float).reshape(7, 3)
     for rank in range(world):
         np.testing.assert_array_equal(np.load(os.path.join(str(tmp_path), "batch_rank%d.npy" % rank)), want)
+
+
+def _t0_worker(rank, world, port, out_dir):
+    """The sharded final_T0_fit (stats.py:135-204 with trial epoch k -> rank k mod world): the per-rank residuals come
+    from the numpy oracle here (no GPU), the all-gather and the strict-'<' scan are the product's."""
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import torch.distributed as dist
+
+    from conftest import load_t0fit_golden
+    from oracle import oracle
+    from tls_b200 import native, stats
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = load_t0fit_golden("small_margin0")
+
+    dy = np.full(len(g["y"]), np.std(g["y"]))
+
+    def fake_device_fit(t, y, dy, model_in, period, trials, device=None):  # what tlsb_final_t0_fit_lc returns for these trials
+        _, resid, _ = oracle.final_T0_fit_numpy(g["signal"], float(g["depth"]), t, y, dy, period, float(g["margin"]), trials=trials)
+        return int(np.argmin(resid)), resid
+
+    native.final_t0_fit, keep = fake_device_fit, native.final_t0_fit
+    try:
+        T0 = stats.final_T0_fit(g["signal"], float(g["depth"]), g["t"], g["y"], dy, float(g["period"]),
+                                float(g["margin"]), False, False, dist=dist)
+    finally:
+        native.final_t0_fit = keep
+    np.save(os.path.join(out_dir, "t0_rank%d.npy" % rank), np.array([T0]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_t0_fit_over_gloo_gives_the_reference_epoch(world, tmp_path):
+    import torch.multiprocessing as mp
+
+    from conftest import load_t0fit_golden
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_t0_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    want = float(load_t0fit_golden("small_margin0")["T0"])
+    for rank in range(world):
+        assert float(np.load(os.path.join(str(tmp_path), "t0_rank%d.npy" % rank))[0]) == want

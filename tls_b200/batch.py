@@ -97,8 +97,12 @@ def batch_power(t, ys, dys=None, device=None, dist=None, return_power=False, **k
 
     Returns a :class:`BatchResults` with one entry per curve for each of ``SUMMARY_FIELDS``, the
     common ``periods`` (ascending) and, when ``return_power`` is set, ``power`` ``[curves, P]``."""
+    import time as _time
+
     from . import native
 
+    tm = dict(prepare=0.0, upload=0.0, search=0.0, t0_fit=0.0, summaries=0.0, gather=0.0)
+    tick = _time.perf_counter()
     t, ys, dys = _validate_batch(t, ys, dys)
     B, n = ys.shape
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
@@ -113,13 +117,19 @@ def batch_power(t, ys, dys=None, device=None, dist=None, return_power=False, **k
                         transit_count=0)
     summary = np.full((B, len(SUMMARY_FIELDS)), np.nan)
     power = np.zeros((B, len(inputs.periods))) if return_power else None
+    tm["prepare"] = _time.perf_counter() - tick
     if len(mine):
         s = native.Searcher.acquire(device=-1 if device is None else device)
         try:
+            tick = _time.perf_counter()
             s.set_templates(inputs.templates, inputs.params)
             s.set_periods(inputs.periods)
             s.set_lightcurves(t if t.ndim == 1 else t[mine], ys[mine], dys[mine])
+            tm["upload"] = _time.perf_counter() - tick
+            tick = _time.perf_counter()
             out = s.search_batch(stats.median_window(model.oversampling_factor), want_power=return_power)
+            tm["search"] = _time.perf_counter() - tick
+            tick_loop = _time.perf_counter()
             for k, c in enumerate(mine):
                 tc = t if t.ndim == 1 else t[c]
                 chi2 = out["chi2"][k]
@@ -133,22 +143,28 @@ def batch_power(t, ys, dys=None, device=None, dist=None, return_power=False, **k
                     model_in, trials = stats.t0_fit_inputs(signal, out["depth"][k][best], tc, ys[c],
                                                            inputs.periods[best], model.T0_fit_margin)
                     s.select(k)
+                    tick = _time.perf_counter()
                     idx, _ = s.final_t0_fit(model_in, inputs.periods[best], trials)
+                    tm["t0_fit"] += _time.perf_counter() - tick
                     T0 = trials[idx] if idx >= 0 else 0
                     row = summarize_curve(model, tc, ys[c], chi2, out["row"][k], out["depth"][k], out["SDE"][k],
                                           out["SDE_raw"][k], best, inputs, T0)
                     if return_power:
                         power[c] = out["power"][k]
                 summary[c] = [row[f] for f in SUMMARY_FIELDS]
+            tm["summaries"] = (_time.perf_counter() - tick_loop) - tm["t0_fit"]
         finally:
             s.release()
     if world > 1:
+        tick = _time.perf_counter()
         summary = _all_gather_rows(summary, mine, B, dist, device)
+        tm["gather"] = _time.perf_counter() - tick
         if return_power:
             power = _all_gather_rows(power, mine, B, dist, device)
     res = BatchResults({f: summary[:, i] for i, f in enumerate(SUMMARY_FIELDS)})
     res["periods"] = np.sort(inputs.periods)
     res["n_curves"] = B
+    res["timings"] = tm  # this rank's wall-clock seconds per section (search = plan + search + spectra kernels and their copies)
     if return_power:
         res["power"] = power
     return res
@@ -175,24 +191,35 @@ def _all_gather_rows(rows, mine, n_rows, dist, device):
     return full
 
 
-def search_planets(t, y, dy=None, n_planets=3, SDE_min=0.0, verbose=False, **kwargs):
+def search_planets(t, y, dy=None, n_planets=3, SDE_min=0.0, verbose=False, timings=None, **kwargs):
     """Iterative multi-planet search: ``power()``, mask ``transit_mask(t, period, 2*duration, T0)``,
     ``cleaned_array``, repeat (tests/test_multi_planet.py:33-40).  Returns the list of results
     objects, strongest signal first; stops early when a run's SDE is below ``SDE_min`` or nothing
-    was fitted."""
+    was fitted.  ``timings``: a list that receives one dict of section seconds per run (``power().timings`` plus
+    ``validate`` = input cleaning in the constructor and ``mask`` = masking + ``cleaned_array``)."""
+    import time as _time
+
     t, y = np.asarray(t, dtype=float), np.asarray(y, dtype=float)
     dy = None if dy is None else np.asarray(dy, dtype=float)
     found = []
     for _ in range(n_planets):
-        res = transitleastsquares(t, y, dy, verbose=verbose).power(**dict(kwargs, show_progress_bar=False))
+        tick = _time.perf_counter()
+        model = transitleastsquares(t, y, dy, verbose=verbose)
+        t_validate = _time.perf_counter() - tick
+        res = model.power(**dict(kwargs, show_progress_bar=False))
+        if timings is not None:
+            timings.append(dict(model.timings, validate=t_validate))
         if not np.isfinite(res.period) or res.SDE < SDE_min:
             break
         found.append(res)
+        tick = _time.perf_counter()
         intransit = transit_mask(t, res.period, 2 * res.duration, res.T0)
         if dy is None:
             t, y = cleaned_array(t[~intransit], y[~intransit])
         else:
             t, y, dy = cleaned_array(t[~intransit], y[~intransit], dy[~intransit])
+        if timings is not None:
+            timings[-1]["mask"] = _time.perf_counter() - tick
         if len(t) < 10:
             break
     return found

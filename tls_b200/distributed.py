@@ -86,6 +86,30 @@ def all_gather_records(local_records, dist, world):
     return out
 
 
+def all_gather_interleaved(local_values, n_total, dist, device=None):
+    """``local_values`` holds elements rank, rank + world, ... of an array of ``n_total`` float64; ONE all-gather
+    returns the whole array in its original order on every rank (NCCL: through the GPU; gloo: on the CPU)."""
+    import torch
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cap = shard_capacity(n_total, world)
+    pad = np.full(cap, np.nan)
+    pad[: len(local_values)] = local_values
+    if dist.get_backend() == "gloo":
+        dev = "cpu"
+    else:
+        dev = "cuda:%d" % (torch.cuda.current_device() if device is None else device)
+    src = torch.from_numpy(pad).to(dev)
+    out = torch.empty(world * cap, dtype=src.dtype, device=dev)
+    dist.all_gather_into_tensor(out, src)
+    out = out.cpu().numpy().reshape(world, cap)
+    full = np.empty(n_total)
+    for r in range(world):
+        n = len(range(r, n_total, world))
+        full[r::world] = out[r, :n]
+    return full
+
+
 class ShardedSearch(object):
     """The period search of one light curve on ``world`` GPUs, one process per GPU.
 

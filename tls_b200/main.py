@@ -47,6 +47,7 @@ class transitleastsquares(object):
     def __init__(self, t, y, dy=None, verbose=True):
         self.t, self.y, self.dy = validate_inputs(t, y, dy)
         self.verbose = verbose
+        self.timings = {}
 
     # ------------------------------------------------------------------ host prep
     def prepare(self, **kwargs):
@@ -107,12 +108,20 @@ class transitleastsquares(object):
         return stats.final_T0_fit(
             signal=signal, depth=depth, t=self.t, y=self.y, dy=self.dy, period=period,
             T0_fit_margin=self.T0_fit_margin, show_progress_bar=self.show_progress_bar,
-            verbose=self.verbose, device=getattr(self, "_t0_device", None),
+            verbose=self.verbose, device=getattr(self, "_t0_device", None), dist=getattr(self, "_dist", None),
         )
 
     def power(self, **kwargs):
-        """Compute the periodogram for a set of user-defined parameters (main.py:51)."""
+        """Compute the periodogram for a set of user-defined parameters (main.py:51).
+
+        ``self.timings`` holds the wall-clock seconds of the call's sections afterwards (prepare = grids + template
+        bank, search, spectra, t0_fit, statistics): what bench.py reports as the shares of ``.power()``."""
+        import time as _time
+
+        tick = _time.perf_counter()
+        self.timings = {}
         inputs = self.prepare(**kwargs)
+        self.timings["prepare"] = _time.perf_counter() - tick
         if self.verbose:
             print(C.VERSION)
         periods = inputs.periods
@@ -129,11 +138,14 @@ class transitleastsquares(object):
             print("Using the B200 search kernels (use_threads=%d is accepted and ignored)" % self.use_threads)
 
         dist = kwargs.get("dist", None)
+        self._dist = dist
         if dist is not None and devices is None:
             import torch
 
             devices = torch.cuda.current_device()  # one process per GPU: this rank's device
+        tick = _time.perf_counter()
         chi2_by_input, rows_by_input, depths_by_input = self._search(inputs, devices, dist)
+        self.timings["search"] = _time.perf_counter() - tick
         self._t0_device = None if devices is None else int(np.atleast_1d(devices)[0])
 
         # main.py:190-196: ascending period order
@@ -142,7 +154,10 @@ class transitleastsquares(object):
         chi2 = np.asarray(chi2_by_input)[order]
         rows = np.asarray(rows_by_input)[order]
         depths = np.asarray(depths_by_input)[order]
-        return self._postprocess(test_statistic_periods, chi2, rows, depths, lc_arr, overview, durations)
+        tick = _time.perf_counter()
+        res = self._postprocess(test_statistic_periods, chi2, rows, depths, lc_arr, overview, durations)
+        self.timings["statistics"] = (_time.perf_counter() - tick) - self.timings.get("spectra", 0.0) - self.timings.get("t0_fit", 0.0)
+        return res
 
     # ------------------------------------------------------------------ host post
     def _postprocess(self, test_statistic_periods, chi2, rows, depths, lc_arr, overview, durations):
@@ -179,11 +194,17 @@ class transitleastsquares(object):
             duration = nan
             in_count = after_count = before_count = nan
         else:
+            import time as _time
+
+            tick = _time.perf_counter()
             SR, power_raw, power, SDE_raw, SDE = self._spectra(chi2)
+            self.timings["spectra"] = _time.perf_counter() - tick
             top = np.argmax(power)
             period = test_statistic_periods[top]
             depth = depths[top]
+            tick = _time.perf_counter()
             T0 = self._final_T0_fit(lc_arr[best_row], depth, period)
+            self.timings["t0_fit"] = _time.perf_counter() - tick
             transit_times = stats.all_transit_times(T0, t, period)
             transit_duration = stats.calculate_transit_duration_in_days(t, period, transit_times, duration)
 

@@ -134,7 +134,7 @@ def t0_fit_inputs(signal, depth, t, y, period, T0_fit_margin):
     return model_in, trials
 
 
-def final_T0_fit(signal, depth, t, y, dy, period, T0_fit_margin, show_progress_bar, verbose, device=None):
+def final_T0_fit(signal, depth, t, y, dy, period, T0_fit_margin, show_progress_bar, verbose, device=None, dist=None):
     """Scan mid-transit epochs at the best period and return the best T0 (stats.py:135-204).
 
     The loop over trial epochs (stats.py:165-202: fold, stable argsort, roll, weighted
@@ -150,6 +150,20 @@ def final_T0_fit(signal, depth, t, y, dy, period, T0_fit_margin, show_progress_b
         print("Searching for best T0 for period", format(period, ".5f"), "days")
     if len(trials) == 0:
         return 0
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1 and len(trials) >= 4 * dist.get_world_size():
+        # one process per GPU: trial epoch k -> rank k mod world (the epochs are independent), ONE all-gather of the
+        # residuals, then the reference's strict '<' scan from +inf over ALL of them (stats.py:200-202)
+        from .distributed import all_gather_interleaved
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        _, mine = native.final_t0_fit(t, y, dy, model_in, period, trials[rank::world], device=device)
+        resid = all_gather_interleaved(mine, len(trials), dist, device=device)
+        best, lowest = -1, np.inf
+        below = np.flatnonzero(resid < np.inf)
+        if len(below):
+            k = int(np.argmin(resid[below]))  # first minimum among the finite ones = the strict-'<' winner
+            best, lowest = int(below[k]), resid[below][k]
+        return trials[best] if best >= 0 else 0
     best, _ = native.final_t0_fit(t, y, dy, model_in, period, trials, device=device)
     return trials[best] if best >= 0 else 0  # stats.py:163: T0 = 0 when nothing is below +inf
 

@@ -130,6 +130,11 @@ _BANKS = collections.OrderedDict()
 _BANKS_MAX = 8
 
 
+def clear_caches():
+    """Forget the cached template banks (bench.py: the cold figure of ``.power()``)."""
+    _BANKS.clear()
+
+
 def _build_bank(durations, maxwidth_in_samples, per, rp, a, inc, ecc, w, u, limb_dark):
     rows = np.size(durations)
     overview = np.zeros(

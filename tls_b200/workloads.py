@@ -48,3 +48,36 @@ def lightcurve(name, hetero=False, planets=None):
     if hetero:
         dy = sigma * np.random.uniform(0.5, 2.0, n)
     return t, y, dy, dict(kw)
+
+
+_PROFILE = {}
+
+
+def _phase_profile(rp=6371.0 / 696342.0, a=19.0, u=(0.4, 0.4), half_width=0.03, n=12001):
+    """The transit of ``inject`` as a function of orbital PHASE only (circular orbit, inc = 90: the projected
+    separation is a*sin(2 pi phase), whatever the period), tabulated once: batches of synthetic curves are then O(n)
+    interpolations instead of one limb-darkening integration per curve."""
+    key = (rp, a, tuple(u), half_width, n)
+    if key not in _PROFILE:
+        ph = np.linspace(-half_width, half_width, n)
+        _PROFILE[key] = (ph, inject(ph, 1.0, 0.0, rp=rp, a=a, u=u))
+    return _PROFILE[key]
+
+
+def batch_lightcurves(n_curves, first_seed=1000, only=None):
+    """cfg-4: ``n_curves`` light curves shaped as cfg-1 (90 d @ 30 min, 4320 points, shared time
+    stamps), curve c seeded with ``first_seed + c``: planet period ~ U(1, 40) d, epoch ~ U(0, period), white noise
+    ~ logU(50, 500) ppm.  ``only``: the curve indices to generate (a rank's shard); the others stay 1.0.
+    Returns ``(t, ys)``."""
+    t = np.linspace(3.14, 93.14, 4320)
+    ph_tab, f_tab = _phase_profile()
+    ys = np.ones((n_curves, len(t)))
+    for c in (range(n_curves) if only is None else only):
+        rng = np.random.RandomState(first_seed + int(c))
+        per = rng.uniform(1.0, 40.0)
+        t0 = 3.14 + rng.uniform(0.0, per)
+        ppm = 10 ** rng.uniform(np.log10(50.0), np.log10(500.0))
+        x = (t - t0) / per
+        x = x - np.rint(x)  # phase in [-0.5, 0.5)
+        ys[c] = np.interp(x, ph_tab, f_tab, left=1.0, right=1.0) + rng.normal(0.0, ppm * 1e-6, len(t))
+    return t, ys
