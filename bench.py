@@ -478,6 +478,8 @@ def run_b200(args):
         k_ms = float(np.mean(kernel_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         roofline = {
+            # frac keeps SURVEY.md §8(d)'s definition (algorithmic bytes of the (period, duration)-tile model / kernel time /
+            # measured HBM peak); "bound" is replaced below by the resource ncu shows binding this build
             "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
             "traffic": None, "peak_source": peak_src,
             "kernel": "tlsb_search_tiled_kernel" if job.searcher.path == "tiled" else "tlsb_search_kernel",
@@ -489,29 +491,47 @@ def run_b200(args):
                      "streaming": "streaming (per-CTA L2 scratch)"}[job.searcher.path],
             "layout": job.searcher.layout,
         }
-        try:  # the second ceiling: fp64 FMAs of the tap loop against the fp64 pipe
+        try:  # the second ceiling: the FMAs of the tap loop against the pipe they run on
             taps, pass_rate, n_sampled = tap_work(inp, job.local_periods)
             prop = torch.cuda.get_device_properties(local)
             clk = sampler.summary().get("sm_mhz") or sampler.summary().get("sm_max_mhz") or 1965.0
-            fma_per_tap = 1 if bool(np.all(inp.dy == inp.dy[0])) else 2
-            peak_fma = prop.multi_processor_count * 64 * float(clk) * 1e6  # 64 fp64 FMA per clock per SM
+            uniform = bool(np.all(inp.dy == inp.dy[0]))
+            # equal weights: the correlation runs in fp32 (filter pass, 128 FMA/clk/SM) and only a handful of finalists
+            # per period are re-evaluated in fp64; per-point weights: two fp64 correlations per tap (64 FMA/clk/SM)
+            fma_per_tap, per_clk, pipe = (1, 128, "fp32") if uniform else (2, 64, "fp64")
+            peak_fma = prop.multi_processor_count * per_clk * float(clk) * 1e6
             ach_fma = taps * fma_per_tap * P_rank / (k_ms * 1e-3)
-            roofline["fp64"] = {
-                "taps_per_period": taps, "gate_pass_rate": pass_rate, "periods_sampled": n_sampled,
+            roofline["fma"] = {
+                "pipe": pipe, "taps_per_period": taps, "gate_pass_rate": pass_rate, "periods_sampled": n_sampled,
                 "fma_per_tap": fma_per_tap, "achieved": ach_fma / 1e12, "peak": peak_fma / 1e12, "unit": "TFMA/s",
                 "frac": ach_fma / peak_fma,
-                "peak_source": "%d SMs x 64 fp64 FMA/clk x %.0f MHz (SM clock sampled during the timed region)" % (
-                    prop.multi_processor_count, float(clk)),
+                "peak_source": "%d SMs x %d %s FMA/clk x %.0f MHz (SM clock sampled during the timed region)" % (
+                    prop.multi_processor_count, per_clk, pipe, float(clk)),
             }
         except Exception as exc:  # never lose the line over the secondary figure
-            roofline["fp64"] = {"error": str(exc)[:200]}
-        traffic_file = os.path.join(REPO, "profiles", "traffic_%s.json" % args.workload)
-        if os.path.exists(traffic_file):
+            roofline["fma"] = {"error": str(exc)[:200]}
+        # what ncu measured for THIS build of the kernels (scripts/ncu_to_json.py): DRAM traffic per launch, the
+        # binding on-chip resource, shared-memory wavefronts and issue-slot utilisation
+        prof_file = os.path.join(REPO, "profiles", "ncu_%s.json" % args.workload)
+        if os.path.exists(prof_file):
             try:
-                with open(traffic_file) as f:
-                    roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+                from tls_b200 import build as lib_build
+
+                with open(prof_file) as f:
+                    prof = json.load(f)
+                fresh = prof.get("source_hash") == lib_build.source_hash()
+                roofline["traffic"] = prof.get("dram_bytes_per_launch")
+                roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full: the folded "
+                                            "curve never leaves the SM, so the algorithmic-bytes figure above is an EFFECTIVE bandwidth")
+                roofline["bound"] = prof.get("bound") or "hbm"
+                roofline["bound_ranking"] = prof.get("bound_ranking")
+                roofline["smem"] = prof.get("smem")
+                roofline["issue_pct"] = (prof.get("pipes_pct_of_peak") or {}).get("issue_pct")
+                roofline["pipes_pct_of_peak"] = prof.get("pipes_pct_of_peak")
+                roofline["profile"] = {"file": "profiles/ncu_%s.json" % args.workload, "of_this_build": bool(fresh),
+                                       "kernel_ms_under_ncu": prof.get("gpu_time_ms")}
+            except Exception as exc:
+                roofline["profile"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline:
             rate, n, cores = cpu_sample(inp, job.local_periods, args.cpu_seconds)
             port = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

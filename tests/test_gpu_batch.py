@@ -195,3 +195,69 @@ def test_power_and_batch_on_two_gpus_equal_one_gpu(tmp_path):
         np.testing.assert_array_equal(z["b_period"], one_b.period)
         np.testing.assert_array_equal(z["b_T0"], one_b.T0)
         np.testing.assert_allclose(z["b_SDE"], one_b.SDE, rtol=1e-12)
+
+
+def _oracle_check(inp, got, n_check, label):
+    """(chi2, row, depth) of the CUDA path against the C oracle on ``n_check`` periods spread over the grid."""
+    from oracle import oracle
+
+    chi2, row, depth = got[:3]
+    sel = np.unique(np.linspace(0, len(inp.periods) - 1, n_check).astype(int))
+    w = oracle.search_periods_c(inp.t, inp.y, inp.dy, inp.periods[sel], inp.templates, inp.params)
+    np.testing.assert_array_equal(np.asarray(row)[sel], w[1], err_msg=label + ": rows")
+    fin = np.isfinite(w[0])
+    np.testing.assert_allclose(np.asarray(chi2)[sel][fin], w[0][fin], rtol=1e-5, atol=0, err_msg=label + ": chi2")
+    np.testing.assert_allclose(np.asarray(depth)[sel], w[2], rtol=1e-5, atol=0, err_msg=label + ": depth")
+
+
+def test_cfg4_batch_records_equal_the_oracle():
+    """cfg-4 (BASELINE.json: a batch of K2-like 90 d curves): the records ``tlsb_search_batch`` returns for several
+    curves of the batch — own planet, own noise level — against the C ORACLE (core.py:96-188 restated), not
+    against this repository's own ``.power()``."""
+    from tls_b200 import native, stats, transitleastsquares, workloads
+
+    t, ys = workloads.batch_lightcurves(6)
+    dys = np.repeat(np.std(ys, axis=1)[:, None], ys.shape[1], axis=1)
+    model = transitleastsquares(t, ys[0], dys[0], verbose=False)
+    inputs = model.prepare(verbose=False, show_progress_bar=False)
+    s = native.Searcher()
+    try:
+        s.set_templates(inputs.templates, inputs.params)
+        s.set_periods(inputs.periods)
+        s.set_lightcurves(t, ys, dys)
+        out = s.search_batch(stats.median_window(model.oversampling_factor), want_power=False)
+    finally:
+        s.close()
+    for c in (0, 2, 3, 5):
+        one = transitleastsquares(t, ys[c], dys[c], verbose=False).prepare(verbose=False, show_progress_bar=False)
+        np.testing.assert_array_equal(one.periods, inputs.periods)
+        _oracle_check(one, (out["chi2"][c], out["row"][c], out["depth"][c]), 40, "cfg-4 curve %d" % c)
+
+
+def test_cfg5_mask_and_rerun_equals_the_oracle_after_every_mask():
+    """cfg-5 (BASELINE.json: mask + rerun x3; tests/test_multi_planet.py:33-40): a three-planet curve of ~13 k points
+    (the tiled kernel).  After EVERY mask the search's (chi2, row, depth) must equal the C oracle on >= 100 periods of
+    that run's own grid, and the three planets must come out."""
+    from tls_b200 import cleaned_array, native, transit_mask, transitleastsquares, workloads
+
+    rng = np.random.RandomState(5)
+    t = np.linspace(0.0, 270.0, 12960)  # 270 d @ 30 min
+    planets = (5.3, 11.7, 23.9)
+    flux = np.ones(len(t))
+    for per in planets:
+        flux = flux * workloads.inject(t, per, 1.0 + 0.37 * per, rp=0.03)
+    y = flux + rng.normal(0, 150e-6, len(t))
+    found = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for run in range(3):
+            model = transitleastsquares(t, y, verbose=False)
+            inp = model.prepare(verbose=False, show_progress_bar=False, period_max=60.0)
+            got = native.search_periods(inp.t, inp.y, inp.dy, inp.periods, inp.templates, inp.params)
+            _oracle_check(inp, got, 110, "cfg-5 run %d (N = %d)" % (run, len(inp.t)))
+            res = model.power(show_progress_bar=False, verbose=False, period_max=60.0)
+            found.append(float(res.period))
+            keep = ~transit_mask(t, res.period, 2 * res.duration, res.T0)
+            t, y = cleaned_array(t[keep], y[keep])
+    for per in planets:
+        assert min(abs(f - per) / per for f in found) < 2e-3, (per, found)

@@ -310,3 +310,46 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "tls_oracle" not in text, f
+
+
+# ---- transit.py:8-42 calls batman; batman's quadratic law is Mandel & Agol's closed form ------------------
+def test_closed_form_mandel_agol_equals_the_quadrature():
+    """tls_b200.mandelagol (Mandel & Agol 2002 eq. 1, eq. 7 + Table 1; elliptic integrals) against the independent
+    radial quadrature of tls_b200.limbdark, over the planet sizes and separations the template bank and the
+    workloads use and well beyond (grazing, z = p, z = 1 - p, centre, planet larger than the star)."""
+    from tls_b200 import limbdark, mandelagol
+
+    worst = 0.0
+    for p in (6371.0 / 696342.0, 0.05, 0.1, 0.3, 0.45, 0.7, 1.2):
+        z = np.concatenate([np.linspace(0, 1 + p + 0.05, 2001), [p, abs(1 - p), 0.0, 1 + p],
+                            p + np.array([-2e-5, -1e-7, -1e-9, 1e-9, 1e-7, 2e-5, 4e-5])])
+        for law, u in (("quadratic", [0.4, 0.4]), ("quadratic", [0.4804, 0.1867]), ("linear", [0.6]), ("uniform", [])):
+            u1, u2 = (u + [0.0, 0.0])[:2]
+            closed = mandelagol.quadratic_flux(z, p, u1, u2)
+            quad = limbdark.occulted_flux(z, p, law, u, 384)
+            worst = max(worst, float(np.max(np.abs(closed - quad))))
+    assert worst < 1e-10, worst
+
+
+def test_template_bank_is_the_same_with_either_transit_model():
+    """The bank (transit.py:98-160: trim index, overshoot, widths, lengths, signal values) built from the closed form
+    and from the quadrature: identical structure, values within 1e-9."""
+    from tls_b200 import limbdark, transit
+
+    kw = dict(durations=duration_grid(period_grid(1, 1, 90.0), shortest=1 / 4320, log_step=1.1), maxwidth_in_samples=518,
+              per=13.4, rp=6371.0 / 696342.0, a=217, inc=90, ecc=0, w=90, u=[0.4804, 0.1867], limb_dark="quadratic", verbose=False)
+    transit.clear_caches()
+    ov_c, lc_c = transit.get_cache(**kw)
+    keep = limbdark.TransitModel.__init__.__defaults__
+    limbdark.TransitModel.__init__.__defaults__ = (384, False)
+    try:
+        transit.clear_caches()
+        ov_q, lc_q = transit.get_cache(**kw)
+    finally:
+        limbdark.TransitModel.__init__.__defaults__ = keep
+        transit.clear_caches()
+    np.testing.assert_array_equal(ov_c["width_in_samples"], ov_q["width_in_samples"])
+    np.testing.assert_allclose(ov_c["overshoot"], ov_q["overshoot"], rtol=1e-8)
+    assert [len(a) for a in lc_c] == [len(a) for a in lc_q]
+    for a, b in zip(lc_c, lc_q):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-9)

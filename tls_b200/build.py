@@ -29,6 +29,18 @@ def nvcc_path():
     raise RuntimeError("nvcc not found; libtlsb200.so cannot be built")
 
 
+def source_hash():
+    """sha256 over the kernel and host sources of the library (profiles/ncu_*.json record it: a profile of another
+    build is reported as stale by bench.py and refused by tests/test_bench_contract.py)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for p in sorted(SRC + HEADERS):
+        with open(p, "rb") as f:
+            h.update(os.path.basename(p).encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True

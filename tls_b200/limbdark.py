@@ -8,9 +8,11 @@ the *published* model that batman implements (Mandel & Agol 2002; Kreidberg
 2015): a dark planet disc of radius ``rp`` (stellar radii) at projected
 separation ``z`` blocks the part of a limb-darkened stellar disc it overlaps.
 
-Instead of the closed-form elliptic-integral expressions (quadratic law only)
-the blocked flux is computed for *any* radial intensity profile I(r) by a 1-D
-quadrature over stellar radius r::
+For the quadratic, linear and uniform laws ``TransitModel`` evaluates the closed-form
+elliptic-integral expressions of that paper (:mod:`tls_b200.mandelagol`, what batman
+evaluates for its default law).  For every other law, and as the independent cross-check
+of the closed form (they agree to 1e-11, ``tests/test_host.py``), the blocked flux is
+computed for *any* radial intensity profile I(r) by a 1-D quadrature over stellar radius r::
 
     blocked(z) = int_{0}^{1} I(r) * 2*kappa(r; z, rp) * r dr
     kappa      = pi                         if r <= rp - z      (ring fully covered)
@@ -234,9 +236,10 @@ class TransitModel(object):
     """``TransitModel(params, t).light_curve(params)`` — the two calls the reference
     makes (``transit.py:24-25``)."""
 
-    def __init__(self, params, t, n_nodes=384):
+    def __init__(self, params, t, n_nodes=384, closed_form=True):
         self.t = np.asarray(t, dtype=float)
         self.n_nodes = n_nodes
+        self.closed_form = closed_form  # quadratic / linear / uniform: Mandel & Agol's analytic model (what batman evaluates)
 
     def light_curve(self, params):
         z = separation(
@@ -245,7 +248,14 @@ class TransitModel(object):
         finite = np.isfinite(z)
         flux = np.ones_like(self.t)
         if np.any(finite):
-            flux[finite] = occulted_flux(
-                z[finite], params.rp, params.limb_dark, params.u, self.n_nodes
-            )
+            law = params.limb_dark
+            if self.closed_form and law in ("quadratic", "linear", "uniform"):
+                from . import mandelagol
+
+                u = [float(v) for v in np.atleast_1d(params.u)] if law != "uniform" else []
+                u1 = u[0] if len(u) > 0 else 0.0
+                u2 = u[1] if len(u) > 1 else 0.0
+                flux[finite] = mandelagol.quadratic_flux(z[finite], params.rp, u1, u2)
+            else:
+                flux[finite] = occulted_flux(z[finite], params.rp, law, params.u, self.n_nodes)
         return flux

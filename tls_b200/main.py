@@ -148,8 +148,8 @@ class transitleastsquares(object):
         self.timings["search"] = _time.perf_counter() - tick
         self._t0_device = None if devices is None else int(np.atleast_1d(devices)[0])
 
-        # main.py:190-196: ascending period order
-        order = np.argsort(periods)
+        # main.py:190-196: ascending period order (the grid arrives descending: a stable sort sees one run)
+        order = np.argsort(periods, kind="stable")
         test_statistic_periods = periods[order]
         chi2 = np.asarray(chi2_by_input)[order]
         rows = np.asarray(rows_by_input)[order]

@@ -49,12 +49,31 @@ def reference_transit(samples, per, rp, a, inc, ecc, w, u, limb_dark):
     return out.copy()
 
 
+_SUPERSAMPLED = {}
+
+
+def _supersampled_flux(per, rp, a, inc, ecc, w, u, limb_dark):
+    """The model light curve on the reference's fixed supersampled time axis (transit.py:12-25).  It does not depend
+    on ``samples``, so the limb-darkening integration runs once per transit shape and process; every
+    ``reference_transit`` of that shape (the bank, and two more per ``power()`` for the model curves, main.py:316-330)
+    is then a resampling."""
+    key = (float(per), float(rp), float(a), float(inc), float(ecc), float(w),
+           tuple(float(x) for x in np.atleast_1d(u)), str(limb_dark))
+    hit = _SUPERSAMPLED.get(key)
+    if hit is None:
+        t = np.linspace(-0.5, 0.5, C.SUPERSAMPLE_SIZE)
+        p = limbdark.TransitParams()
+        p.t0, p.per, p.rp, p.a, p.inc, p.ecc, p.w = 0, per, rp, a, inc, ecc, w
+        p.u, p.limb_dark = u, limb_dark
+        hit = (t, limbdark.TransitModel(p, t).light_curve(p))
+        if len(_SUPERSAMPLED) >= 16:
+            _SUPERSAMPLED.pop(next(iter(_SUPERSAMPLED)))
+        _SUPERSAMPLED[key] = hit
+    return hit
+
+
 def _reference_transit(samples, per, rp, a, inc, ecc, w, u, limb_dark):
-    t = np.linspace(-0.5, 0.5, C.SUPERSAMPLE_SIZE)
-    p = limbdark.TransitParams()
-    p.t0, p.per, p.rp, p.a, p.inc, p.ecc, p.w = 0, per, rp, a, inc, ecc, w
-    p.u, p.limb_dark = u, limb_dark
-    flux = limbdark.TransitModel(p, t).light_curve(p)
+    t, flux = _supersampled_flux(per, rp, a, inc, ecc, w, u, limb_dark)
 
     first = int(np.argmax(flux < 1))
     in_flux = flux[first : -first + 1]
@@ -131,8 +150,10 @@ _BANKS_MAX = 8
 
 
 def clear_caches():
-    """Forget the cached template banks (bench.py: the cold figure of ``.power()``)."""
+    """Forget the cached template banks and model curves (bench.py: the cold figure of ``.power()``)."""
     _BANKS.clear()
+    _REFERENCE_CACHE.clear()
+    _SUPERSAMPLED.clear()
 
 
 def _build_bank(durations, maxwidth_in_samples, per, rp, a, inc, ecc, w, u, limb_dark):
