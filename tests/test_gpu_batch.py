@@ -218,7 +218,7 @@ def test_cfg4_batch_records_equal_the_oracle():
 
     t, ys = workloads.batch_lightcurves(6)
     dys = np.repeat(np.std(ys, axis=1)[:, None], ys.shape[1], axis=1)
-    model = transitleastsquares(t, ys[0], dys[0], verbose=False)
+    model = transitleastsquares(t, ys[0], verbose=False)  # dy=None: std(y) everywhere (validate.py:39-40), as in the batch
     inputs = model.prepare(verbose=False, show_progress_bar=False)
     s = native.Searcher()
     try:
@@ -229,7 +229,8 @@ def test_cfg4_batch_records_equal_the_oracle():
     finally:
         s.close()
     for c in (0, 2, 3, 5):
-        one = transitleastsquares(t, ys[c], dys[c], verbose=False).prepare(verbose=False, show_progress_bar=False)
+        one = transitleastsquares(t, ys[c], verbose=False).prepare(verbose=False, show_progress_bar=False)
+        np.testing.assert_array_equal(one.dy, dys[c])
         np.testing.assert_array_equal(one.periods, inputs.periods)
         _oracle_check(one, (out["chi2"][c], out["row"][c], out["depth"][c]), 40, "cfg-4 curve %d" % c)
 
