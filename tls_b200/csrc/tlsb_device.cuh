@@ -487,11 +487,12 @@ __device__ __forceinline__ void block_min(const WidthRec &wr, const double *cs, 
 // Zero padded taps add exact zeros.  NaN / inf anywhere make the comparison fail safe (the candidate is a finalist).
 // ------------------------------------------------------------------------------------------
 // One pass of the fp32 tap loop over a residue class (V = 1) or a pair of adjacent classes (V = 2, even strides:
-// samples and template values are then aligned float2).  Step m multiplies the sample vector at sp + m*X with the
-// template vectors of steps m, m-1, ..., m-kBlock+1 (one per candidate).  Steps run in unguarded groups of kG = 8;
-// the template values of two consecutive groups live in two register sets that swap roles every group: the set of
-// the previous group is refilled with the NEXT group's values as soon as its entries are dead (entry k is last used
-// at step k-2), so there is no window copy, and samples are loaded one group ahead.
+// samples are then aligned float2).  Step m multiplies the sample vector at sp + m*X with the template vectors of
+// steps m, m-1, ..., m-kBlock+1 (one per candidate).  The class's template values are CONTIGUOUS in tq32
+// (residue-class major, tlsb_internal.h), so 8 / V steps' worth arrive per float4 broadcast load.  Steps run in
+// unguarded groups of kG = 8; the template values of two consecutive groups live in two register sets that swap
+// roles every group: the set of the previous group is refilled with the NEXT group's values as soon as its entries
+// are dead (entry k is last used at step k-2), so there is no window copy, and samples are loaded one group ahead.
 template <int kBlock, int V, bool kUnit>
 __device__ __forceinline__ void tap_pass32(const float *__restrict__ qp, const float *__restrict__ sp, int X, int groups,
                                            float (&B)[kBlock])
@@ -502,18 +503,14 @@ __device__ __forceinline__ void tap_pass32(const float *__restrict__ qp, const f
     float qa[kG][V], qb[kG][V];  // template values of the even / odd groups
     float sa[kG][V], sb[kG][V];  // samples, one group ahead
     auto load_q = [&](float (&dst)[kG][V], const float *__restrict__ p, int from) {  // entries [from, from + 4)
-        if (kUnit) {
+        if (V == 2) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p + 2 * from));
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p + 2 * from + 4));
+            dst[from][0] = v0.x; dst[from][V - 1] = v0.y; dst[from + 1][0] = v0.z; dst[from + 1][V - 1] = v0.w;
+            dst[from + 2][0] = v1.x; dst[from + 2][V - 1] = v1.y; dst[from + 3][0] = v1.z; dst[from + 3][V - 1] = v1.w;
+        } else {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(p + from));
             dst[from][0] = v.x; dst[from + 1][0] = v.y; dst[from + 2][0] = v.z; dst[from + 3][0] = v.w;
-        } else if (V == 2) {
-#pragma unroll
-            for (int k = from; k < from + 4; ++k) {
-                const float2 v = __ldg(reinterpret_cast<const float2 *>(p + k * Xs));
-                dst[k][0] = v.x; dst[k][V - 1] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = from; k < from + 4; ++k) dst[k][0] = __ldg(p + k * Xs);
         }
     };
     auto load_s = [&](float (&dst)[kG][V], const float *__restrict__ p) {
@@ -551,11 +548,11 @@ __device__ __forceinline__ void tap_pass32(const float *__restrict__ qp, const f
 #pragma unroll 1
     for (int g = 0; g < groups; g += 2) {
         load_s(sb, sp + kG * Xs);
-        group(qa, qb, sa, qp + kG * Xs);   // qb <- template values of group g + 1
+        group(qa, qb, sa, qp + kG * V);   // qb <- template values of group g + 1
         if (g + 1 >= groups) break;
         load_s(sa, sp + 2 * kG * Xs);
-        group(qb, qa, sb, qp + 2 * kG * Xs);  // qa <- template values of group g + 2
-        qp += 2 * kG * Xs;
+        group(qb, qa, sb, qp + 2 * kG * V);  // qa <- template values of group g + 2
+        qp += 2 * kG * V;
         sp += 2 * kG * Xs;
     }
 }
@@ -563,8 +560,8 @@ __device__ __forceinline__ void tap_pass32(const float *__restrict__ qp, const f
 // The fp32 correlation B[r] = sum_j q_j (w d)_{i0 + r X + j} of one block of kBlock candidates of width record wr.
 // With the stride X the taps split into residue classes j = X a + b; odd strides run one pass per class (neighbouring
 // lanes sit kBlock*X floats apart: odd, so the 32 banks are conflict free), even strides one pass per PAIR of classes
-// with 8-byte loads (candidates start at multiples of X, so the pairs are aligned, and lanes sit kBlock*X/2 eight-byte
-// units apart: odd again).  Every lane of a warp walks the classes in the same order: template loads are broadcasts.
+// with 8-byte sample loads (candidates start at multiples of X, so the pairs are aligned).  Every lane of a warp
+// walks the classes in the same order: template loads are broadcasts.
 template <int kBlock, bool kUnit>
 __device__ __forceinline__ void tap_block32(const WidthRec &wr, const float *__restrict__ tq32,
                                             const float *__restrict__ wd32, int c0, float (&B)[kBlock])
@@ -573,15 +570,15 @@ __device__ __forceinline__ void tap_block32(const WidthRec &wr, const float *__r
     const int L = wr.L, X = kUnit ? 1 : wr.X;
 #pragma unroll
     for (int r = 0; r < kBlock; ++r) B[r] = 0.f;
-    const float *__restrict__ qp = tq32 + wr.q;
+    const float *__restrict__ qp = tq32 + wr.q32;
     const float *__restrict__ sp = wd32 + c0 * X;
     const int groups = ((L + X - 1) / X + kBlock - 1 + kG - 1) / kG;  // steps: taps of the widest class + kBlock - 1
     if (kUnit) {
         tap_pass32<kBlock, 1, true>(qp, sp, 1, groups, B);
     } else if ((X & 1) == 0) {
-        for (int b = 0; b < X && b < L; b += 2) tap_pass32<kBlock, 2, false>(qp + b, sp + b, X, groups, B);
+        for (int b = 0; b < X && b < L; b += 2) tap_pass32<kBlock, 2, false>(qp + b * wr.astride, sp + b, X, groups, B);
     } else {
-        for (int b = 0; b < X && b < L; ++b) tap_pass32<kBlock, 1, false>(qp + b, sp + b, X, groups, B);
+        for (int b = 0; b < X && b < L; ++b) tap_pass32<kBlock, 1, false>(qp + b * wr.astride, sp + b, X, groups, B);
     }
 }
 

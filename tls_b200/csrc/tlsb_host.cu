@@ -782,7 +782,24 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     int rc;
     if (h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));  // an earlier asynchronous upload may still read h_tq
     h->h_tq.swap(tq);  // stays alive behind the asynchronous upload
-    h->h_tq32.assign(h->h_tq.begin(), h->h_tq.end());
+    // the filter pass's copy: fp32, residue-class major (tlsb_internal.h: tq32_class_stride)
+    h->h_tq32.clear();
+    for (int u = 0; u < nU; ++u) {
+        WidthRec &wr = recs[u];
+        const int X = wr.X, L = wr.L, A = tq32_class_stride(L, X);
+        wr.q32 = (int)h->h_tq32.size();
+        wr.astride = A;
+        const double *q = h->h_tq.data() + wr.q;
+        const int n_units = (X & 1) ? X : X / 2, V = (X & 1) ? 1 : 2;
+        h->h_tq32.resize(h->h_tq32.size() + (size_t)n_units * V * A, 0.f);
+        float *dst = h->h_tq32.data() + wr.q32;
+        for (int c = 0; c < n_units; ++c)
+            for (int a = 0; a < A; ++a)
+                for (int v = 0; v < V; ++v) {
+                    const long long j = (long long)X * a + (long long)V * c + v;
+                    dst[((size_t)c * A + a) * V + v] = j < L ? (float)q[j] : 0.f;
+                }
+    }
     if ((rc = upload(h->tq, h->h_tq.data(), h->h_tq.size() * 8, h->up_stream))) return rc;
     if ((rc = upload(h->tq32, h->h_tq32.data(), h->h_tq32.size() * 4, h->up_stream))) return rc;
     if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));

@@ -46,8 +46,8 @@ int spectra_device(const double *chi2, int64_t P, int64_t n_curves, int64_t win,
 constexpr int kBlockMax = 7;          // host-side slack (template padding, array slack) is sized for the largest R
 constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per queue reservation
 __host__ __device__ constexpr int tile_size(int kb) { return 32 * kb * kSub; }  // candidates one warp gates at a time
-constexpr int kPadGroups = 4;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kGroup32 = 8;           // steps per unrolled group of the fp32 tap loop (template values arrive as two float4)
+constexpr int kPadGroups = 4;         // slack (in groups of kBlock steps) behind templates and patched arrays
 constexpr int kScanItems = 5;         // items per thread per scan tile (odd: conflict-free in smem)
 constexpr int kResScanItems = 19;     // ... of the resident kernel: one tile covers 19 * 256 = 4864 samples (cfg-1: one tile, 3 barriers)
 #ifndef TLSB_RES_HSCAN
@@ -86,7 +86,19 @@ struct WidthRec {
     double invW;  // 1 / W
     double sq2;   // sum_j q_j^2 (the quadratic term when all weights are equal)
     double eb;    // fp32 filter pass: |B32 - B64| <= eb * max|w d|, eb = (L + 8) * 2^-24 * sum_j |q_j| (rounded up)
+    int q32;      // offset of the template in tq32 (fp32, residue-class major: see class_stride)
+    int astride;  // floats per residue class in tq32 (zero padded, a multiple of 4)
 };
+
+// tq32 layout (the filter pass's templates).  Stride X splits the taps into residue classes j = X a + b.  Odd X:
+// class b occupies floats [q32 + b * astride, +astride) holding q[X a + b] for a = 0, 1, ...  Even X: the PAIR of
+// classes (2 c, 2 c + 1) occupies [q32 + c * 2 * astride, + 2 * astride) as interleaved float2 (q[X a + 2c],
+// q[X a + 2c + 1]).  Zero padded behind the last tap; class starts are 16-byte aligned, so every lane of a warp
+// fetches the template values of 8 (or 4 x 2) consecutive steps with float4 loads of the same address (broadcast).
+__host__ __device__ inline int tq32_class_stride(int L, int X)
+{
+    return (((L + X - 1) / X + (kBlockMax - 1) + 2 * kGroup32 + 1) + 3) & ~3;
+}
 
 struct PlanArgs {
     const double *periods;
