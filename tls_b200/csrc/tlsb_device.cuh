@@ -576,7 +576,17 @@ __device__ __forceinline__ void tap_block32(const WidthRec &wr, const float *__r
     if (kUnit) {
         tap_pass32<kBlock, 1, true>(qp, sp, 1, groups, B);
     } else if ((X & 1) == 0) {
-        for (int b = 0; b < X && b < L; b += 2) tap_pass32<kBlock, 2, false>(qp + b * wr.astride, sp + b, X, groups, B);
+        // Neighbouring lanes sit kBlock * X / 2 eight-byte units apart: conflict free on the 16 eight-byte banks of a
+        // half-warp when X / 2 is odd.  When X / 2 = 2^e * odd, lanes 16 / g blocks apart (g = min(2^e, 16)) share a
+        // bank; they start at DIFFERENT pair classes (one class = one unit further), rotated by the block index, so
+        // the half-warp is conflict free again and the template loads touch g addresses instead of one.
+        const int npc = X / 2;
+        const int g = min(npc & -npc, 16);
+        int pc = ((c0 / kBlock) / (16 / g)) & (g - 1);
+        for (int t = 0; t < npc && 2 * t < L; ++t) {
+            tap_pass32<kBlock, 2, false>(qp + 2 * pc * wr.astride, sp + 2 * pc, X, groups, B);
+            if (++pc == npc) pc = 0;
+        }
     } else {
         for (int b = 0; b < X && b < L; ++b) tap_pass32<kBlock, 1, false>(qp + b * wr.astride, sp + b, X, groups, B);
     }
