@@ -229,10 +229,13 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
 // With begin > 0 the pass resumes at position `begin` with the running sum `carry` (the samples
 // there already hold their d; nothing is wrapped).
 // kWd64 / kWd32: write the products w*d in fp64 (wd) and / or rounded to fp32 (wd32, the filter pass's samples).
-template <int kT, bool kUniformW, int kScanItems = tlsb::kScanItems, bool kWd64 = true, bool kWd32 = false>
+// kCs32: also write the DETRENDED cumulative sums rounded to fp32, cs32_1[e] = fl32(cs1[e] - (e + 1) mu) (cs32_1 = cs32 + 1:
+// the fp32 gate and screen read these, tlsb_device.cuh "fp32 gate"), and return the largest |cs32| written in *cmax32.
+template <int kT, bool kUniformW, int kScanItems = tlsb::kScanItems, bool kWd64 = true, bool kWd32 = false, bool kCs32 = false>
 __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, double *wd, double w0, int N, int NM,
                                                    int NMP, double *warp_tot /* [kT/32 + 1] shared */,
-                                                   int begin = 0, double carry = 0.0, float *wd32 = nullptr)
+                                                   int begin = 0, double carry = 0.0, float *wd32 = nullptr,
+                                                   float *cs32_1 = nullptr, double mu = 0.0, float *cmax32 = nullptr)
 {
     constexpr int kW = kT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -250,6 +253,7 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
     }
     __syncthreads();
     double tpart = 0.0;
+    float cmax = 0.f;
     for (int base = begin; base < NM; base += kT * kScanItems) {
         const int first = base + tid * kScanItems;
         double v[kScanItems];
@@ -300,10 +304,19 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
         const double offset = carry + warp_tot[wid] + excl;
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k)
-            if (first + k < NM) cs1[first + k] = v[k] + offset;
+            if (first + k < NM) {
+                const double c = v[k] + offset;
+                cs1[first + k] = c;
+                if (kCs32) {
+                    const float c32 = (float)fma(-(double)(first + k + 1), mu, c);
+                    cs32_1[first + k] = c32;
+                    cmax = fmaxf(cmax, fabsf(c32));
+                }
+            }
         carry += warp_tot[kW];
         __syncthreads();
     }
+    if (kCs32) *cmax32 = cmax;
     return tpart;
 }
 
@@ -431,6 +444,59 @@ __device__ __forceinline__ int gate_block(const double *cs, int c0, int c_end, i
             if (c < c_end) {
                 const int i = c * Xs;
                 if ((cs[i + W] - cs[i]) * invW > depth_min) mask |= 1 << rr;
+            }
+        }
+    }
+    return mask;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 gate (equal-weights paths).  The gate of core.py:58 is mean_i = (cs[i+W] - cs[i]) / W > transit_depth_min, two
+// 8-byte shared-memory reads and three fp64 operations per candidate - for EVERY offset of every admissible width,
+// most of which fail on quiet data.  The filter paths therefore keep the cumulative sums as DETRENDED fp32 values,
+// cs32[k] = fl32(cs[k] - k mu) (mu = the light curve's mean of d: without it cs would grow linearly for flux that is not
+// normalised to 1 and fp32 would resolve nothing), and test diff32 = cs32[i+W] - cs32[i] against a threshold lowered by
+// a rigorous bound on |diff32 - ((cs[i+W] - cs[i]) - W mu)|:
+//     2^-24 (|cs32[i+W]| + |cs32[i]|) (rounding cs to fp32) + 2^-24 |diff32| (the subtraction) <= 2^-22 Cmax,
+//     plus the fp64 roundings of cs[k] - k mu (<= 2^-52 (Cmax + NM |mu|)),     Cmax = max_k |cs32[k]| of this period.
+// Every candidate the exact gate passes also passes this one (a SUPERSET; NaN passes); the exact fp64 gate is applied
+// where it matters, in bound_one, before a candidate can lower the threshold or become a finalist.  Half the
+// shared-memory bytes, one FADD + one FSETP instead of DADD + DMUL + DSETP per candidate.
+struct Gate32 {
+    double mu;         // detrending slope
+    double err;        // bound on |diff32 - (diff64 - W mu)| for this period
+    double depth_min;  // core.py:58
+    __device__ __forceinline__ void set_err(float cmax, int NM)
+    {
+        err = 2.5e-7 * (double)cmax + 1e-13 * ((double)cmax + (double)NM * fabs(mu));
+    }
+    // a candidate passes iff !(diff32 <= thr(W))
+    __device__ __forceinline__ float thr(int W) const
+    {
+        const double w = (double)W;
+        return __double2float_rd(w * (depth_min - mu) - err - 1e-13 * (fabs(w * depth_min) + fabs(w * mu)));
+    }
+};
+
+template <int kBlock, bool kUnit>
+__device__ __forceinline__ int gate_block32(const float *cs32, int c0, int c_end, int W, int X, float thr)
+{
+    const int Xs = kUnit ? 1 : X;
+    int mask = 0;
+    if (c0 + kBlock <= c_end) {  // straight line: all loads in flight, then the compares
+        const float *__restrict__ lo = cs32 + (size_t)c0 * Xs;
+        const float *__restrict__ hi = lo + W;
+        float diff[kBlock];
+#pragma unroll
+        for (int rr = 0; rr < kBlock; ++rr) diff[rr] = hi[rr * Xs] - lo[rr * Xs];
+#pragma unroll
+        for (int rr = 0; rr < kBlock; ++rr) mask |= (diff[rr] <= thr ? 0 : 1) << rr;
+    } else {  // the last, partial block of this width (or nothing)
+        for (int rr = 0; rr < kBlock; ++rr) {
+            const int c = c0 + rr;
+            if (c < c_end) {
+                const int i = c * Xs;
+                if (!(cs32[i + W] - cs32[i] <= thr)) mask |= 1 << rr;
             }
         }
     }
@@ -633,7 +699,7 @@ __device__ __noinline__ void eval_exact_warp(const ExactView<kGather> &v, const 
     for (int j = lane; j < L; j += 32) B = fma(__ldg(q + j), v.wdv(i + j), B);
 #pragma unroll
     for (int off = 16; off; off >>= 1) B += __shfl_xor_sync(kFull, B, off);
-    const double mean = (v.cs[i + wr.W] - v.cs[i]) * wr.invW;
+    const double mean = (__ldcg(v.cs + i + wr.W) - __ldcg(v.cs + i)) * wr.invW;  // global memory, written by this CTA
     const double D = mean * wr.os;
     double chi = chi2_value(v.T, D, v.w0 * wr.sq2, B);
     if (L < wr.W) {  // samples L..W-1 are in neither sum
@@ -673,33 +739,36 @@ struct Threshold {
 };
 
 // After tap_block32, cheap screen in fp32.  chi2 = T - R with the reduction R = D (2 B - D Aq); a candidate can only
-// matter if R + (error bounds) >= G = T - U.  R is evaluated in fp32 from D rounded to fp32: against the exact
-// R(B32) that costs less than 16 u relative to the magnitude of its terms (D: 3 roundings, Aq: 1, three
-// operations), covered by 2e-6 |D| (2 |B| + |D| Aq); 2 |D| EB bounds |R(B32) - R(B64)| (see tap_block32) and slopT the
-// fp64 evaluation roundings.  Returns the candidates that are NOT ruled out (they get exact fp64 bounds next).  NaN
-// anywhere fails safe.  diff[] returns the window sums cs[i+W] - cs[i].
+// matter if R + (error bounds) >= G = T - U.  R is evaluated in fp32 from D = (diff32 + W mu) c1, c1 = fl32(os / W):
+// against the exact R(B32) the roundings cost less than 16 u relative to the magnitude of its terms (D: 3 roundings,
+// Aq: 1, three operations), covered by 2e-6 |D| (2 |B| + |D| Aq); the ABSOLUTE error of diff32 + W mu (Gate32::err plus
+// the rounding of W mu) moves D by at most dD and R by at most dD (2 |B| + 2 |D| Aq + dD Aq); 2 |D| EB bounds
+// |R(B32) - R(B64)| (see tap_block32) and slopT the fp64 evaluation roundings.  Returns the candidates that are NOT
+// ruled out (they get exact fp64 bounds next).  NaN anywhere fails safe.
 template <int kBlock, bool kUnit>
-__device__ __forceinline__ int block_screen(const WidthRec &wr, const double *cs, double w0, int c0, int mask,
-                                            const float (&B)[kBlock], float G32, float EB2f, float slopTf,
-                                            double (&diff)[kBlock])
+__device__ __forceinline__ int block_screen(const WidthRec &wr, const float *cs32, double w0, int c0, int mask,
+                                            const float (&B)[kBlock], float G32, float EB2f, float slopTf, float Wmu32,
+                                            float dD)
 {
-    double lo[kBlock], hi[kBlock];
+    float lo[kBlock], hi[kBlock];
     const int X = kUnit ? 1 : wr.X;
-    const double *__restrict__ p = cs + c0 * X;
-    const double *__restrict__ ph = p + wr.W;
+    const float *__restrict__ p = cs32 + c0 * X;
+    const float *__restrict__ ph = p + wr.W;
 #pragma unroll
     for (int rr = 0; rr < kBlock; ++rr) {
         lo[rr] = p[rr * X];
         hi[rr] = ph[rr * X];
     }
     const float c1 = (float)(wr.invW * wr.os), Aq32 = (float)(w0 * wr.sq2);
+    const float dDA = dD * Aq32;
     int keep = 0;
 #pragma unroll
     for (int rr = 0; rr < kBlock; ++rr) {
-        diff[rr] = hi[rr] - lo[rr];
-        const float Df = (float)diff[rr] * c1, aD = fabsf(Df);
+        const float Df = ((hi[rr] - lo[rr]) + Wmu32) * c1, aD = fabsf(Df);
         const float R = Df * fmaf(-Df, Aq32, 2.f * B[rr]);
-        const float m = fmaf(aD * fmaf(aD, Aq32, 2.f * fabsf(B[rr])), 2e-6f, fmaf(aD, EB2f, slopTf));
+        const float t = fmaf(aD, Aq32, 2.f * fabsf(B[rr]));  // |D| Aq + 2 |B|
+        float m = fmaf(aD * t, 2e-6f, fmaf(aD, EB2f, slopTf));
+        m = fmaf(dD, fmaf(aD, Aq32, t) + dDA, m);  // dD (2 |B| + 2 |D| Aq + dD Aq)
         keep |= (R + m < G32 ? 0 : 1) << rr;
     }
     if (wr.L < wr.W) keep = -1;  // the untouched tail adds to R: no screen for trimmed templates (rare)
@@ -707,13 +776,19 @@ __device__ __forceinline__ int block_screen(const WidthRec &wr, const double *cs
 }
 
 // Exact fp64 bounds of ONE candidate the screen did not rule out (rare: kept out of line, scalars only, so that the
-// hot loop keeps its registers and its instruction-cache footprint): returns the lower bound of chi2 rounded down
-// to fp32 and lowers the CTA-wide threshold to the upper bound if that is smaller.
-//   diff = cs[i+W] - cs[i], B = the fp32 correlation, EB = the bound on |B32 - B64|;
+// hot loop keeps its registers and its instruction-cache footprint).  First the EXACT gate of core.py:58 on the fp64
+// cumulative sums (the fp32 gate let a superset through): a candidate that fails it returns +inf and touches nothing.
+// Otherwise returns the lower bound of chi2 rounded down to fp32 and lowers the CTA-wide threshold to the upper bound
+// if that is smaller.
+//   cs64 = the fp64 cumulative sums (global memory, written by this CTA before the last barrier), i = window start,
+//   B = the fp32 correlation, EB = the bound on |B32 - B64|;
 //   n_tail > 0: the template was trimmed (L < W) and wd32 + k_tail are the n_tail window samples it does not cover.
-__device__ __noinline__ float bound_one(double diff, float B, double invW, double os, double Aq, double EB, double T,
-                                        double w0, const float *wd32, int k_tail, int n_tail, FilterShared *fs)
+__device__ __noinline__ float bound_one(const double *cs64, int i, int W, double depth_min, float B, double invW, double os,
+                                        double Aq, double EB, double T, double w0, const float *wd32, int k_tail, int n_tail,
+                                        FilterShared *fs)
 {
+    const double diff = __ldcg(cs64 + i + W) - __ldcg(cs64 + i);
+    if (!(diff * invW > depth_min)) return INFINITY;  // helpers.py:70-73 + core.py:58, as gate_block evaluates it
     const double D = diff * invW * os;
     const double Bd = (double)B;
     const double chi = chi2_value(T, D, Aq, Bd);
@@ -741,6 +816,7 @@ struct FilterCtx {
     float *fq_lo;
     int fq_cap;
     unsigned long long *stats;
+    Gate32 g32;  // the fp32 gate's parameters of this period (mu, err, depth_min)
 };
 
 // Finalists of one batch (bit rr of `fin`, lower bounds rounded down to fp32) go to the finalist queue once more
@@ -821,10 +897,10 @@ struct Pending {
     }
 };
 
-// One batch of survivor blocks (one per lane, `have`): fp32 correlation, fp32 screen, exact bounds for what the
-// screen lets through; then the PREVIOUS batch's finalists are pushed and this batch's become pending.
+// One batch of survivor blocks (one per lane, `have`): fp32 correlation, fp32 screen, exact gate + exact bounds for
+// what the screen lets through; then the PREVIOUS batch's finalists are pushed and this batch's become pending.
 template <int kBlock, bool kGather>
-__device__ __forceinline__ void tap_batch(bool have, int2 e, const FilterCtx<kGather> &cx, const double *cs, const float *wd32,
+__device__ __forceinline__ void tap_batch(bool have, int2 e, const FilterCtx<kGather> &cx, const float *cs32, const float *wd32,
                                           const float *__restrict__ tq32, double w0, double T, double eb_scale, float slopTf,
                                           Threshold &th, Pending<kBlock> &pend, Best &best)
 {
@@ -837,24 +913,27 @@ __device__ __forceinline__ void tap_batch(bool have, int2 e, const FilterCtx<kGa
         const WidthRec wr = cx.rec[u];
         const double EB = wr.eb * eb_scale;
         const float EB2f = __double2float_ru(2.000001 * EB);
+        // the screen's D comes from diff32 + W mu: absolute error of that sum (Gate32::err + the rounding of W mu), as an error of D
+        const double wmu = (double)wr.W * cx.g32.mu;
+        const float Wmu32 = (float)wmu;
+        const float dD = __double2float_ru((cx.g32.err + 6.1e-8 * fabs(wmu)) * (wr.invW * wr.os) * 1.00001);
         float B[kBlock];
-        double diff[kBlock];
         th.refresh(cx.fs, T);
         int keep;
         if (wr.X == 1) {
             tap_block32<kBlock, true>(wr, tq32, wd32, e.x, B);
-            keep = block_screen<kBlock, true>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+            keep = block_screen<kBlock, true>(wr, cs32, w0, e.x, mask, B, th.G32, EB2f, slopTf, Wmu32, dD);
         } else {
             tap_block32<kBlock, false>(wr, tq32, wd32, e.x, B);
-            keep = block_screen<kBlock, false>(wr, cs, w0, e.x, mask, B, th.G32, EB2f, slopTf, diff);
+            keep = block_screen<kBlock, false>(wr, cs32, w0, e.x, mask, B, th.G32, EB2f, slopTf, Wmu32, dD);
         }
         if (keep) {  // rare
             const double Aq = w0 * wr.sq2;
 #pragma unroll
             for (int rr = 0; rr < kBlock; ++rr)
                 if ((keep >> rr) & 1)
-                    lo_now[rr] = bound_one(diff[rr], B[rr], wr.invW, wr.os, Aq, EB, T, w0, wd32, (e.x + rr) * wr.X + wr.L,
-                                           wr.W - wr.L, cx.fs);
+                    lo_now[rr] = bound_one(cx.view.cs, (e.x + rr) * wr.X, wr.W, cx.g32.depth_min, B[rr], wr.invW, wr.os, Aq, EB, T,
+                                           w0, wd32, (e.x + rr) * wr.X + wr.L, wr.W - wr.L, cx.fs);
             th.refresh(cx.fs, T);
 #pragma unroll
             for (int rr = 0; rr < kBlock; ++rr) fin |= (((keep >> rr) & 1) && !((double)lo_now[rr] > th.U) ? 1 : 0) << rr;
@@ -890,9 +969,9 @@ struct SweepShared {
 // (contains barriers: all threads of the CTA must call).  cs / wd32 must be indexable by global offsets.
 template <int kT, int kBlock, bool kGather>
 __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int qmask, int tile_end, int ub, const int *t_lo,
-                                             const int *t_hi, const int *t_tiles, const WidthRec *rec, const double *cs,
+                                             const int *t_hi, const int *t_tiles, const WidthRec *rec, const float *cs32,
                                              const float *wd32, const float *__restrict__ tq32, double w0, double T,
-                                             double depth_min, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo,
+                                             const Gate32 &g32, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo,
                                              int fq_cap, const ExactView<kGather> &view, Best &best,
                                              unsigned long long *stats)
 {
@@ -902,7 +981,7 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
     const unsigned lt_mask = (1u << lane) - 1u;
     const int qroom = qmask + 1 - kW * 32 * kSub;  // gating pauses above this fill: every warp can still add one tile
     FilterCtx<kGather> cx;
-    cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats;
+    cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats; cx.g32 = g32;
     Threshold th;
     th.set(INFINITY, T);
     th.refresh(fs, T);
@@ -949,7 +1028,7 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
             }
             __syncwarp();
             if (lane == 0) atomicAdd(&ss->q_done, n);
-            tap_batch<kBlock, kGather>(have, e, cx, cs, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
+            tap_batch<kBlock, kGather>(have, e, cx, cs32, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
             continue;
         }
         if (do_gate) {
@@ -966,7 +1045,7 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
             }
             const int u = cur_u;
             const int W = rec[u].W, X = rec[u].X, c_end = t_hi[u];
-            const double invW = rec[u].invW;
+            const float thr = g32.thr(W);
             const int c_tile = t_lo[u] + (g - u_begin) * kTile + lane * kBlock;
             int masks[kSub];
             unsigned votes[kSub];
@@ -974,11 +1053,11 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
             if (X == 1) {
 #pragma unroll
                 for (int sb = 0; sb < kSub; ++sb)
-                    masks[sb] = gate_block<kBlock, true>(cs, c_tile + sb * 32 * kBlock, c_end, W, 1, invW, depth_min);
+                    masks[sb] = gate_block32<kBlock, true>(cs32, c_tile + sb * 32 * kBlock, c_end, W, 1, thr);
             } else {
 #pragma unroll
                 for (int sb = 0; sb < kSub; ++sb)
-                    masks[sb] = gate_block<kBlock, false>(cs, c_tile + sb * 32 * kBlock, c_end, W, X, invW, depth_min);
+                    masks[sb] = gate_block32<kBlock, false>(cs32, c_tile + sb * 32 * kBlock, c_end, W, X, thr);
             }
 #pragma unroll
             for (int sb = 0; sb < kSub; ++sb) {
@@ -1017,14 +1096,14 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
 // waits, and short batches make the ring's bookkeeping the larger cost): one ROUND of the survivor queue, filled by
 // the gate before a barrier; warps take batches of 32 entries until the queue is empty, then drain the finalists.
 template <int kT, int kBlock, bool kGather>
-__device__ __forceinline__ void filter_round(const int2 *queue, int qfill, int *q_head, const WidthRec *rec, const double *cs,
+__device__ __forceinline__ void filter_round(const int2 *queue, int qfill, int *q_head, const WidthRec *rec, const float *cs32,
                                              const float *wd32, const float *__restrict__ tq32, double w0, double T,
-                                             double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo, int fq_cap,
-                                             const ExactView<kGather> &view, Best &best, unsigned long long *stats)
+                                             const Gate32 &g32, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo,
+                                             int fq_cap, const ExactView<kGather> &view, Best &best, unsigned long long *stats)
 {
     const int lane = threadIdx.x & 31;
     FilterCtx<kGather> cx;
-    cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats;
+    cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats; cx.g32 = g32;
     Threshold th;
     th.set(INFINITY, T);
     th.refresh(fs, T);
@@ -1038,7 +1117,7 @@ __device__ __forceinline__ void filter_round(const int2 *queue, int qfill, int *
         if (h >= qfill) break;
         const bool have = h + lane < qfill;
         const int2 e = have ? queue[h + lane] : make_int2(0, 0);
-        tap_batch<kBlock, kGather>(have, e, cx, cs, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
+        tap_batch<kBlock, kGather>(have, e, cx, cs32, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
     }
     pend.push(cx, best);
     __syncthreads();  // every finalist of this round is in the queue
@@ -1061,6 +1140,26 @@ __device__ double block_max_abs(const double *__restrict__ x, int n, double *scr
     for (int k = 0; k < kT / 32; ++k) r = fmax(r, scratch[k]);
     __syncthreads();
     return r;
+}
+
+// mean of x_k over k < n, the same value in every thread (all threads must call; scratch: kT/32 doubles, shared).  Only used
+// as the detrending slope of the fp32 cumulative sums: any value is CORRECT there, a good one keeps them small.
+template <int kT>
+__device__ double block_mean(const double *__restrict__ x, int n, double *scratch)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double m = 0.0;
+    for (int k = tid; k < n; k += kT) m += __ldg(x + k);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) m += __shfl_xor_sync(kFull, m, off);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = m;
+    __syncthreads();
+    double r = 0.0;
+    for (int k = 0; k < kT / 32; ++k) r += scratch[k];
+    __syncthreads();
+    r /= (double)n;
+    return (r == r && fabs(r) < 1e300) ? r : 0.0;  // NaN / inf in the data: no detrending
 }
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }

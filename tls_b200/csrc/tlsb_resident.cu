@@ -22,9 +22,11 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     // w    : NMP doubles      weights (not kept when all weights are equal)
     // wd   : NMP doubles      w*d                                   [the sorted d before that]
     // queue: qcap int2        survivor blocks                       [resident: H + sid while sorting]
-    // kFilter (resident, equal weights): cs | sorted sample ids (u16) | tail | area, where the area holds the sort's
-    // keys, histogram and bucket-ordered ids first and then wd32 (the products w*d rounded to fp32), the survivor
-    // queue and the finalist queue.
+    // kFilter (resident, equal weights): X | sorted sample ids (u16) | tail | area.  X holds the sorted d, scanned in place
+    // into the fp64 cumulative sums, which are then copied to this CTA's global scratch (only the rare exact evaluations
+    // read them, from L2) - after that X is the survivor queue.  The area holds the sort's keys, histogram and
+    // bucket-ordered ids first and then what the search reads: cs32 (detrended cumulative sums in fp32: the gate and the
+    // screen), wd32 (the products w*d rounded to fp32: the taps) and the finalist queue.
     constexpr bool kFilter = kResident && kUniformW;
     const size_t cs_elems = (size_t)(NM + 2) & ~(size_t)1;
     double *cs, *w, *wd;
@@ -32,7 +34,8 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     int *H;
     int2 *queue;
     unsigned char *tail;
-    float *wd32 = nullptr;
+    float *wd32 = nullptr, *cs32 = nullptr;
+    double *cs64g = nullptr;
     idx_t *sid_sorted = nullptr;
     int2 *fq = nullptr;
     float *fq_lo = nullptr;
@@ -40,16 +43,19 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     if (kFilter) {
         cs = reinterpret_cast<double *>(smem_raw);
         w = wd = nullptr;
-        sid_sorted = reinterpret_cast<idx_t *>(cs + cs_elems);
+        queue = reinterpret_cast<int2 *>(smem_raw);
+        const size_t xbytes = ((cs_elems > (size_t)a.qcap ? cs_elems : (size_t)a.qcap) * 8 + 15) & ~(size_t)15;
+        sid_sorted = reinterpret_cast<idx_t *>(smem_raw + xbytes);
         tail = reinterpret_cast<unsigned char *>(sid_sorted) + (((size_t)N * sizeof(idx_t) + 15) & ~(size_t)15);
         unsigned char *area = tail + filter_tail_bytes(nU, kT);
         skey = reinterpret_cast<double *>(area);
         H = reinterpret_cast<int *>(skey + N);
         sid = reinterpret_cast<idx_t *>(H + NB + 1);
-        wd32 = reinterpret_cast<float *>(area);
-        queue = reinterpret_cast<int2 *>(wd32 + (((size_t)NMP + 3) & ~(size_t)3));
-        fq = queue + a.qcap;
+        cs32 = reinterpret_cast<float *>(area);
+        wd32 = cs32 + (((size_t)NM + 2 + 3) & ~(size_t)3);
+        fq = reinterpret_cast<int2 *>(wd32 + (((size_t)NMP + 3) & ~(size_t)3));
         fq_lo = reinterpret_cast<float *>(fq + a.fq_cap);
+        cs64g = reinterpret_cast<double *>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta);
     } else if (kResident) {
         cs = reinterpret_cast<double *>(smem_raw);
         w = cs + cs_elems;
@@ -94,7 +100,12 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     const int qstop = a.qcap - kW * 32 * kSub;  // gating pauses here: every warp can still add one tile
     // filter pass: scale of the error bound = max |w d| over the light curve (period independent)
     double eb_scale = 0.0;
-    if (kFilter) eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
+    Gate32 g32;
+    g32.mu = 0.0; g32.err = 0.0; g32.depth_min = depth_min;
+    if (kFilter) {
+        eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
+        g32.mu = block_mean<kT>(a.dval, N, red_d);
+    }
 
     for (;;) {
         if (tid == 0) {
@@ -131,16 +142,31 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w, reinterpret_cast<int *>(red_d), sid_sorted);
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
-        if (kFilter && kT > 256)  // the survivor ring shares its memory with the sort: a slot is valid when it is non-zero
-            for (int k = tid; k < a.qcap; k += kT) reinterpret_cast<unsigned long long *>(queue)[k] = 0ull;
-        double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems), !kFilter, kFilter>(
-            cs + 1, w, wd, a.w0, N, NM, NMP, red_d, 0, 0.0, wd32);
+        float cmax = 0.f;
+        if (kFilter && tid == 0) cs32[0] = 0.f;
+        double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems), !kFilter, kFilter, kFilter>(
+            cs + 1, w, wd, a.w0, N, NM, NMP, red_d, 0, 0.0, wd32, cs32 + 1, g32.mu, &cmax);
+        if (kFilter) {  // the fp64 cumulative sums leave the SM: only bound_one / eval_exact_warp read them again (L2)
+            for (int k = tid; k <= NM; k += kT) __stcg(cs64g + k, cs[k]);
+#pragma unroll
+            for (int off = 16; off; off >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(kFull, cmax, off));
+            if (lane == 0) red_i[wid] = __float_as_int(cmax);
+        }
 #pragma unroll
         for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
         if (lane == 0) red_d[kW + 1 + wid] = tpart;
-        __syncthreads();
+        __syncthreads();  // X (the fp64 cumulative sums) is dead from here on: it becomes the survivor queue
         double T = 0.0;
         for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];  // T = sum w d^2 over the unpatched curve; fixed order
+        if (kFilter) {
+            float cm = 0.f;
+            for (int k = 0; k < kW; ++k) cm = fmaxf(cm, __int_as_float(red_i[k]));
+            g32.set_err(cm, NM);
+            if (kT > 256) {  // the survivor ring: a slot is valid when it is non-zero (a barrier follows inside the sweep set-up)
+                for (int k = tid; k < a.qcap; k += kT) reinterpret_cast<unsigned long long *>(queue)[k] = 0ull;
+                __syncthreads();
+            }
+        }
 
         // ---- B. gate + survivor compaction + tap loop ----------------------------------------
         // B1: warp `wid` gates tiles wid, wid+kW, ... of the sweep (wide widths first) from two
@@ -159,15 +185,15 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         constexpr bool kDynamic = kFilter && kT > 256;  // one big CTA per SM: nothing else would fill a barrier wait
         ExactView<true> view;
         if (kFilter) {
-            view.cs = cs; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
+            view.cs = cs64g; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
             view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
         }
         if constexpr (kDynamic) {
             // B1 + B2 as one barrier-free sweep: warps switch between gating tiles and taking batches of survivors
             // (fp32 correlation, screen, bounds); finalists are evaluated in fp64 by whole warps at the end
             const int tile_total = rec[ulo].cum + rec[ulo].tiles - rec[uhi - 1].cum;
-            sweep_filter<kT, kBlock, true>(ss, queue, a.qcap - 1, tile_total, uhi, t_lo, t_hi, t_tiles, rec, cs, wd32, a.tq32, a.w0, T,
-                                           depth_min, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
+            sweep_filter<kT, kBlock, true>(ss, queue, a.qcap - 1, tile_total, uhi, t_lo, t_hi, t_tiles, rec, cs32, wd32, a.tq32, a.w0, T,
+                                           g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
         } else {
             const int tile_end = rec[ulo].cum + rec[ulo].tiles;
             int g_next = rec[uhi - 1].cum + wid;
@@ -188,19 +214,32 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
                     }
                     const int u = cur_u;
                     const int W = rec[u].W, X = rec[u].X, ncand = rec[u].ncand;
-                    const double invW = rec[u].invW;
                     const int c_tile = (g - u_begin) * kTile + lane * kBlock;
                     int masks[kSub];
                     unsigned votes[kSub];
                     int total = 0;
-                    if (X == 1) {
+                    if constexpr (kFilter) {  // fp32 gate on the detrended cumulative sums: a superset (bound_one settles it)
+                        const float thr = g32.thr(W);
+                        if (X == 1) {
     #pragma unroll
-                        for (int sb = 0; sb < kSub; ++sb)
-                            masks[sb] = gate_block<kBlock, true>(cs, c_tile + sb * 32 * kBlock, ncand, W, 1, invW, depth_min);
+                            for (int sb = 0; sb < kSub; ++sb)
+                                masks[sb] = gate_block32<kBlock, true>(cs32, c_tile + sb * 32 * kBlock, ncand, W, 1, thr);
+                        } else {
+    #pragma unroll
+                            for (int sb = 0; sb < kSub; ++sb)
+                                masks[sb] = gate_block32<kBlock, false>(cs32, c_tile + sb * 32 * kBlock, ncand, W, X, thr);
+                        }
                     } else {
+                        const double invW = rec[u].invW;
+                        if (X == 1) {
     #pragma unroll
-                        for (int sb = 0; sb < kSub; ++sb)
-                            masks[sb] = gate_block<kBlock, false>(cs, c_tile + sb * 32 * kBlock, ncand, W, X, invW, depth_min);
+                            for (int sb = 0; sb < kSub; ++sb)
+                                masks[sb] = gate_block<kBlock, true>(cs, c_tile + sb * 32 * kBlock, ncand, W, 1, invW, depth_min);
+                        } else {
+    #pragma unroll
+                            for (int sb = 0; sb < kSub; ++sb)
+                                masks[sb] = gate_block<kBlock, false>(cs, c_tile + sb * 32 * kBlock, ncand, W, X, invW, depth_min);
+                        }
                     }
     #pragma unroll
                     for (int sb = 0; sb < kSub; ++sb) {
@@ -226,8 +265,8 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
                 const bool more = s_next[1] != 0;
                 // B2
                 if constexpr (kFilter) {
-                    filter_round<kT, kBlock, true>(queue, qfill, &s_next[3], rec, cs, wd32, a.tq32, a.w0, T, eb_scale, fs, fq, fq_lo,
-                                                   a.fq_cap, view, best, a.stats);
+                    filter_round<kT, kBlock, true>(queue, qfill, &s_next[3], rec, cs32, wd32, a.tq32, a.w0, T, g32, eb_scale, fs, fq,
+                                                   fq_lo, a.fq_cap, view, best, a.stats);
                 } else
                 for (;;) {
                     int h = 0;

@@ -26,7 +26,8 @@ namespace {
 template <int kT, bool kUniformW>
 __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsigned char *area, int *cnt,
                                              double *gkey, unsigned *gid, double *cs1, double *w, double *wd, float *wd32,
-                                             int nmp_even, double *red_d, double &tpart_out)
+                                             int nmp_even, double *red_d, double &tpart_out, float *cs32_1, double mu,
+                                             float &cmax_out)
 {
     constexpr int kU = 4;                  // independent chains of the rank / gather loop
     constexpr int kUP = 4;                 // ... of the partition pass
@@ -82,6 +83,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         return fb < 0 ? 0 : (fb < S - 1 ? fb : S - 1);
     };
     double tpart = 0.0, carry = 0.0;
+    float cmax = 0.f;
     int off = 0;
     for (int j = 0; j < ns; ++j) {
         const int nj = cnt[j];
@@ -177,14 +179,25 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         }
         __syncthreads();
         block_inclusive_scan<kT, double, kSegScanItems>(val_s, nj, red_d);
-        for (int q = tid; q < nj; q += kT) cs1[off + q] = carry + val_s[q];
+        for (int q = tid; q < nj; q += kT) {
+            const double c = carry + val_s[q];
+            cs1[off + q] = c;
+            if (kUniformW) {  // the detrended fp32 copy the gate and the screen read (tlsb_device.cuh: fp32 gate)
+                const float c32 = (float)fma(-(double)(off + q + 1), mu, c);
+                cs32_1[off + q] = c32;
+                cmax = fmaxf(cmax, fabsf(c32));
+            }
+        }
         carry += val_s[nj - 1];
         off += nj;
         __syncthreads();
     }
     // positions N .. NM-1 hold the wrapped d: continue the cumulative sum, weight them, zero the slack
-    wrap_weight_scan<kT, kUniformW, kSegScanItems, true, kUniformW>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry, wd32);
+    float cmax2 = 0.f;
+    wrap_weight_scan<kT, kUniformW, kSegScanItems, true, kUniformW, kUniformW>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry, wd32,
+                                                                              cs32_1, mu, &cmax2);
     tpart_out = tpart;
+    cmax_out = fmaxf(cmax, cmax2);
     return true;
 }
 
@@ -208,7 +221,10 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     double *w = cs + cs_elems;
     double *wd = kUniformW ? w : w + nmp_even;
     const size_t nmp4 = ((size_t)NMP + 3) & ~(size_t)3;
-    float *wd32 = reinterpret_cast<float *>(wd + nmp_even);  // equal weights: w*d rounded to fp32 (the filter pass)
+    const size_t cs4 = ((size_t)NM + 2 + 3) & ~(size_t)3;
+    // equal weights: the detrended cumulative sums and the products w*d rounded to fp32 (what the chunks stage)
+    float *cs32 = reinterpret_cast<float *>(wd + nmp_even);
+    float *wd32 = cs32 + cs4;
     unsigned *sid = kUniformW ? reinterpret_cast<unsigned *>(wd32 + nmp4) : reinterpret_cast<unsigned *>(wd + nmp_even);
     double *skey = wd;  // the sort keys borrow the wd area; the sorted d go straight to cs[1..N]
 
@@ -217,10 +233,12 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     int2 *queue = reinterpret_cast<int2 *>(smem_raw);
     int2 *fq = queue + a.qcap;
     float *fq_lo = reinterpret_cast<float *>(fq + a.fq_cap);
+    // equal weights: chunks of cs32 and wd32 (8 bytes per folded sample); else chunks of cs, w, w*d in fp64 (24 bytes)
     double *cs_s = reinterpret_cast<double *>(fq_lo + a.fq_cap);
     double *w_s = cs_s + C;
     double *wd_s = kUniformW ? w_s : w_s + C;
-    float *wd32_s = reinterpret_cast<float *>(cs_s + C);
+    float *cs32_s = reinterpret_cast<float *>(cs_s);
+    float *wd32_s = cs32_s + C;
     int *H = reinterpret_cast<int *>(cs_s);  // phase A only: the histogram borrows the chunk area
     WidthRec *rec = kUniformW ? reinterpret_cast<WidthRec *>(wd32_s + C) : reinterpret_cast<WidthRec *>(wd_s + C);  // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
@@ -251,7 +269,12 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     const double depth_min = a.depth_min;
     const int qstop = a.qcap - kW * 32 * kSub;
     double eb_scale = 0.0;  // filter pass: scale of the error bound = max |w d| over the light curve
-    if (kUniformW) eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
+    Gate32 g32;
+    g32.mu = 0.0; g32.err = 0.0; g32.depth_min = depth_min;
+    if (kUniformW) {
+        eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
+        g32.mu = block_mean<kT>(a.dval, N, red_d);
+    }
 
     for (;;) {
         if (tid == 0) {
@@ -281,25 +304,40 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
 
         // ---- A. fold + stable sort + gather, wrap, w*d, T, cumulative sums (global scratch) ----
         double tpart = 0.0;
-        if (tid == 0) cs[0] = 0.0;
+        float cmax = 0.f;
+        if (tid == 0) {
+            cs[0] = 0.0;
+            if (kUniformW) cs32[0] = 0.f;
+        }
         bool on_chip = false;
         if (a.seg_cap > 0)
             on_chip = sort_on_chip<kT, kUniformW>(a, r, reinterpret_cast<unsigned char *>(cs_s), seg_cnt, gkey, gid,
-                                                  cs + 1, w, wd, wd32, (int)nmp_even, red_d, tpart);
+                                                  cs + 1, w, wd, wd32, (int)nmp_even, red_d, tpart, cs32 + 1, g32.mu, cmax);
         if (!on_chip) {  // clustered phases (or no room for segments): sort in the global scratch
             if (tid == 0 && a.seg_cap > 0) atomicAdd(a.counter + 4, 1);
             fold_sort_gather<kT, unsigned, !kUniformW, false, 8>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval,
                                                                  cs + 1, w, reinterpret_cast<int *>(red_d));
             __syncthreads();
-            tpart = wrap_weight_scan<kT, kUniformW, kScanItems, true, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d, 0,
-                                                                                 0.0, wd32);
+            tpart = wrap_weight_scan<kT, kUniformW, kScanItems, true, kUniformW, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even,
+                                                                                            red_d, 0, 0.0, wd32, cs32 + 1, g32.mu, &cmax);
         }
 #pragma unroll
-        for (int off = 16; off; off >>= 1) tpart += __shfl_xor_sync(kFull, tpart, off);
-        if (lane == 0) red_d[kW + 1 + wid] = tpart;
+        for (int off = 16; off; off >>= 1) {
+            tpart += __shfl_xor_sync(kFull, tpart, off);
+            cmax = fmaxf(cmax, __shfl_xor_sync(kFull, cmax, off));
+        }
+        if (lane == 0) {
+            red_d[kW + 1 + wid] = tpart;
+            red_i[wid] = __float_as_int(cmax);
+        }
         __syncthreads();
         double T = 0.0;
         for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];
+        if (kUniformW) {
+            float cm = 0.f;
+            for (int k = 0; k < kW; ++k) cm = fmaxf(cm, __int_as_float(red_i[k]));
+            g32.set_err(cm, NM);
+        }
         fence_proxy_async();  // this thread's global writes -> visible to the bulk copies below
 
         // ---- B. chunks ---------------------------------------------------------------------
@@ -343,11 +381,11 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         // gate + taps over the tables' tiles, widths ub-1 downwards; csb / wb / wdb are indexable by global offsets
         ExactView<false> view;
         view.cs = cs; view.wd = wd; view.dval = nullptr; view.sid = nullptr; view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
-        auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *wd32b, int ub) {
+        auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *cs32b, const float *wd32b, int ub) {
             const int tile_end = s_next[4];
             if constexpr (kUniformW) {  // barrier-free gate + filter sweep (tlsb_device.cuh)
-                sweep_filter<kT, kBlock, false>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, csb, wd32b, a.tq32,
-                                                a.w0, T, depth_min, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
+                sweep_filter<kT, kBlock, false>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, cs32b, wd32b, a.tq32,
+                                                a.w0, T, g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
                 return;
             }
             int g_next = wid;
@@ -443,9 +481,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 if (tid == 0) {
                     const int len_cs = min(C, (int)cs_elems - a0);
                     if (kUniformW) {
-                        const int len_32 = min(C, (int)nmp4 - a0);
-                        mbar_expect_tx(bar, 8u * (unsigned)len_cs + 4u * (unsigned)len_32);
-                        bulk_copy_g2s(cs_s, cs + a0, 8u * (unsigned)len_cs, bar);
+                        const int len_c32 = min(C, (int)cs4 - a0), len_32 = min(C, (int)nmp4 - a0);
+                        mbar_expect_tx(bar, 4u * (unsigned)(len_c32 + len_32));
+                        bulk_copy_g2s(cs32_s, cs32 + a0, 4u * (unsigned)len_c32, bar);
                         bulk_copy_g2s(wd32_s, wd32 + a0, 4u * (unsigned)len_32, bar);
                         fs->fq_fill = 0;
                         *ss = SweepShared{};
@@ -464,7 +502,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 __syncthreads();
                 mbar_wait(bar, parity);
                 parity ^= 1u;
-                sweep(cs_s - a0, w_s - a0, wd_s - a0, wd32_s - a0, uT);
+                sweep(cs_s - a0, w_s - a0, wd_s - a0, cs32_s - a0, wd32_s - a0, uT);
             }
         }
         if (uT < uhi) {  // the widest widths: gate and taps read the scratch through L1/L2
@@ -475,7 +513,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
             }
             build_tables(0, 1 << 30, max(ulo, uT), uhi);
             __syncthreads();
-            sweep(cs, w, wd, wd32, uhi);
+            sweep(cs, w, wd, cs32, wd32, uhi);
         }
 
         // ---- C. block arg-min with the reference's tie order ---------------------------
