@@ -165,6 +165,8 @@ struct tlsb_handle {
     std::vector<int64_t> in_meta;  // offset | length | width
     // results of the one-shot call come back through ONE copy into pinned memory
     PinBuf pin_out;
+    bool tq_in_flight = false;     // an asynchronous upload from h_tq / h_tq32 may not have finished (on tq_stream)
+    cudaStream_t tq_stream = nullptr;
     // the device plan is a pure function of (periods, bank, N, span, stellar limits): remembered across searches once
     // its status word has been read back clean
     int64_t bank_ver = 0, periods_ver = 0;
@@ -440,8 +442,10 @@ Layout choose_layout(const tlsb_handle *h)
                 }
                 if (n_tiled < 1 || (!exact_cap && 4 * n_tiled < 3 * h->nU)) continue;
                 TP = C - window_need(h->recs[(size_t)n_tiled - 1].W, h->recs[(size_t)n_tiled - 1].X, 5);
-            } else if (h->chunk_cap == 0 && t[1] == 2 && forced < 0 && (TP < 2048 || 5 * TP < 3 * C)) {
-                continue;  // two CTAs per SM only when most of a chunk is start offsets (halo below ~40 %); one big CTA otherwise
+            } else if (h->chunk_cap == 0 && t[1] == 2 && forced < 0 && (TP < 2048 || 5 * TP < 4 * C)) {
+                // two CTAs per SM only when nearly all of a chunk is start offsets (halo below 20 %); one big CTA with the
+                // barrier-free sweep otherwise (cfg-3, halo 34 %: 22.0 ms with two CTAs, 21.2 ms with one)
+                continue;
             }
             best.resident = false;
             best.tiled = true;
@@ -833,6 +837,8 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
             if ((rc0 = upload(h->tq, h->h_tq.p, h->n_tq * 8, h->up_stream))) return rc0;
             if ((rc0 = upload(h->tq32, h->h_tq32.p, h->n_tq32 * 4, h->up_stream))) return rc0;
             if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));
+            h->tq_in_flight = h->defer_sync;
+            h->tq_stream = h->up_stream;
             return 0;
         }
         if (memo_enabled()) {
@@ -892,7 +898,10 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     int M = recs[nU - 1].W;  // core.py:114-116
     if (M % 2 != 0) M += 1;
     int rc;
-    if (h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));  // an earlier asynchronous upload may still read h_tq
+    if (h->tq_in_flight) {  // an earlier asynchronous upload may still read h_tq / h_tq32
+        CUDA_TRY(cudaStreamSynchronize(h->tq_stream));
+        h->tq_in_flight = false;
+    }
     if (h->h_tq.ensure(n_tq * 8 + 8) || h->h_tq32.ensure(n_tq32 * 4 + 4)) return fail(TLSB_ERR_ALLOC, "pinned host allocation failed");
     double *tq = h->h_tq.as<double>();
     float *tq32 = h->h_tq32.as<float>();
@@ -929,6 +938,8 @@ int tlsb_set_templates(tlsb_handle *h, const tlsb_templates *tp, const tlsb_para
     h->n_tq32 = n_tq32;
     if ((rc = upload(h->tq, tq, n_tq * 8, h->up_stream))) return rc;
     if ((rc = upload(h->tq32, tq32, n_tq32 * 4, h->up_stream))) return rc;
+    h->tq_in_flight = h->defer_sync;
+    h->tq_stream = h->up_stream;
     if (!h->defer_sync) CUDA_TRY(cudaStreamSynchronize(h->up_stream));
     h->recs.swap(recs);
     h->pad = kPadGroups * kBlockMax * xmax;
@@ -1066,6 +1077,7 @@ int tlsb_get_results(tlsb_handle *h, void *cuda_stream, double *chi2_out, int64_
     for (int attempt = 0; attempt < 2; ++attempt) {
         CUDA_TRY(cudaMemcpyAsync(h->pin_out.p, h->out.p, words * 8, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        if (s == h->tq_stream) h->tq_in_flight = false;
         if (packed[P] == 0 && attempt == 0 && h->plan_key_launched) h->plan_key_clean = true;  // the device plan stands
         if (packed[P] == 0 || attempt == 1) break;
         // the device plan was not sure about some periods' limits: settle those on the host and search

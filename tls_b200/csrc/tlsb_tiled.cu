@@ -44,10 +44,17 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     for (int j = tid; j <= ns; j += kT) cnt[j] = 0;
     __syncthreads();
     // ---- partition: one pass over t ------------------------------------------------------------
+    double tnext[kUP];  // the time stamps of the next trip are in flight while this one is folded and appended
+#pragma unroll
+    for (int u = 0; u < kUP; ++u) tnext[u] = (wid * 32 + u * kT + lane < N) ? __ldcs(a.t + wid * 32 + u * kT + lane) : 0.0;
     for (int kb = wid * 32; kb < N; kb += kT * kUP) {  // warp-uniform bounds: every lane reaches the match
         double tv[kUP];
 #pragma unroll
-        for (int u = 0; u < kUP; ++u) tv[u] = (kb + u * kT + lane < N) ? __ldcs(a.t + kb + u * kT + lane) : 0.0;
+        for (int u = 0; u < kUP; ++u) {
+            tv[u] = tnext[u];
+            const int kn = kb + kT * kUP + u * kT + lane;
+            tnext[u] = kn < N ? __ldcs(a.t + kn) : 0.0;
+        }
 #pragma unroll
         for (int u = 0; u < kUP; ++u) {
             const int k = kb + u * kT + lane;
@@ -91,6 +98,12 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         const double *lk = gkey + (size_t)j * S;
         const unsigned *li = gid + (size_t)j * S;
         for (int b = tid; b <= S; b += kT) H[b] = 0;
+        if (j + 1 < ns) {  // the next segment's lists were written a while ago and may have left L2: fetch them back now
+            const int nn = cnt[j + 1];
+            const char *pk = reinterpret_cast<const char *>(lk + S), *pi = reinterpret_cast<const char *>(li + S);
+            for (int b = tid * 128; b < nn * 8; b += kT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + b));
+            for (int b = tid * 128; b < nn * 4; b += kT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + b));
+        }
         __syncthreads();
         // histogram: every key of this thread stays in registers together with its bucket and its
         // arrival index inside the bucket, so the scatter below needs neither a reload nor atomics
