@@ -111,11 +111,62 @@ __device__ void block_inclusive_scan(T *data, int n, T *warp_tot /* [kT/32+1] sh
     }
 }
 
+// The same scan over 16-bit counters packed two per word (entry 2k in the low half of word k): every prefix must stay
+// below 65536 (the callers sort fewer than 65536 keys), so no half ever carries into its neighbour.
+template <int kT, int kScanItems>
+__device__ void block_inclusive_scan_u16x2(unsigned *data, int nwords, int *warp_tot /* [kT/32+1] shared */)
+{
+    constexpr int kW = kT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < nwords; base += kT * kScanItems) {
+        const int first = base + tid * kScanItems;
+        unsigned v[kScanItems];
+        int run = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            const unsigned x = (first + k < nwords) ? data[first + k] : 0u;
+            run += (int)(x & 0xffffu);
+            const unsigned lo = (unsigned)run;
+            run += (int)(x >> 16);
+            v[k] = lo | ((unsigned)run << 16);
+        }
+        int incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(kFull, incl, off);
+            if (lane >= off) incl += o;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int wv = (lane < kW) ? warp_tot[lane] : 0;
+            int wi = wv;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(kFull, wi, off);
+                if (lane >= off) wi += o;
+            }
+            if (lane < kW) warp_tot[lane] = wi - wv;
+            if (lane == kW - 1) warp_tot[kW] = wi;
+        }
+        __syncthreads();
+        int excl = __shfl_up_sync(kFull, incl, 1);
+        if (lane == 0) excl = 0;
+        const unsigned offset = (unsigned)(carry + warp_tot[wid] + excl) * 0x10001u;  // the same offset in both halves
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+            if (first + k < nwords) data[first + k] = v[k] + offset;
+        carry += warp_tot[kW];
+        __syncthreads();
+    }
+}
+
 // Second half of the sort: skey/sid hold the keys grouped by bucket (any order inside a bucket); rank every key
 // inside its bucket by (phase, index) = numpy's stable mergesort order, and gather src1 (src2) to the sorted
 // slots of dst1 (dst2).  Bucket b spans [H[b-1], H[b]) with kShift = 0 (H[-1] = 0), [H[b], H[b+1]) with
 // kShift = 1.  Ends WITHOUT a barrier.
-template <int kT, typename idx_t, bool kTwo, int kU, int kShift, bool kKeepIds = false>
+template <int kT, typename idx_t, bool kTwo, int kU, int kShift, bool kKeepIds = false, bool kH16 = false>
 __device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const double *skey, const idx_t *sid,
                                             const double *__restrict__ src1, const double *__restrict__ src2,
                                             double *dst1, double *dst2, idx_t *sid_sorted = nullptr)
@@ -135,8 +186,14 @@ __device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const d
             v1[u] = __ldcs(src1 + id[u]);
             v2[u] = kTwo ? __ldcs(src2 + id[u]) : 0.0;
             const int bk = bucket_of(key[u], NB);
-            lo[u] = (bk + kShift) ? H[bk - 1 + kShift] : 0;
-            hi[u] = H[bk + kShift];
+            if (kH16) {
+                const unsigned short *H16 = reinterpret_cast<const unsigned short *>(H);
+                lo[u] = (bk + kShift) ? (int)H16[bk - 1 + kShift] : 0;
+                hi[u] = (int)H16[bk + kShift];
+            } else {
+                lo[u] = (bk + kShift) ? H[bk - 1 + kShift] : 0;
+                hi[u] = H[bk + kShift];
+            }
         }
         // the kU ranking loops run in lockstep so that their loads are in flight together
         int rank[kU], longest = 0;
@@ -176,7 +233,10 @@ __device__ __forceinline__ void rank_gather(int N, int NB, const int *H, const d
 // rank inside the bucket by (phase, index) = numpy's stable mergesort order; src1 (and src2) are
 // gathered to their sorted slots in dst1 (dst2).  dst1 doubles as the store of the unsorted
 // phases until the ranking step; skey/sid/H are scratch.  Ends WITHOUT a barrier.
-template <int kT, typename idx_t, bool kTwo, bool kEpoch, int kU = 4, int kHScanItems = tlsb::kScanItems, bool kKeepIds = false>
+// kH16: the histogram is kept as 16-bit counters, two per word (fewer than 65536 keys), so that twice as many buckets fit
+// the same shared memory: with NB = 2 N most keys are alone in their bucket and the ranking loops are short.
+template <int kT, typename idx_t, bool kTwo, bool kEpoch, int kU = 4, int kHScanItems = tlsb::kScanItems, bool kKeepIds = false,
+          bool kH16 = false>
 __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, double T0, double r, int N, int NB,
                                                  int *H, double *skey, idx_t *sid,
                                                  const double *__restrict__ src1, const double *__restrict__ src2,
@@ -185,7 +245,13 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
 {
     // kU independent load chains per thread (the streaming layouts sort in L2/HBM)
     const int tid = threadIdx.x;
-    for (int b = tid; b <= NB; b += kT) H[b] = 0;
+    unsigned *Hw = reinterpret_cast<unsigned *>(H);
+    const int nwords = (NB + 2) / 2;  // kH16: entries 0..NB, two per word
+    if (kH16) {
+        for (int b = tid; b < nwords; b += kT) Hw[b] = 0u;
+    } else {
+        for (int b = tid; b <= NB; b += kT) H[b] = 0;
+    }
     __syncthreads();
     double *ph_unsorted = dst1;  // [N], free until the ranking step writes the sorted values
     for (int k0 = tid; k0 < N; k0 += kT * kU) {
@@ -198,13 +264,16 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
             if (k < N) {
                 const double ph = fold_phase(kEpoch ? tv[u] - T0 : tv[u], r);
                 ph_unsorted[k] = ph;
-                atomicAdd(&H[bucket_of(ph, NB) + 1], 1);
+                const int e = bucket_of(ph, NB) + 1;
+                if (kH16) atomicAdd(&Hw[e >> 1], 1u << ((e & 1) * 16));
+                else atomicAdd(&H[e], 1);
             }
         }
     }
     __syncthreads();
     // inclusive scan of H[0..NB] (H[0] = 0): H[b] = number of keys in buckets < b
-    block_inclusive_scan<kT, int, kHScanItems>(H, NB + 1, scan_scratch);
+    if (kH16) block_inclusive_scan_u16x2<kT, kHScanItems>(Hw, nwords, scan_scratch);
+    else block_inclusive_scan<kT, int, kHScanItems>(H, NB + 1, scan_scratch);
     for (int k0 = tid; k0 < N; k0 += kT * kU) {
         double ph[kU];
 #pragma unroll
@@ -213,14 +282,20 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
         for (int u = 0; u < kU; ++u) {
             const int k = k0 + u * kT;
             if (k < N) {
-                const int pos = atomicAdd(&H[bucket_of(ph[u], NB)], 1);  // any order inside the bucket
+                int pos;  // any order inside the bucket
+                if (kH16) {
+                    const int e = bucket_of(ph[u], NB), sh = (e & 1) * 16;
+                    pos = (int)((atomicAdd(&Hw[e >> 1], 1u << sh) >> sh) & 0xffffu);
+                } else {
+                    pos = atomicAdd(&H[bucket_of(ph[u], NB)], 1);
+                }
                 skey[pos] = ph[u];
                 sid[pos] = (idx_t)k;
             }
         }
     }
     __syncthreads();  // now H[b] = end of bucket b; the unsorted phases are dead
-    rank_gather<kT, idx_t, kTwo, kU, 0, kKeepIds>(N, NB, H, skey, sid, src1, src2, dst1, dst2, sid_sorted);
+    rank_gather<kT, idx_t, kTwo, kU, 0, kKeepIds, kH16>(N, NB, H, skey, sid, src1, src2, dst1, dst2, sid_sorted);
 }
 
 // After the sort: cs1[0..N) holds the sorted d = 1 - y (cs1 = cs + 1).  Wrap the first M samples to

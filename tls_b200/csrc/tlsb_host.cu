@@ -296,7 +296,7 @@ size_t resident_filter_smem_bytes(int N, int M, int pad, int nU, int qcap, int f
     const size_t NM = (size_t)N + M, NMP = NM + pad;
     // X: the sorted d / fp64 cumulative sums while they are built, the survivor queue afterwards
     const size_t x = align16(std::max(((NM + 2) & ~(size_t)1), (size_t)qcap) * 8);
-    const size_t sort_area = (size_t)N * 8 + ((size_t)NB + 1) * 4 + (size_t)N * 2;
+    const size_t sort_area = (size_t)N * 8 + (((size_t)NB + 2) / 2) * 4 + (size_t)N * 2;  // 16-bit bucket counters
     const size_t search_area = ((NM + 2 + 3) & ~(size_t)3) * 4 + ((NMP + 3) & ~(size_t)3) * 4 + (size_t)fq_cap * 12;
     return x + align16((size_t)N * 2) + tail_bytes(nU, threads) + align16(std::max(sort_area, search_area));
 }
@@ -328,7 +328,7 @@ Layout choose_layout(const tlsb_handle *h)
                                  {256, 2, 2560, 512, 4}, {512, 1, 8192, 2048, 1}, {512, 1, 4096, 1024, 1}};
         const int cs_elems = (N + h->M + 2) & ~1;
         for (const auto &t : tries) {
-            const int NB = std::max(64, N / t[4]);
+            const int NB = std::max(64, 2 * (N / t[4]));  // 16-bit counters: two buckets per sample in the space of one
             const int qcap = t[0] == 256 ? std::min(16384, std::max(t[2], cs_elems)) : t[2];
             const size_t bytes = resident_filter_smem_bytes(N, h->M, h->pad, h->nU, qcap, t[3], t[0], NB);
             if (bytes > h->max_smem) continue;

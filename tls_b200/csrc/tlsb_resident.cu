@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         tail = reinterpret_cast<unsigned char *>(sid_sorted) + (((size_t)N * sizeof(idx_t) + 15) & ~(size_t)15);
         unsigned char *area = tail + filter_tail_bytes(nU, kT);
         skey = reinterpret_cast<double *>(area);
-        H = reinterpret_cast<int *>(skey + N);
-        sid = reinterpret_cast<idx_t *>(H + NB + 1);
+        H = reinterpret_cast<int *>(skey + N);                    // 16-bit counters, two per word: NB + 1 entries
+        sid = reinterpret_cast<idx_t *>(H + (NB + 2) / 2);
         cs32 = reinterpret_cast<float *>(area);
         wd32 = cs32 + (((size_t)NM + 2 + 3) & ~(size_t)3);
         fq = reinterpret_cast<int2 *>(wd32 + (((size_t)NMP + 3) & ~(size_t)3));
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         }
 
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
-        fold_sort_gather<kT, idx_t, !kUniformW, false, (kResident ? kResSortU : 4), (kResident ? kResHScanItems : kScanItems), kFilter>(
+        fold_sort_gather<kT, idx_t, !kUniformW, false, (kResident ? kResSortU : 4), (kResident ? kResHScanItems : kScanItems), kFilter, kFilter>(
             a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w, reinterpret_cast<int *>(red_d), sid_sorted);
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
@@ -305,7 +305,9 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             o.i = __shfl_xor_sync(kFull, best.i, off);
             if (better(o.chi2, o.u, o.i, best)) best = o;
         }
-        __syncthreads();  // everyone is done reading red_d (T) and the queue before they are reused
+        // Filter paths: the barrier in front of drain_finalists already separates every read of red_d / red_i (T, the
+        // largest |cs32|) from the writes below.
+        if (!kFilter) __syncthreads();  // everyone is done reading red_d (T) and the queue before they are reused
         if (lane == 0) {
             red_d[wid] = best.chi2;
             red_d[kW + wid] = best.D;
@@ -343,7 +345,8 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
                 }
             }
         }
-        __syncthreads();
+        // no barrier here: the one at the top of the loop (after thread 0 has taken the next period) is the first point at
+        // which red_d / red_i / the scheduler words are written again by anyone but warp 0 itself
     }
 
     // last CTA out resets the scheduler so the next launch needs no memset

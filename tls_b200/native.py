@@ -148,7 +148,7 @@ def _i64(a):
 
 
 def _ptr(a):
-    return a.ctypes.data_as(_c_vp)
+    return a.ctypes.data  # an int: ctypes converts it for c_void_p arguments and fields (data_as costs 3x as much)
 
 
 class _Packed(object):
