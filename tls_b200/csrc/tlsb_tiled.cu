@@ -37,9 +37,12 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     double *val_s = reinterpret_cast<double *>(area);            // [S] sorted d of the segment
     double *wv_s = val_s + S;                                    // [S] sorted w (unequal weights only)
     double *skey_s = kUniformW ? wv_s : wv_s + S;                // [S] keys, bucket order
-    int *H = reinterpret_cast<int *>(skey_s + S);                // [S + 2] fine-bucket histogram
-    unsigned *sid_s = reinterpret_cast<unsigned *>(H + S + 2);   // [S] sample ids, bucket order
-    const double dns = (double)ns, dS = (double)S;
+    // fine-bucket histogram: 2 S buckets as 16-bit counters packed two per word (S < 32768 keys per segment), S + 2 words
+    unsigned *Hw = reinterpret_cast<unsigned *>(skey_s + S);
+    const unsigned short *H16 = reinterpret_cast<const unsigned short *>(Hw);
+    unsigned *sid_s = Hw + S + 2;                                // [S] sample ids, bucket order
+    const int S2 = 2 * S;
+    const double dns = (double)ns, dS = (double)S2;
 
     for (int j = tid; j <= ns; j += kT) cnt[j] = 0;
     __syncthreads();
@@ -87,7 +90,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         // explicit roundings: the three passes must map a key to the same bucket (no FMA contraction)
         const double x = __dsub_rn(__dmul_rn(ph, dns), (double)j);
         const int fb = __double2int_rz(__dmul_rn(x, dS));
-        return fb < 0 ? 0 : (fb < S - 1 ? fb : S - 1);
+        return fb < 0 ? 0 : (fb < S2 - 1 ? fb : S2 - 1);
     };
     double tpart = 0.0, carry = 0.0;
     float cmax = 0.f;
@@ -97,7 +100,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         if (nj == 0) continue;
         const double *lk = gkey + (size_t)j * S;
         const unsigned *li = gid + (size_t)j * S;
-        for (int b = tid; b <= S; b += kT) H[b] = 0;
+        for (int b = tid; b <= S; b += kT) Hw[b] = 0u;  // entries 0 .. 2 S + 1
         if (j + 1 < ns) {  // the next segment's lists were written a while ago and may have left L2: fetch them back now
             const int nn = cnt[j + 1];
             const char *pk = reinterpret_cast<const char *>(lk + S), *pi = reinterpret_cast<const char *>(li + S);
@@ -118,16 +121,16 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
 #pragma unroll
         for (int i = 0; i < kSegPerThread; ++i) {
             if (tid + i * kT < nj) {
-                const int fb = fine(ph[i], j);
-                where[i] = ((unsigned)atomicAdd(&H[fb + 1], 1) << 16) | (unsigned)fb;
+                const int fb = fine(ph[i], j), e = fb + 1, sh = (e & 1) * 16;
+                where[i] = (((atomicAdd(&Hw[e >> 1], 1u << sh) >> sh) & 0xffffu) << 16) | (unsigned)fb;
             }
         }
         __syncthreads();
-        block_inclusive_scan<kT, int, kSegScanItems>(H, S + 1, reinterpret_cast<int *>(red_d));  // H[b] = keys in buckets < b
+        block_inclusive_scan_u16x2<kT, kSegScanItems>(Hw, S + 1, reinterpret_cast<int *>(red_d));  // H16[b] = keys in buckets < b
 #pragma unroll
         for (int i = 0; i < kSegPerThread; ++i) {
             if (tid + i * kT < nj) {
-                const int pos = H[where[i] & 0xffffu] + (int)(where[i] >> 16);
+                const int pos = (int)H16[where[i] & 0xffffu] + (int)(where[i] >> 16);
                 skey_s[pos] = ph[i];
                 sid_s[pos] = id[i];
             }
@@ -148,8 +151,8 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
                 v1[u] = __ldcs(a.dval + sidq[u]);
                 v2[u] = kUniformW ? 0.0 : __ldcs(a.wval + sidq[u]);
                 const int fb = fine(key[u], j);
-                lo[u] = H[fb];
-                hi[u] = q0 + u * kT < nj ? H[fb + 1] : lo[u];
+                lo[u] = (int)H16[fb];
+                hi[u] = q0 + u * kT < nj ? (int)H16[fb + 1] : lo[u];
                 rank[u] = lo[u];
                 longest = max(longest, hi[u] - lo[u]);
             }
