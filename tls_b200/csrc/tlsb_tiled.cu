@@ -29,8 +29,14 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
                                              int nmp_even, double *red_d, double &tpart_out, float *cs32_1, double mu,
                                              float &cmax_out)
 {
-    constexpr int kU = 4;                  // independent chains of the rank / gather loop
-    constexpr int kUP = 4;                 // ... of the partition pass
+#ifndef TLSB_SEG_RANK_U
+#define TLSB_SEG_RANK_U 4
+#endif
+#ifndef TLSB_SEG_PART_U
+#define TLSB_SEG_PART_U 4
+#endif
+    constexpr int kU = TLSB_SEG_RANK_U;    // independent chains of the rank / gather loop
+    constexpr int kUP = TLSB_SEG_PART_U;   // ... of the partition pass
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int N = a.N, M = a.M, NM = N + M, S = a.seg_cap, ns = a.n_seg;
     const unsigned lt_mask = (1u << lane) - 1u;
