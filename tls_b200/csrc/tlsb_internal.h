@@ -44,7 +44,10 @@ int spectra_device(const double *chi2, int64_t P, int64_t n_curves, int64_t win,
 // tap loop.  Odd (neighbouring lanes sit R*stride doubles apart in shared memory): 7 when all weights
 // are equal (one correlation: the register window fits), 5 with unequal weights (two correlations).
 constexpr int kBlockMax = 7;          // host-side slack (template padding, array slack) is sized for the largest R
-constexpr int kSub = 4;               // sub-tiles of 32 blocks a warp gates per queue reservation
+#ifndef TLSB_SUB
+#define TLSB_SUB 4
+#endif
+constexpr int kSub = TLSB_SUB;        // sub-tiles of 32 blocks a warp gates per queue reservation
 __host__ __device__ constexpr int tile_size(int kb) { return 32 * kb * kSub; }  // candidates one warp gates at a time
 constexpr int kGroup32 = 8;           // steps per unrolled group of the fp32 tap loop (template values arrive as two float4)
 constexpr int kPadGroups = 4;         // slack (in groups of kBlock steps) behind templates and patched arrays
@@ -54,7 +57,7 @@ constexpr int kResScanItems = 19;     // ... of the resident kernel: one tile co
 #define TLSB_RES_HSCAN 19  // one tile for cfg-1's 4,322 histogram words, like kResScanItems (5 -> 17: 2.611 -> 2.579 ms per cfg-1 grid)
 #endif
 #ifndef TLSB_RES_SORT_U
-#define TLSB_RES_SORT_U 4
+#define TLSB_RES_SORT_U 3  // 2 / 3 / 4 chains: 2.092 / 2.084 / 2.103 ms per cfg-1 grid
 #endif
 constexpr int kResHScanItems = TLSB_RES_HSCAN;  // ... of the bucket-histogram scan of the resident kernel
 constexpr int kResSortU = TLSB_RES_SORT_U;      // independent key chains per thread in the resident kernel's fold / scatter / rank loops
