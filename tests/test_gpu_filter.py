@@ -72,3 +72,70 @@ def test_filter_passes_few_candidates_on_noisy_data():
     assert st["candidates"] > 1000 * len(g["periods"])
     assert st["finalists"] < 0.05 * st["candidates"], st
     assert st["overflows"] == 0, st
+
+
+def _oracle(g, periods=None):
+    from oracle import oracle
+
+    return oracle.search_periods_c(g["t"], g["y"], g["dy"], g["periods"] if periods is None else periods, g["templates"], g["params"])
+
+
+@pytest.mark.parametrize("name,path,chunk", [("small", "auto", 0), ("cfg1_500ppm", "auto", 0), ("small", "tiled", 512),
+                                              ("cfg1_500ppm", "tiled", 1536)])
+@pytest.mark.parametrize("case", ["scale_0.97", "scale_1.02", "offset_+3e-3", "offset_-3e-3", "trend", "scale_0.5"])
+def test_fp32_gate_on_flux_that_is_not_normalised(name, path, chunk, case):
+    """The fp32 gate tests detrended cumulative sums cs32[k] = fl32(cs[k] - k mu) against a threshold lowered by a rigorous
+    error bound (tlsb_device.cuh: Gate32); candidates it lets through are settled by the exact fp64 gate in bound_one.
+    Flux that is not normalised to 1 makes the cumulative sums grow linearly (what the detrending is for) and, with a
+    trend, leaves large excursions after it (what the error bound is for).  Whatever the gate's resolution: filter on ==
+    filter off bit for bit, and both equal the C oracle (core.py:58 gate, rows exact, chi2 to 1e-9)."""
+    g = dict(load_search_golden(name))
+    y = g["y"].copy()
+    if case.startswith("scale_"):
+        y = y * float(case.split("_")[1])
+    elif case.startswith("offset_"):
+        y = y + float(case.split("_")[1])
+    else:
+        y = y * (1.0 + 4e-3 * (g["t"] - g["t"].mean()) / (g["t"].max() - g["t"].min()))
+    g["y"] = y
+    periods = g["periods"][:: max(1, len(g["periods"]) // 24)]
+    on, _, used = _run(g, True, path, chunk, periods=periods)
+    off, _, _ = _run(g, False, path, chunk, periods=periods)
+    for a, b, what in zip(on, off, ("chi2", "row", "depth", "t0_index")):
+        np.testing.assert_array_equal(a, b, err_msg="%s differs with the filter on (%s, %s, %s)" % (what, name, case, used))
+    want = _oracle(g, periods)
+    np.testing.assert_array_equal(on[1], want[1], err_msg="rows (%s, %s, %s)" % (name, case, used))
+    fin = np.isfinite(want[0])
+    np.testing.assert_array_equal(on[0][~fin], want[0][~fin])
+    np.testing.assert_allclose(on[0][fin], want[0][fin], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(on[2], want[2], rtol=1e-9, atol=1e-300)
+
+
+def test_memo_switch_changes_nothing_but_the_launch_count():
+    """TLSB_MEMO=0 makes every call redo the plan and the derived template arrays (bench.py's e2e figure); results are
+    identical either way."""
+    import os
+
+    from tls_b200 import native
+
+    g = load_search_golden("small")
+    outs = {}
+    for memo in ("1", "0"):
+        os.environ["TLSB_MEMO"] = memo
+        try:
+            s = native.Searcher()
+            s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])
+            s.set_periods(g["periods"])
+            counts = []
+            for _ in range(3):
+                s.set_inputs(g["t"], g["y"], g["dy"], g["templates"], g["params"])  # the same bank again
+                s.search_async()
+                counts.append(s.launch_count)
+                outs.setdefault(memo, []).append(s.results())
+            s.close()
+        finally:
+            os.environ.pop("TLSB_MEMO", None)
+        assert counts == ([2, 1, 1] if memo == "1" else [2, 2, 2]), (memo, counts)
+    for a, b in zip(outs["1"], outs["0"]):
+        for x, z in zip(a, b):
+            np.testing.assert_array_equal(x, z)

@@ -468,7 +468,7 @@ def unpack_records(records, n_periods):
     rec = np.asarray(records)[: 3 * n_periods].reshape(3, n_periods)
     chi2 = rec[0].view(np.float64)
     depth = rec[1].view(np.float64)
-    packed = rec[2].view(np.int64)
-    row = (packed & 0xFFFFFFFF).astype(np.int64)
-    t0 = (packed >> 32).astype(np.int64)
+    # packed = row | t0_index << 32 (little endian): the low and high halves as strided 32-bit views, widened once
+    row = rec[2].view(np.uint32)[0::2].astype(np.int64)
+    t0 = rec[2].view(np.int32)[1::2].astype(np.int64)
     return chi2, row, depth, t0
