@@ -15,8 +15,8 @@ python bench.py --impl reference --steps 3 --warmup 1 --workload $WL > $OUT/benc
 cat $OUT/bench_ref_$WL.json
 # launch list (cold-cache, serialised: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$WL.csv \
-    python bench.py --workload $WL --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
+    python bench.py --workload $WL --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_launches.log 2>&1
 # one full capture of the search kernel
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tlsb_search -s 3 -c 1 -f -o $OUT/prof_$WL \
-    python bench.py --workload $WL --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
+    python bench.py --workload $WL --steps 3 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_full.log 2>&1
 ls -la $OUT

@@ -29,8 +29,9 @@ with open(os.path.join(dst, "r%s_%s_launches.csv" % (rnd, wl)), "w") as f:
         f.write('%s,"%s","%s","%s",%d\n' % r)
 share = {}
 for _, k, _, _, ns in rows:
-    name = "tlsb_search_kernel" if "tlsb_search_kernel" in k else "tlsb_plan_kernel" if "tlsb_plan" in k else \
-        "tlsb_prepare_kernel" if "tlsb_prepare" in k else "torch fill (L2 flush / buffers, outside the timed events)"
+    import re
+    mm = re.search(r"(tlsb_\w+?_kernel)", k)
+    name = mm.group(1) if mm else "torch fill (L2 flush / buffers, outside the timed events)"
     share[name] = share.get(name, 0) + ns
 ours = {k: v for k, v in share.items() if k.startswith("tlsb_")}
 tot = float(sum(ours.values()))
@@ -62,7 +63,7 @@ with open(os.path.join(dst, "traffic_%s.json" % wl), "w") as f:
     json.dump({"kernel": m["Kernel Name"][0] if "Kernel Name" in m else "tlsb_search_kernel",
                "dram_bytes_per_launch": traffic, "source": "ncu --set full, profiles/r%s_%s_ncu_summary.md" % (rnd, wl)}, f)
 
-lines_out = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "ncu_lines.py"), rep, "25"], capture_output=True, text=True).stdout
+lines_out = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "ncu_breakdown.py"), rep], capture_output=True, text=True).stdout
 bench = {}
 try:
     bench = json.load(open(os.path.join(src, "bench_%s.json" % wl)))
@@ -71,7 +72,7 @@ except Exception:
 with open(os.path.join(dst, "r%s_%s_ncu_summary.md" % (rnd, wl)), "w") as f:
     f.write("# Round %s — ncu summary, workload %s (capture %s)\n\n" % (rnd, wl, tag))
     f.write("Commands (scripts/gpu_check.sh, run under gpurun on one B200):\n\n```\n")
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv ... python bench.py --workload %s --steps 3 --warmup 3 --no-cpu-baseline\n" % wl)
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv ... python bench.py --workload %s --steps 3 --warmup 3 --no-cpu-baseline --no-secondary\n" % wl)
     f.write("ncu --set full --clock-control none --import-source on -k regex:tlsb_search -s 3 -c 1 ... (same command)\n```\n\n")
     if bench:
         r = bench["roofline"]
@@ -90,5 +91,5 @@ with open(os.path.join(dst, "r%s_%s_ncu_summary.md" % (rnd, wl)), "w") as f:
         if k in m:
             f.write("| %s | %s | %s |\n" % (k, m[k][0], m[k][1]))
     f.write("| dram traffic per launch (read+write) | %.0f | byte |\n" % traffic)
-    f.write("\n## Hottest source lines (warp-state samples; tls_b200/csrc/tlsb_search.cu)\n\n```\n%s```\n" % lines_out)
+    f.write("\n## Hottest source lines (warp-state samples; line numbers of tls_b200/csrc/tlsb_device.cuh, tlsb_resident.cu / tlsb_tiled.cu)\n\n```\n%s```\n" % lines_out)
 print("ok", share)
