@@ -32,9 +32,7 @@ def _run(g, on, path="auto", chunk=0, stats=False, periods=None):
 
 @pytest.mark.parametrize("name", [n for n in search_goldens()])
 def test_filter_on_equals_filter_off_bit_for_bit(name):
-    g = load_search_golden(name)
-    if not _uniform(g):
-        pytest.skip("per-point weights take the two-correlation fp64 path (no filter)")
+    g = load_search_golden(name)  # per-point weights: the filter runs two fp32 correlations (resident layouts)
     on, _, path = _run(g, True)
     off, _, _ = _run(g, False)
     for a, b, what in zip(on, off, ("chi2", "row", "depth", "t0_index")):
@@ -44,7 +42,7 @@ def test_filter_on_equals_filter_off_bit_for_bit(name):
 
 @pytest.mark.parametrize("name,path,chunk", [("cfg1_500ppm", "tiled", 1536), ("small", "tiled", 512),
                                               ("ragged_L", "tiled", 700), ("cfg3", "tiled", 0),
-                                              ("ties_unsorted", "tiled", 600)])
+                                              ("ties_unsorted", "tiled", 600), ("cfg1_hetero", "tiled", 1536)])
 def test_filter_on_equals_off_on_the_tiled_layout(name, path, chunk):
     g = load_search_golden(name)
     on, _, used = _run(g, True, path, chunk)
@@ -81,7 +79,7 @@ def _oracle(g, periods=None):
 
 
 @pytest.mark.parametrize("name,path,chunk", [("small", "auto", 0), ("cfg1_500ppm", "auto", 0), ("small", "tiled", 512),
-                                              ("cfg1_500ppm", "tiled", 1536)])
+                                              ("cfg1_500ppm", "tiled", 1536), ("cfg1_hetero", "auto", 0), ("cfg1_hetero", "tiled", 1536)])
 @pytest.mark.parametrize("case", ["scale_0.97", "scale_1.02", "offset_+3e-3", "offset_-3e-3", "trend", "scale_0.5"])
 def test_fp32_gate_on_flux_that_is_not_normalised(name, path, chunk, case):
     """The fp32 gate tests detrended cumulative sums cs32[k] = fl32(cs[k] - k mu) against a threshold lowered by a rigorous
@@ -139,3 +137,22 @@ def test_memo_switch_changes_nothing_but_the_launch_count():
     for a, b in zip(outs["1"], outs["0"]):
         for x, z in zip(a, b):
             np.testing.assert_array_equal(x, z)
+
+
+@pytest.mark.parametrize("name", [n for n in search_goldens()])
+def test_unequal_weights_filter_equals_the_all_fp64_kernel(name, monkeypatch):
+    """Per-point dy: the filter layouts (fp32 gate, two fp32 correlations, exact fp64 for finalists) against the
+    all-fp64 kernels (TLSB_WFILTER=0: tap_block / block_min on every gate survivor).  The two sum the taps in different
+    orders, so chi2 agrees to rounding (1e-11), rows and t0 exactly."""
+    g = load_search_golden(name)
+    if _uniform(g):
+        pytest.skip("equal weights")
+    new, _, path = _run(g, True)
+    monkeypatch.setenv("TLSB_WFILTER", "0")
+    old, _, _ = _run(g, True)
+    np.testing.assert_array_equal(new[1], old[1], err_msg="rows (%s, %s)" % (name, path))
+    np.testing.assert_array_equal(new[3], old[3], err_msg="t0 index (%s, %s)" % (name, path))
+    fin = np.isfinite(old[0])
+    np.testing.assert_array_equal(new[0][~fin], old[0][~fin])
+    np.testing.assert_allclose(new[0][fin], old[0][fin], rtol=1e-11, atol=0)
+    np.testing.assert_allclose(new[2], old[2], rtol=1e-11, atol=1e-300)

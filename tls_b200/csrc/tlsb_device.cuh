@@ -306,11 +306,16 @@ __device__ __forceinline__ void fold_sort_gather(const double *__restrict__ t, d
 // kWd64 / kWd32: write the products w*d in fp64 (wd) and / or rounded to fp32 (wd32, the filter pass's samples).
 // kCs32: also write the DETRENDED cumulative sums rounded to fp32, cs32_1[e] = fl32(cs1[e] - (e + 1) mu) (cs32_1 = cs32 + 1:
 // the fp32 gate and screen read these, tlsb_device.cuh "fp32 gate"), and return the largest |cs32| written in *cmax32.
-template <int kT, bool kUniformW, int kScanItems = tlsb::kScanItems, bool kWd64 = true, bool kWd32 = false, bool kCs32 = false>
+// kGatherW (unequal weights, filter layouts): the weights are not kept per folded position in fp64; they are gathered
+// from the light curve through the sorted sample ids (wsrc[sid[k]]) and written rounded to fp32 (w32).
+template <int kT, bool kUniformW, int kScanItems = tlsb::kScanItems, bool kWd64 = true, bool kWd32 = false, bool kCs32 = false,
+          bool kGatherW = false, typename sid_t = unsigned short, bool kW32 = kGatherW>
 __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, double *wd, double w0, int N, int NM,
                                                    int NMP, double *warp_tot /* [kT/32 + 1] shared */,
                                                    int begin = 0, double carry = 0.0, float *wd32 = nullptr,
-                                                   float *cs32_1 = nullptr, double mu = 0.0, float *cmax32 = nullptr)
+                                                   float *cs32_1 = nullptr, double mu = 0.0, float *cmax32 = nullptr,
+                                                   const double *__restrict__ wsrc = nullptr, const sid_t *sid = nullptr,
+                                                   float *w32 = nullptr)
 {
     constexpr int kW = kT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -318,12 +323,13 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
         if (k < NM) {
             if (begin == 0) {
                 cs1[k] = cs1[k - N];
-                if (!kUniformW) w[k] = w[k - N];
+                if (!kUniformW && !kGatherW) w[k] = w[k - N];
             }
         } else {  // slack read (never used) by the unguarded tap groups
             if (kWd64) wd[k] = 0.0;
             if (kWd32) wd32[k] = 0.f;
-            if (!kUniformW) w[k] = 0.0;
+            if (!kUniformW && !kGatherW) w[k] = 0.0;
+            if (kW32) w32[k] = 0.f;
         }
     }
     __syncthreads();
@@ -338,7 +344,8 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
         for (int k = 0; k < kScanItems; ++k) {  // every load in flight before the arithmetic
             const int e = first + k < NM ? first + k : NM - 1;
             dv[k] = cs1[e];
-            wv[k] = kUniformW ? w0 : w[e];
+            if (kGatherW) wv[k] = __ldg(wsrc + sid[e < N ? e : e - N]);
+            else wv[k] = kUniformW ? w0 : w[e];
         }
 #pragma unroll
         for (int k = 0; k < kScanItems; ++k) {
@@ -349,6 +356,7 @@ __device__ __forceinline__ double wrap_weight_scan(double *cs1, double *w, doubl
                 const double x = wv[k] * d;
                 if (kWd64) wd[e] = x;
                 if (kWd32) wd32[e] = (float)x;
+                if (kW32) w32[e] = (float)wv[k];
                 if (e < N) tpart = fma(x, d, tpart);
             }
             run += d;
@@ -733,6 +741,94 @@ __device__ __forceinline__ void tap_block32(const WidthRec &wr, const float *__r
     }
 }
 
+// ---- unequal weights (per-point dy): the filter pass accumulates TWO correlations in fp32,
+//   B = sum_j q_j (w d)_{i+j}   and   A = sum_j q_j^2 w_{i+j},
+// from wd32 = fl32(w d) and w32 = fl32(w).  One residue class per pass (V = 1); kQ2 = 2: the class's template values sit
+// at every second float (the pair-interleaved layout of even strides) and are fetched with scalar broadcast loads.
+// The squares q^2 are formed in fp32 from the fp32 template values when they enter the register window (three roundings
+// against the exact q^2 instead of one: the bound on |A32 - A64| uses L + 12 instead of L + 8 units).
+template <int kBlock, bool kUnit, int kQ2>
+__device__ __forceinline__ void tap_pass32w(const float *__restrict__ qp, const float *__restrict__ sp, const float *__restrict__ wp,
+                                            int X, int groups, float (&A)[kBlock], float (&B)[kBlock])
+{
+    constexpr int kG = kGroup32;
+    static_assert(kBlock + 1 <= kG, "entry k of the previous group must be dead after step k-2");
+    const int Xs = kUnit ? 1 : X;
+    float qa[kG], qb[kG], pa[kG], pb[kG];  // template values and their squares of the even / odd groups
+    float sa[kG], sb[kG], wa[kG], wb[kG];  // samples w d and w, one group ahead
+    auto load_q = [&](float (&dq)[kG], float (&dp)[kG], const float *__restrict__ p, int from) {  // entries [from, from + 4)
+        if (kQ2 == 1) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p + from));
+            dq[from] = v.x; dq[from + 1] = v.y; dq[from + 2] = v.z; dq[from + 3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dq[from + k] = __ldg(p + 2 * (from + k));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dp[from + k] = dq[from + k] * dq[from + k];
+    };
+    auto load_s = [&](float (&ds)[kG], float (&dw)[kG], const float *__restrict__ p, const float *__restrict__ pw) {
+#pragma unroll
+        for (int k = 0; k < kG; ++k) {
+            ds[k] = p[k * Xs];
+            dw[k] = pw[k * Xs];
+        }
+    };
+    auto group = [&](float (&cq)[kG], float (&cp)[kG], float (&pq)[kG], float (&pp)[kG], const float (&sv)[kG], const float (&wv)[kG],
+                     const float *__restrict__ qnext) {
+#pragma unroll
+        for (int mm = 0; mm < kG; ++mm) {
+#pragma unroll
+            for (int r = 0; r < kBlock; ++r) {
+                const int slot = mm - r;
+                B[r] = fmaf(slot >= 0 ? cq[slot] : pq[slot + kG], sv[mm], B[r]);
+                A[r] = fmaf(slot >= 0 ? cp[slot] : pp[slot + kG], wv[mm], A[r]);
+            }
+            // prev[j] is last read at step j - kG + kBlock - 1: entries 0..3 are dead after step 1, entries 4..7 after step 5
+            if (mm == 2) load_q(pq, pp, qnext, 0);
+            if (mm == 6) load_q(pq, pp, qnext, 4);
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < kG; ++k) { qb[k] = 0.f; pb[k] = 0.f; }  // "group -1": nothing before the first tap
+    load_q(qa, pa, qp, 0);
+    load_q(qa, pa, qp, 4);
+    load_s(sa, wa, sp, wp);
+#pragma unroll 1
+    for (int g = 0; g < groups; g += 2) {
+        load_s(sb, wb, sp + kG * Xs, wp + kG * Xs);
+        group(qa, pa, qb, pb, sa, wa, qp + kG * kQ2);   // qb <- template values of group g + 1
+        if (g + 1 >= groups) break;
+        load_s(sa, wa, sp + 2 * kG * Xs, wp + 2 * kG * Xs);
+        group(qb, pb, qa, pa, sb, wb, qp + 2 * kG * kQ2);  // qa <- template values of group g + 2
+        qp += 2 * kG * kQ2;
+        sp += 2 * kG * Xs;
+        wp += 2 * kG * Xs;
+    }
+}
+
+template <int kBlock, bool kUnit>
+__device__ __forceinline__ void tap_block32w(const WidthRec &wr, const float *__restrict__ tq32, const float *__restrict__ wd32,
+                                             const float *__restrict__ w32, int c0, float (&A)[kBlock], float (&B)[kBlock])
+{
+    constexpr int kG = kGroup32;
+    const int L = wr.L, X = kUnit ? 1 : wr.X;
+#pragma unroll
+    for (int r = 0; r < kBlock; ++r) { A[r] = 0.f; B[r] = 0.f; }
+    const float *__restrict__ qp = tq32 + wr.q32;
+    const float *__restrict__ sp = wd32 + c0 * X;
+    const float *__restrict__ wp = w32 + c0 * X;
+    const int groups = ((L + X - 1) / X + kBlock - 1 + kG - 1) / kG;
+    if (kUnit) {
+        tap_pass32w<kBlock, true, 1>(qp, sp, wp, 1, groups, A, B);
+    } else if ((X & 1) == 0) {  // pair-interleaved template layout: class b = 2 c + v at ((c A + a) 2 + v)
+        for (int b = 0; b < X && b < L; ++b)
+            tap_pass32w<kBlock, false, 2>(qp + 2 * (b >> 1) * wr.astride + (b & 1), sp + b, wp + b, X, groups, A, B);
+    } else {
+        for (int b = 0; b < X && b < L; ++b) tap_pass32w<kBlock, false, 1>(qp + b * wr.astride, sp + b, wp + b, X, groups, A, B);
+    }
+}
+
 __device__ __forceinline__ double chi2_value(double T, double D, double Aq, double B)
 {
     return __fma_rn(D, __fma_rn(D, Aq, -2.0 * B), T);  // T + D (D Aq - 2 B), core.py:67-70 after the algebra of DESIGN.md §3
@@ -749,10 +845,24 @@ struct ExactView {
     const double *tq;
     double w0, T;
     int N;
+    const double *wval;    // kGather, unequal weights: 1 / dy^2 per sample
+    const double *w;       // !kGather, unequal weights: w per folded position
     __device__ __forceinline__ double wdv(int k) const
     {
         if (kGather) return __dmul_rn(w0, __ldg(dval + sid[k < N ? k : k - N]));
         return wd[k];
+    }
+    // unequal weights: the weight and the product w*d of folded position k (the same product the fp64 arrays would hold)
+    __device__ __forceinline__ void wpair(int k, double &wk, double &wdk) const
+    {
+        if (kGather) {
+            const int id = sid[k < N ? k : k - N];
+            wk = __ldg(wval + id);
+            wdk = __dmul_rn(wk, __ldg(dval + id));
+        } else {
+            wk = w[k];
+            wdk = wd[k];
+        }
     }
 };
 
@@ -761,7 +871,8 @@ struct ExactView {
 // partial sums (every lane ends with the same bits), and every lane offers the candidate to its running best.
 // This is the ONLY place the equal-weights paths evaluate chi2 in fp64, so results do not depend on what the
 // filter let through.
-template <bool kGather>
+// kUW = false (unequal weights): the quadratic term A = sum_j q_j^2 w_{i+j} is accumulated the same way.
+template <bool kGather, bool kUW = true>
 __device__ __noinline__ void eval_exact_warp(const ExactView<kGather> &v, const WidthRec *rec, int c0, int rr, int u,
                                              Best &best)
 {
@@ -769,19 +880,39 @@ __device__ __noinline__ void eval_exact_warp(const ExactView<kGather> &v, const 
     const WidthRec wr = rec[u];
     const int L = wr.L, i = (c0 + rr) * wr.X;
     const double *__restrict__ q = v.tq + wr.q;
-    double B = 0.0;
+    double B = 0.0, A = 0.0;
+    if (kUW) {
 #pragma unroll 4
-    for (int j = lane; j < L; j += 32) B = fma(__ldg(q + j), v.wdv(i + j), B);
+        for (int j = lane; j < L; j += 32) B = fma(__ldg(q + j), v.wdv(i + j), B);
+    } else {
+#pragma unroll 2
+        for (int j = lane; j < L; j += 32) {
+            const double qv = __ldg(q + j);
+            double wk, wdk;
+            v.wpair(i + j, wk, wdk);
+            B = fma(qv, wdk, B);
+            A = fma(__dmul_rn(qv, qv), wk, A);
+        }
+    }
 #pragma unroll
-    for (int off = 16; off; off >>= 1) B += __shfl_xor_sync(kFull, B, off);
+    for (int off = 16; off; off >>= 1) {
+        B += __shfl_xor_sync(kFull, B, off);
+        if (!kUW) A += __shfl_xor_sync(kFull, A, off);
+    }
     const double mean = (__ldcg(v.cs + i + wr.W) - __ldcg(v.cs + i)) * wr.invW;  // global memory, written by this CTA
     const double D = mean * wr.os;
-    double chi = chi2_value(v.T, D, v.w0 * wr.sq2, B);
+    double chi = chi2_value(v.T, D, kUW ? v.w0 * wr.sq2 : A, B);
     if (L < wr.W) {  // samples L..W-1 are in neither sum
         double rest = 0.0;
         for (int k = i + L + lane; k < i + wr.W; k += 32) {
-            const double x = v.wdv(k);
-            rest += x * x / v.w0;
+            if (kUW) {
+                const double x = v.wdv(k);
+                rest += x * x / v.w0;
+            } else {
+                double wk, wdk;
+                v.wpair(k, wk, wdk);
+                rest += wdk * wdk / wk;
+            }
         }
 #pragma unroll
         for (int off = 16; off; off >>= 1) rest += __shfl_xor_sync(kFull, rest, off);
@@ -881,6 +1012,61 @@ __device__ __noinline__ float bound_one(const double *cs64, int i, int W, double
     return __double2float_rd(l);
 }
 
+// Unequal weights: the screen with both fp32 correlations, R = D (2 B - D A).  Besides the terms of block_screen the margin
+// carries |D|^2 EA for |A32 - A64| <= EA.
+template <int kBlock, bool kUnit>
+__device__ __forceinline__ int block_screen_w(const WidthRec &wr, const float *cs32, int c0, int mask, const float (&A)[kBlock],
+                                              const float (&B)[kBlock], float G32, float EB2f, float EAf, float slopTf, float Wmu32,
+                                              float dD)
+{
+    float lo[kBlock], hi[kBlock];
+    const int X = kUnit ? 1 : wr.X;
+    const float *__restrict__ p = cs32 + c0 * X;
+    const float *__restrict__ ph = p + wr.W;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        lo[rr] = p[rr * X];
+        hi[rr] = ph[rr * X];
+    }
+    const float c1 = (float)(wr.invW * wr.os);
+    int keep = 0;
+#pragma unroll
+    for (int rr = 0; rr < kBlock; ++rr) {
+        const float Df = ((hi[rr] - lo[rr]) + Wmu32) * c1, aD = fabsf(Df), aA = fabsf(A[rr]);
+        const float R = Df * fmaf(-Df, A[rr], 2.f * B[rr]);
+        const float t = fmaf(aD, aA, 2.f * fabsf(B[rr]));  // |D| |A| + 2 |B|
+        float m = fmaf(aD * t, 2e-6f, fmaf(aD, fmaf(aD, EAf, EB2f), slopTf));
+        m = fmaf(dD, fmaf(aD, aA, t) + dD * aA, m);  // dD (2 |B| + 2 |D| |A| + dD |A|)
+        keep |= (R + m < G32 ? 0 : 1) << rr;
+    }
+    if (wr.L < wr.W) keep = -1;  // the untouched tail adds to R: no screen for trimmed templates (rare)
+    return keep & mask;
+}
+
+// bound_one for unequal weights: chi2 = T + D (D A - 2 B) from the fp32 correlations, |A32 - A64| <= EA, |B32 - B64| <= EB;
+// the untouched tail of a trimmed template is sum (w d)^2 / w over the fp32 samples.
+__device__ __noinline__ float bound_one_w(const double *cs64, int i, int W, double depth_min, float A, float B, double invW,
+                                          double os, double EA, double EB, double T, const float *wd32, const float *w32,
+                                          int k_tail, int n_tail, FilterShared *fs)
+{
+    const double diff = __ldcg(cs64 + i + W) - __ldcg(cs64 + i);
+    if (!(diff * invW > depth_min)) return INFINITY;  // the exact gate (helpers.py:70-73 + core.py:58)
+    const double D = diff * invW * os;
+    const double Ad = (double)A, Bd = (double)B;
+    const double chi = chi2_value(T, D, Ad, Bd);
+    const double E = 2.0 * fabs(D) * EB + D * D * EA + 1e-14 * (fabs(T) + fabs(D) * (fabs(D) * fabs(Ad) + 2.0 * fabs(Bd)));
+    double l = chi - E, h = chi + E;
+    if (n_tail > 0) {
+        float rest = 0.f;
+        for (int k = k_tail; k < k_tail + n_tail; ++k) rest += wd32[k] * wd32[k] / w32[k];
+        const double tail = (double)rest, e = (double)(n_tail + 8) * 2.4e-7;
+        l -= tail * (1.0 + e);
+        h -= tail * (1.0 - e);
+    }
+    if (h > 0.0) atomicMin(&fs->U, (unsigned long long)__double_as_longlong(h));  // NaN compares false: no update
+    return __double2float_rd(l);
+}
+
 // What the cold paths of a sweep need, gathered once per sweep (lives in local memory)
 template <bool kGather>
 struct FilterCtx {
@@ -892,12 +1078,13 @@ struct FilterCtx {
     int fq_cap;
     unsigned long long *stats;
     Gate32 g32;  // the fp32 gate's parameters of this period (mu, err, depth_min)
+    double ea_scale;  // unequal weights: max w (the scale of the bound on |A32 - A64|)
 };
 
 // Finalists of one batch (bit rr of `fin`, lower bounds rounded down to fp32) go to the finalist queue once more
 // checked against the threshold as it is NOW; the bound travels with them and is checked a last time before the
 // exact evaluation.  All 32 lanes must call.  Queue full (rare): the warp evaluates the leftovers on the spot.
-template <int kBlock, bool kGather>
+template <int kBlock, bool kGather, bool kUW = true>
 __device__ __noinline__ void warp_push(const FilterCtx<kGather> &cx, int fin, int c0, int u, float l0, float l1, float l2,
                                        float l3, float l4, float l5, float l6, Best &best)
 {
@@ -923,7 +1110,7 @@ __device__ __noinline__ void warp_push(const FilterCtx<kGather> &cx, int fin, in
         const int oc0 = __shfl_sync(kFull, c0, src), ou = __shfl_sync(kFull, u, src), oo = __shfl_sync(kFull, over, src);
         for (int rr = 0; rr < kBlock; ++rr)
             if ((oo >> rr) & 1) {
-                eval_exact_warp<kGather>(cx.view, cx.rec, oc0, rr, ou, best);
+                eval_exact_warp<kGather, kUW>(cx.view, cx.rec, oc0, rr, ou, best);
                 if (cx.stats && (threadIdx.x & 31) == 0) atomicAdd(cx.stats + 2, 1ull);
             }
         any &= any - 1;
@@ -933,7 +1120,7 @@ __device__ __noinline__ void warp_push(const FilterCtx<kGather> &cx, int fin, in
 // The queued finalists, one per warp at a time (call after a barrier, all threads of the CTA): each is checked
 // against the current threshold once more (most were queued while it was still settling), evaluated in fp64, and
 // its exact chi2 tightens the threshold for the rest.
-template <int kT, bool kGather>
+template <int kT, bool kGather, bool kUW = true>
 __device__ __forceinline__ void drain_finalists(const FilterCtx<kGather> &cx, Best &best)
 {
     constexpr int kW = kT / 32;
@@ -944,7 +1131,7 @@ __device__ __forceinline__ void drain_finalists(const FilterCtx<kGather> &cx, Be
         if ((double)cx.fq_lo[k] > U) continue;
         const int2 e = cx.fq[k];
         const double before = best.chi2;
-        eval_exact_warp<kGather>(cx.view, cx.rec, e.x, e.y >> 16, e.y & 0xffff, best);
+        eval_exact_warp<kGather, kUW>(cx.view, cx.rec, e.x, e.y >> 16, e.y & 0xffff, best);
         if (lane == 0 && best.chi2 < before && best.chi2 > 0.0)
             atomicMin(&cx.fs->U, (unsigned long long)__double_as_longlong(best.chi2));
         if (cx.stats && lane == 0) atomicAdd(cx.stats + 1, 1ull);
@@ -963,21 +1150,22 @@ struct Pending {
 #pragma unroll
         for (int rr = 0; rr < kBlock; ++rr) lo[rr] = 0.f;
     }
-    template <bool kGather>
+    __device__ __forceinline__ float at(int k) const { return k < kBlock ? lo[k < kBlock ? k : 0] : 0.f; }
+    template <bool kGather, bool kUW = true>
     __device__ __forceinline__ void push(const FilterCtx<kGather> &cx, Best &best)  // all 32 lanes must call
     {
         if (__any_sync(kFull, fin != 0))
-            warp_push<kBlock, kGather>(cx, fin, c0, u, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], best);
+            warp_push<kBlock, kGather, kUW>(cx, fin, c0, u, at(0), at(1), at(2), at(3), at(4), at(5), at(6), best);
         fin = 0;
     }
 };
 
 // One batch of survivor blocks (one per lane, `have`): fp32 correlation, fp32 screen, exact gate + exact bounds for
 // what the screen lets through; then the PREVIOUS batch's finalists are pushed and this batch's become pending.
-template <int kBlock, bool kGather>
+template <int kBlock, bool kGather, bool kUW = true>
 __device__ __forceinline__ void tap_batch(bool have, int2 e, const FilterCtx<kGather> &cx, const float *cs32, const float *wd32,
                                           const float *__restrict__ tq32, double w0, double T, double eb_scale, float slopTf,
-                                          Threshold &th, Pending<kBlock> &pend, Best &best)
+                                          Threshold &th, Pending<kBlock> &pend, Best &best, const float *w32 = nullptr)
 {
     int fin = 0;
     float lo_now[kBlock];
@@ -993,29 +1181,49 @@ __device__ __forceinline__ void tap_batch(bool have, int2 e, const FilterCtx<kGa
         const float Wmu32 = (float)wmu;
         const float dD = __double2float_ru((cx.g32.err + 6.1e-8 * fabs(wmu)) * (wr.invW * wr.os) * 1.00001);
         float B[kBlock];
+        float A[kBlock];  // unequal weights only
+        double EA = 0.0;
         th.refresh(cx.fs, T);
         int keep;
-        if (wr.X == 1) {
-            tap_block32<kBlock, true>(wr, tq32, wd32, e.x, B);
-            keep = block_screen<kBlock, true>(wr, cs32, w0, e.x, mask, B, th.G32, EB2f, slopTf, Wmu32, dD);
+        if constexpr (kUW) {
+            if (wr.X == 1) {
+                tap_block32<kBlock, true>(wr, tq32, wd32, e.x, B);
+                keep = block_screen<kBlock, true>(wr, cs32, w0, e.x, mask, B, th.G32, EB2f, slopTf, Wmu32, dD);
+            } else {
+                tap_block32<kBlock, false>(wr, tq32, wd32, e.x, B);
+                keep = block_screen<kBlock, false>(wr, cs32, w0, e.x, mask, B, th.G32, EB2f, slopTf, Wmu32, dD);
+            }
         } else {
-            tap_block32<kBlock, false>(wr, tq32, wd32, e.x, B);
-            keep = block_screen<kBlock, false>(wr, cs32, w0, e.x, mask, B, th.G32, EB2f, slopTf, Wmu32, dD);
+            // |A32 - A64| <= EA: the same chain bound as for B with q^2 (three fp32 roundings: L + 12 units) and max w
+            EA = (double)(wr.L + 12) * 5.9604644775390625e-08 * wr.sq2 * (1.0 + 1e-6) * cx.ea_scale;
+            const float EAf = __double2float_ru(1.000001 * EA);
+            if (wr.X == 1) {
+                tap_block32w<kBlock, true>(wr, tq32, wd32, w32, e.x, A, B);
+                keep = block_screen_w<kBlock, true>(wr, cs32, e.x, mask, A, B, th.G32, EB2f, EAf, slopTf, Wmu32, dD);
+            } else {
+                tap_block32w<kBlock, false>(wr, tq32, wd32, w32, e.x, A, B);
+                keep = block_screen_w<kBlock, false>(wr, cs32, e.x, mask, A, B, th.G32, EB2f, EAf, slopTf, Wmu32, dD);
+            }
         }
         if (keep) {  // rare
             const double Aq = w0 * wr.sq2;
 #pragma unroll
             for (int rr = 0; rr < kBlock; ++rr)
-                if ((keep >> rr) & 1)
-                    lo_now[rr] = bound_one(cx.view.cs, (e.x + rr) * wr.X, wr.W, cx.g32.depth_min, B[rr], wr.invW, wr.os, Aq, EB, T,
-                                           w0, wd32, (e.x + rr) * wr.X + wr.L, wr.W - wr.L, cx.fs);
+                if ((keep >> rr) & 1) {
+                    if constexpr (kUW)
+                        lo_now[rr] = bound_one(cx.view.cs, (e.x + rr) * wr.X, wr.W, cx.g32.depth_min, B[rr], wr.invW, wr.os, Aq, EB, T,
+                                               w0, wd32, (e.x + rr) * wr.X + wr.L, wr.W - wr.L, cx.fs);
+                    else
+                        lo_now[rr] = bound_one_w(cx.view.cs, (e.x + rr) * wr.X, wr.W, cx.g32.depth_min, A[rr], B[rr], wr.invW, wr.os,
+                                                 EA, EB, T, wd32, w32, (e.x + rr) * wr.X + wr.L, wr.W - wr.L, cx.fs);
+                }
             th.refresh(cx.fs, T);
 #pragma unroll
             for (int rr = 0; rr < kBlock; ++rr) fin |= (((keep >> rr) & 1) && !((double)lo_now[rr] > th.U) ? 1 : 0) << rr;
         }
         if (cx.stats) atomicAdd(cx.stats, (unsigned long long)__popc(mask));
     }
-    pend.push(cx, best);  // the previous batch's finalists, against the threshold as it is now
+    pend.template push<kGather, kUW>(cx, best);  // the previous batch's finalists, against the threshold as it is now
     pend.fin = fin;
     pend.c0 = e.x;
     pend.u = e.y & 0xffff;
@@ -1042,13 +1250,13 @@ struct SweepShared {
 // ub-1 and cover its candidates [t_lo, t_hi), and so on downwards.  Finalists are pushed one batch late, so that
 // their bounds meet a threshold every active warp has contributed to.  Ends with the finalist queue drained
 // (contains barriers: all threads of the CTA must call).  cs / wd32 must be indexable by global offsets.
-template <int kT, int kBlock, bool kGather>
+template <int kT, int kBlock, bool kGather, bool kUW = true>
 __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int qmask, int tile_end, int ub, const int *t_lo,
                                              const int *t_hi, const int *t_tiles, const WidthRec *rec, const float *cs32,
                                              const float *wd32, const float *__restrict__ tq32, double w0, double T,
                                              const Gate32 &g32, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo,
                                              int fq_cap, const ExactView<kGather> &view, Best &best,
-                                             unsigned long long *stats)
+                                             unsigned long long *stats, const float *w32 = nullptr, double ea_scale = 0.0)
 {
     constexpr int kW = kT / 32;
     constexpr int kTile = tile_size(kBlock);
@@ -1057,6 +1265,7 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
     const int qroom = qmask + 1 - kW * 32 * kSub;  // gating pauses above this fill: every warp can still add one tile
     FilterCtx<kGather> cx;
     cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats; cx.g32 = g32;
+    cx.ea_scale = ea_scale;
     Threshold th;
     th.set(INFINITY, T);
     th.refresh(fs, T);
@@ -1103,7 +1312,7 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
             }
             __syncwarp();
             if (lane == 0) atomicAdd(&ss->q_done, n);
-            tap_batch<kBlock, kGather>(have, e, cx, cs32, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
+            tap_batch<kBlock, kGather, kUW>(have, e, cx, cs32, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best, w32);
             continue;
         }
         if (do_gate) {
@@ -1162,23 +1371,25 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
         if (++idle > (1 << 24)) __trap();  // never seen; a hang here would take the GPU with it
         __nanosleep(20);
     }
-    pend.push(cx, best);
+    pend.template push<kGather, kUW>(cx, best);
     __syncthreads();  // every finalist of this sweep is in the queue
-    drain_finalists<kT, kGather>(cx, best);
+    drain_finalists<kT, kGather, kUW>(cx, best);
 }
 
 // The same work with the classic schedule, for layouts with two CTAs per SM (the other CTA fills this one's barrier
 // waits, and short batches make the ring's bookkeeping the larger cost): one ROUND of the survivor queue, filled by
 // the gate before a barrier; warps take batches of 32 entries until the queue is empty, then drain the finalists.
-template <int kT, int kBlock, bool kGather>
+template <int kT, int kBlock, bool kGather, bool kUW = true>
 __device__ __forceinline__ void filter_round(const int2 *queue, int qfill, int *q_head, const WidthRec *rec, const float *cs32,
                                              const float *wd32, const float *__restrict__ tq32, double w0, double T,
                                              const Gate32 &g32, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo,
-                                             int fq_cap, const ExactView<kGather> &view, Best &best, unsigned long long *stats)
+                                             int fq_cap, const ExactView<kGather> &view, Best &best, unsigned long long *stats,
+                                             const float *w32 = nullptr, double ea_scale = 0.0)
 {
     const int lane = threadIdx.x & 31;
     FilterCtx<kGather> cx;
     cx.view = view; cx.rec = rec; cx.fs = fs; cx.fq = fq; cx.fq_lo = fq_lo; cx.fq_cap = fq_cap; cx.stats = stats; cx.g32 = g32;
+    cx.ea_scale = ea_scale;
     Threshold th;
     th.set(INFINITY, T);
     th.refresh(fs, T);
@@ -1192,11 +1403,11 @@ __device__ __forceinline__ void filter_round(const int2 *queue, int qfill, int *
         if (h >= qfill) break;
         const bool have = h + lane < qfill;
         const int2 e = have ? queue[h + lane] : make_int2(0, 0);
-        tap_batch<kBlock, kGather>(have, e, cx, cs32, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best);
+        tap_batch<kBlock, kGather, kUW>(have, e, cx, cs32, wd32, tq32, w0, T, eb_scale, slopTf, th, pend, best, w32);
     }
-    pend.push(cx, best);
+    pend.template push<kGather, kUW>(cx, best);
     __syncthreads();  // every finalist of this round is in the queue
-    drain_finalists<kT, kGather>(cx, best);
+    drain_finalists<kT, kGather, kUW>(cx, best);
 }
 
 // max |x_k| over k < n, the same value in every thread (all threads must call; scratch: kT/32 doubles, shared)
@@ -1215,6 +1426,30 @@ __device__ double block_max_abs(const double *__restrict__ x, int n, double *scr
     for (int k = 0; k < kT / 32; ++k) r = fmax(r, scratch[k]);
     __syncthreads();
     return r;
+}
+
+// max |x_k y_k| and max |y_k| over k < n, the same values in every thread (unequal weights: the scales of the filter's bounds)
+template <int kT>
+__device__ void block_max_abs2(const double *__restrict__ x, const double *__restrict__ y, int n, double *scratch, double &mxy, double &my)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double a = 0.0, b = 0.0;
+    for (int k = tid; k < n; k += kT) {
+        const double yk = __ldg(y + k);
+        a = fmax(a, fabs(__ldg(x + k) * yk));
+        b = fmax(b, fabs(yk));
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        a = fmax(a, __shfl_xor_sync(kFull, a, off));
+        b = fmax(b, __shfl_xor_sync(kFull, b, off));
+    }
+    __syncthreads();
+    if (lane == 0) { scratch[wid] = a; scratch[kT / 32 + wid] = b; }
+    __syncthreads();
+    mxy = 0.0; my = 0.0;
+    for (int k = 0; k < kT / 32; ++k) { mxy = fmax(mxy, scratch[k]); my = fmax(my, scratch[kT / 32 + k]); }
+    __syncthreads();
 }
 
 // mean of x_k over k < n, the same value in every thread (all threads must call; scratch: kT/32 doubles, shared).  Only used

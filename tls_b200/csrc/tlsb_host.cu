@@ -291,13 +291,15 @@ size_t tail_bytes(int nU, int threads) { return filter_tail_bytes(nU, threads); 
 // resident layout with the fp32 filter pass (equal weights): cs | sorted ids (u16) | tail | area, the area being the
 // larger of the sort's scratch (keys, histogram with N buckets, bucket-ordered ids) and the search's arrays (w*d in
 // fp32, survivor queue, finalist queue); mirrors the carve in tlsb_search_kernel
-size_t resident_filter_smem_bytes(int N, int M, int pad, int nU, int qcap, int fq_cap, int threads, int NB)
+size_t resident_filter_smem_bytes(int N, int M, int pad, int nU, int qcap, int fq_cap, int threads, int NB, bool uniform = true)
 {
     const size_t NM = (size_t)N + M, NMP = NM + pad;
-    // X: the sorted d / fp64 cumulative sums while they are built, the survivor queue afterwards
-    const size_t x = align16(std::max(((NM + 2) & ~(size_t)1), (size_t)qcap) * 8);
+    // X: the sorted d / fp64 cumulative sums while they are built, the survivor queue afterwards (unequal weights: the
+    // finalist queue too, because the area then holds a third fp32 array, w32)
+    const size_t x = align16(std::max(((NM + 2) & ~(size_t)1) * 8, (size_t)qcap * 8 + (uniform ? 0 : (size_t)fq_cap * 12)));
     const size_t sort_area = (size_t)N * 8 + (((size_t)NB + 2) / 2) * 4 + (size_t)N * 2;  // 16-bit bucket counters
-    const size_t search_area = ((NM + 2 + 3) & ~(size_t)3) * 4 + ((NMP + 3) & ~(size_t)3) * 4 + (size_t)fq_cap * 12;
+    const size_t nmp4 = ((NMP + 3) & ~(size_t)3) * 4;
+    const size_t search_area = ((NM + 2 + 3) & ~(size_t)3) * 4 + (uniform ? nmp4 + (size_t)fq_cap * 12 : 2 * nmp4);
     return x + align16((size_t)N * 2) + tail_bytes(nU, threads) + align16(std::max(sort_area, search_area));
 }
 
@@ -344,6 +346,29 @@ Layout choose_layout(const tlsb_handle *h)
             return best;
         }
     }
+    const char *wf = std::getenv("TLSB_WFILTER");  // "0": unequal weights keep the all-fp64 kernels (experiments / A-B runs)
+    if (N < 65536 && h->path_mode <= 1 && !h->uniform_w && !(wf && std::atoi(wf) == 0)) {
+        // unequal weights: fp32 gate + two fp32 correlations (R = 5); cs32, wd32, w32 and the sorted ids stay on chip
+        const int tries[5][5] = {{256, 2, 3584, 832, 1}, {256, 2, 3072, 512, 1}, {256, 2, 3072, 512, 2}, {512, 1, 8192, 2048, 1},
+                                 {512, 1, 4096, 1024, 1}};
+        const int cs_elems = (N + h->M + 2) & ~1;
+        for (const auto &t : tries) {
+            const int NB = std::max(64, 2 * (N / t[4]));
+            const size_t bytes = resident_filter_smem_bytes(N, h->M, h->pad, h->nU, t[2], t[3], t[0], NB, false);
+            if (bytes > h->max_smem) continue;
+            if ((bytes + 1024) * (size_t)t[1] > h->smem_per_sm) continue;
+            best.kb = 5;
+            best.resident = true;
+            best.threads = t[0];
+            best.ctas_per_sm = t[1];
+            best.qcap = t[2];
+            best.fq_cap = t[3];
+            best.NB = NB;
+            best.smem = bytes;
+            best.scratch_per_cta = ((size_t)cs_elems * 8 + 255) & ~(size_t)255;
+            return best;
+        }
+    }
     if (N < 65536 && h->path_mode <= 1) {
         const int tries[2][2] = {{256, 2}, {512, 1}};
         const int qcaps[3] = {4096, 3584, 3072};
@@ -375,10 +400,12 @@ Layout choose_layout(const tlsb_handle *h)
     const int narr = h->uniform_w ? 2 : 3;
     // bytes a folded sample takes in a staged chunk: detrended cs in fp32 (4) + w*d in fp32 (4) with equal weights
     // (fp32 gate + filter pass), cs + w + w*d in fp64 otherwise
-    const size_t elem = h->uniform_w ? 8 : 24;
+    const bool wfilter = !h->uniform_w && !(wf && std::atoi(wf) == 0);  // unequal weights with the fp32 gate + filter pass
+    const bool filt = h->uniform_w || wfilter;
+    const size_t elem = h->uniform_w ? 8 : wfilter ? 12 : 24;
     const size_t nmp4 = (NMP + 3) & ~(size_t)3;
     const size_t cs4 = (NM + 2 + 3) & ~(size_t)3;
-    const int fq_cap = h->uniform_w ? 1024 : 0;
+    const int fq_cap = filt ? 1024 : 0;
     int need_max = 0, need5 = 0;
     for (const WidthRec &wr : h->recs) {
         need_max = std::max(need_max, window_need(wr.W, wr.X, kb_pref));
@@ -388,7 +415,7 @@ Layout choose_layout(const tlsb_handle *h)
     const int forced = force ? std::atoi(force) : -1;
     if (forced != 0 && h->path_mode != 3) {
         // threads, CTAs per SM, queue entries (equal weights: a ring, power of two)
-        const int tries[2][3] = {{256, 2, h->uniform_w ? 2048 : 3072}, {512, 1, 4096}};
+        const int tries[2][3] = {{256, 2, filt ? 2048 : 3072}, {512, 1, 4096}};
         for (const auto &t : tries) {
             if (forced > 0 && forced != t[0]) continue;
             size_t per_cta = std::min(h->max_smem, h->smem_per_sm / (size_t)t[1] - 1024);
@@ -459,7 +486,8 @@ Layout choose_layout(const tlsb_handle *h)
             best.NB = (int)std::min<long long>(N, (long long)(elem * (size_t)C / 4) - 2);
             best.smem = (size_t)t[2] * 8 + (size_t)fq_cap * 12 + elem * (size_t)C + tail_bytes(h->nU, t[0]) + (size_t)h->nU * 12 + 128 +
                         (size_t)(kMaxSegments + 2) * 4;
-            best.scratch_per_cta = cs + (size_t)(narr - 1) * nmp_even * 8 + (h->uniform_w ? (cs4 + nmp4) * 4 : 0) + align16((size_t)N * 4);
+            best.scratch_per_cta = cs + (size_t)(narr - 1) * nmp_even * 8 +
+                                   (h->uniform_w ? (cs4 + nmp4) * 4 : wfilter ? (cs4 + 2 * nmp4) * 4 : 0) + align16((size_t)N * 4);
             // on-chip sort: segments of S keys sorted in the chunk area; 1.5x head room over N / n_seg
             const char *oc = std::getenv("TLSB_ONCHIP_SORT");  // "0" disables (experiments)
             const size_t area = elem * (size_t)C;

@@ -5,7 +5,10 @@
 
 namespace {
 
-template <int kT, bool kResident, bool kUniformW, int kBlock>
+// kFilt: the fp32 gate + fp32 filter pass with exact fp64 evaluation of the finalists (resident layouts; with unequal
+// weights two fp32 correlations).  Without it (streaming layout; unequal weights when the filter layout does not fit)
+// every gate survivor is evaluated in fp64 by tap_block / block_min.
+template <int kT, bool kResident, bool kUniformW, int kBlock, bool kFilt = (kResident && kUniformW)>
 __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(const __grid_constant__ SearchArgs a)
 {
     constexpr int kW = kT / 32;
@@ -27,14 +30,15 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     // read them, from L2) - after that X is the survivor queue.  The area holds the sort's keys, histogram and
     // bucket-ordered ids first and then what the search reads: cs32 (detrended cumulative sums in fp32: the gate and the
     // screen), wd32 (the products w*d rounded to fp32: the taps) and the finalist queue.
-    constexpr bool kFilter = kResident && kUniformW;
+    constexpr bool kFilter = kFilt;
+    static_assert(!kFilt || kResident, "the filter layouts keep the folded curve in shared memory");
     const size_t cs_elems = (size_t)(NM + 2) & ~(size_t)1;
     double *cs, *w, *wd;
     idx_t *sid;
     int *H;
     int2 *queue;
     unsigned char *tail;
-    float *wd32 = nullptr, *cs32 = nullptr;
+    float *wd32 = nullptr, *cs32 = nullptr, *w32 = nullptr;
     double *cs64g = nullptr;
     idx_t *sid_sorted = nullptr;
     int2 *fq = nullptr;
@@ -44,7 +48,9 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         cs = reinterpret_cast<double *>(smem_raw);
         w = wd = nullptr;
         queue = reinterpret_cast<int2 *>(smem_raw);
-        const size_t xbytes = ((cs_elems > (size_t)a.qcap ? cs_elems : (size_t)a.qcap) * 8 + 15) & ~(size_t)15;
+        // unequal weights: the finalist queue follows the survivor queue inside X (the area holds a third fp32 array, w32)
+        const size_t qbytes = (size_t)a.qcap * 8 + (kUniformW ? 0 : (size_t)a.fq_cap * 12);
+        const size_t xbytes = ((cs_elems * 8 > qbytes ? cs_elems * 8 : qbytes) + 15) & ~(size_t)15;
         sid_sorted = reinterpret_cast<idx_t *>(smem_raw + xbytes);
         tail = reinterpret_cast<unsigned char *>(sid_sorted) + (((size_t)N * sizeof(idx_t) + 15) & ~(size_t)15);
         unsigned char *area = tail + filter_tail_bytes(nU, kT);
@@ -53,7 +59,12 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         sid = reinterpret_cast<idx_t *>(H + (NB + 2) / 2);
         cs32 = reinterpret_cast<float *>(area);
         wd32 = cs32 + (((size_t)NM + 2 + 3) & ~(size_t)3);
-        fq = reinterpret_cast<int2 *>(wd32 + (((size_t)NMP + 3) & ~(size_t)3));
+        if (kUniformW) {
+            fq = reinterpret_cast<int2 *>(wd32 + (((size_t)NMP + 3) & ~(size_t)3));
+        } else {
+            w32 = wd32 + (((size_t)NMP + 3) & ~(size_t)3);
+            fq = queue + a.qcap;
+        }
         fq_lo = reinterpret_cast<float *>(fq + a.fq_cap);
         cs64g = reinterpret_cast<double *>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta);
     } else if (kResident) {
@@ -99,11 +110,16 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
     const double depth_min = a.depth_min;
     const int qstop = a.qcap - kW * 32 * kSub;  // gating pauses here: every warp can still add one tile
     // filter pass: scale of the error bound = max |w d| over the light curve (period independent)
-    double eb_scale = 0.0;
+    double eb_scale = 0.0, ea_scale = 0.0;  // max |w d| and (unequal weights) max w over the light curve
     Gate32 g32;
     g32.mu = 0.0; g32.err = 0.0; g32.depth_min = depth_min;
     if (kFilter) {
-        eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
+        if (kUniformW) {
+            eb_scale = a.w0 * block_max_abs<kT>(a.dval, N, red_d);
+        } else {
+            block_max_abs2<kT>(a.dval, a.wval, N, red_d, eb_scale, ea_scale);
+        }
+        if (!a.filter) eb_scale = ea_scale = INFINITY;
         g32.mu = block_mean<kT>(a.dval, N, red_d);
     }
 
@@ -138,14 +154,15 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         }
 
         // ---- A. fold + stable bucket-rank sort + gather --------------------------------
-        fold_sort_gather<kT, idx_t, !kUniformW, false, (kResident ? kResSortU : 4), (kResident ? kResHScanItems : kScanItems), kFilter, kFilter>(
+        fold_sort_gather<kT, idx_t, (!kUniformW && !kFilter), false, (kResident ? kResSortU : 4), (kResident ? kResHScanItems : kScanItems), kFilter, kFilter>(
             a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval, cs + 1, w, reinterpret_cast<int *>(red_d), sid_sorted);
         if (tid == 0) cs[0] = 0.0;
         __syncthreads();  // the sorted d sit in cs[1..N]; the keys (in the wd area) are dead
         float cmax = 0.f;
         if (kFilter && tid == 0) cs32[0] = 0.f;
-        double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems), !kFilter, kFilter, kFilter>(
-            cs + 1, w, wd, a.w0, N, NM, NMP, red_d, 0, 0.0, wd32, cs32 + 1, g32.mu, &cmax);
+        double tpart = wrap_weight_scan<kT, kUniformW, (kResident ? kResScanItems : kScanItems), !kFilter, kFilter, kFilter,
+                                        (kFilter && !kUniformW), idx_t>(
+            cs + 1, w, wd, a.w0, N, NM, NMP, red_d, 0, 0.0, wd32, cs32 + 1, g32.mu, &cmax, a.wval, sid_sorted, w32);
         if (kFilter) {  // the fp64 cumulative sums leave the SM: only bound_one / eval_exact_warp read them again (L2)
             for (int k = tid; k <= NM; k += kT) __stcg(cs64g + k, cs[k]);
 #pragma unroll
@@ -186,14 +203,14 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         ExactView<true> view;
         if (kFilter) {
             view.cs = cs64g; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
-            view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
+            view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N; view.wval = a.wval; view.w = nullptr;
         }
         if constexpr (kDynamic) {
             // B1 + B2 as one barrier-free sweep: warps switch between gating tiles and taking batches of survivors
             // (fp32 correlation, screen, bounds); finalists are evaluated in fp64 by whole warps at the end
             const int tile_total = rec[ulo].cum + rec[ulo].tiles - rec[uhi - 1].cum;
-            sweep_filter<kT, kBlock, true>(ss, queue, a.qcap - 1, tile_total, uhi, t_lo, t_hi, t_tiles, rec, cs32, wd32, a.tq32, a.w0, T,
-                                           g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
+            sweep_filter<kT, kBlock, true, kUniformW>(ss, queue, a.qcap - 1, tile_total, uhi, t_lo, t_hi, t_tiles, rec, cs32, wd32, a.tq32,
+                                                      a.w0, T, g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats, w32, ea_scale);
         } else {
             const int tile_end = rec[ulo].cum + rec[ulo].tiles;
             int g_next = rec[uhi - 1].cum + wid;
@@ -265,8 +282,8 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
                 const bool more = s_next[1] != 0;
                 // B2
                 if constexpr (kFilter) {
-                    filter_round<kT, kBlock, true>(queue, qfill, &s_next[3], rec, cs32, wd32, a.tq32, a.w0, T, g32, eb_scale, fs, fq,
-                                                   fq_lo, a.fq_cap, view, best, a.stats);
+                    filter_round<kT, kBlock, true, kUniformW>(queue, qfill, &s_next[3], rec, cs32, wd32, a.tq32, a.w0, T, g32, eb_scale, fs,
+                                                              fq, fq_lo, a.fq_cap, view, best, a.stats, w32, ea_scale);
                 } else
                 for (;;) {
                     int h = 0;
@@ -381,10 +398,12 @@ cudaError_t launch_search_resident(const SearchArgs &a, int threads, bool reside
         if (threads == 256) {
             if (uni && kb == 7) TLSB_GO((tlsb_search_kernel<256, true, true, 7>));
             else if (uni) TLSB_GO((tlsb_search_kernel<256, true, true, 5>));
+            else if (a.fq_cap > 0) TLSB_GO((tlsb_search_kernel<256, true, false, 5, true>));
             else TLSB_GO((tlsb_search_kernel<256, true, false, 5>));
         } else {
             if (uni && kb == 7) TLSB_GO((tlsb_search_kernel<512, true, true, 7>));
             else if (uni) TLSB_GO((tlsb_search_kernel<512, true, true, 5>));
+            else if (a.fq_cap > 0) TLSB_GO((tlsb_search_kernel<512, true, false, 5, true>));
             else TLSB_GO((tlsb_search_kernel<512, true, false, 5>));
         }
     } else {

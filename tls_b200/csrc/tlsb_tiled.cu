@@ -23,11 +23,11 @@ namespace {
 // continued from the previous segment, and the first M samples stashed behind position N for the
 // wrap (core.py:126-132).  Returns false (nothing consumed) if a segment overflows its capacity -
 // strongly clustered phases - and the caller then sorts in global scratch instead.
-template <int kT, bool kUniformW>
+template <int kT, bool kUniformW, bool kFilt>
 __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsigned char *area, int *cnt,
                                              double *gkey, unsigned *gid, double *cs1, double *w, double *wd, float *wd32,
                                              int nmp_even, double *red_d, double &tpart_out, float *cs32_1, double mu,
-                                             float &cmax_out)
+                                             float &cmax_out, float *w32)
 {
 #ifndef TLSB_SEG_RANK_U
 #define TLSB_SEG_RANK_U 4
@@ -191,9 +191,10 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
             const double wv = kUniformW ? a.w0 : wv_s[q];
             const double x = wv * d;
             wd[pos] = x;
-            if (kUniformW) wd32[pos] = (float)x;  // the filter pass's samples
+            if (kFilt) wd32[pos] = (float)x;  // the filter pass's samples
             tpart = fma(x, d, tpart);
             if (!kUniformW) w[pos] = wv;
+            if (kFilt && !kUniformW) w32[pos] = (float)wv;
             if (pos < M) {
                 cs1[N + pos] = d;
                 if (!kUniformW) w[N + pos] = wv;
@@ -204,7 +205,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         for (int q = tid; q < nj; q += kT) {
             const double c = carry + val_s[q];
             cs1[off + q] = c;
-            if (kUniformW) {  // the detrended fp32 copy the gate and the screen read (tlsb_device.cuh: fp32 gate)
+            if (kFilt) {  // the detrended fp32 copy the gate and the screen read (tlsb_device.cuh: fp32 gate)
                 const float c32 = (float)fma(-(double)(off + q + 1), mu, c);
                 cs32_1[off + q] = c32;
                 cmax = fmaxf(cmax, fabsf(c32));
@@ -216,16 +217,19 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     }
     // positions N .. NM-1 hold the wrapped d: continue the cumulative sum, weight them, zero the slack
     float cmax2 = 0.f;
-    wrap_weight_scan<kT, kUniformW, kSegScanItems, true, kUniformW, kUniformW>(cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry, wd32,
-                                                                              cs32_1, mu, &cmax2);
+    wrap_weight_scan<kT, kUniformW, kSegScanItems, true, kFilt, kFilt, false, unsigned short, (kFilt && !kUniformW)>(
+        cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry, wd32, cs32_1, mu, &cmax2, nullptr, nullptr, w32);
     tpart_out = tpart;
     cmax_out = fmaxf(cmax, cmax2);
     return true;
 }
 
-template <int kT, bool kUniformW, int kBlock>
+// kFilt: fp32 gate + fp32 filter pass from chunks of cs32 / wd32 (/ w32 with unequal weights), exact fp64 evaluation of
+// the finalists from the CTA's scratch; without it (unequal weights, TLSB_WFILTER=0) chunks of cs / w / w*d in fp64.
+template <int kT, bool kUniformW, int kBlock, bool kFilt = kUniformW>
 __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_kernel(const __grid_constant__ SearchArgs a)
 {
+    static_assert(kFilt || !kUniformW, "equal weights always take the filter");
     constexpr int kW = kT / 32;
     constexpr int kTile = tile_size(kBlock);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -247,7 +251,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     // equal weights: the detrended cumulative sums and the products w*d rounded to fp32 (what the chunks stage)
     float *cs32 = reinterpret_cast<float *>(wd + nmp_even);
     float *wd32 = cs32 + cs4;
-    unsigned *sid = kUniformW ? reinterpret_cast<unsigned *>(wd32 + nmp4) : reinterpret_cast<unsigned *>(wd + nmp_even);
+    float *w32 = wd32 + nmp4;  // unequal weights only
+    unsigned *sid = !kFilt ? reinterpret_cast<unsigned *>(wd + nmp_even)
+                           : reinterpret_cast<unsigned *>(kUniformW ? wd32 + nmp4 : w32 + nmp4);
     double *skey = wd;  // the sort keys borrow the wd area; the sorted d go straight to cs[1..N]
 
     // ---- shared: queue | finalist queue | chunk of cs | chunk of w*d in fp32 (equal weights) or chunks of w and w*d
@@ -255,14 +261,17 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     int2 *queue = reinterpret_cast<int2 *>(smem_raw);
     int2 *fq = queue + a.qcap;
     float *fq_lo = reinterpret_cast<float *>(fq + a.fq_cap);
-    // equal weights: chunks of cs32 and wd32 (8 bytes per folded sample); else chunks of cs, w, w*d in fp64 (24 bytes)
+    // filter layouts: chunks of cs32 and wd32 (8 bytes per folded sample; 12 with w32 for unequal weights); else chunks of
+    // cs, w, w*d in fp64 (24 bytes)
     double *cs_s = reinterpret_cast<double *>(fq_lo + a.fq_cap);
     double *w_s = cs_s + C;
     double *wd_s = kUniformW ? w_s : w_s + C;
     float *cs32_s = reinterpret_cast<float *>(cs_s);
     float *wd32_s = cs32_s + C;
+    float *w32_s = wd32_s + C;
     int *H = reinterpret_cast<int *>(cs_s);  // phase A only: the histogram borrows the chunk area
-    WidthRec *rec = kUniformW ? reinterpret_cast<WidthRec *>(wd32_s + C) : reinterpret_cast<WidthRec *>(wd_s + C);  // [nU]
+    WidthRec *rec = kFilt ? reinterpret_cast<WidthRec *>(kUniformW ? wd32_s + C : w32_s + C)
+                          : reinterpret_cast<WidthRec *>(wd_s + C);  // [nU]
     double *red_d = reinterpret_cast<double *>(rec + nU);                     // [2*kW + 2]
     FilterShared *fs = reinterpret_cast<FilterShared *>(red_d + 2 * kW + 2);
     SweepShared *ss = reinterpret_cast<SweepShared *>(fs + 1);
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
 
     for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
         reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
-    if (kUniformW)  // the survivor ring: a slot is valid when it is non-zero, readers clear it
+    if (kFilt)  // the survivor ring: a slot is valid when it is non-zero, readers clear it
         for (int k = tid; k < a.qcap; k += kT) reinterpret_cast<unsigned long long *>(queue)[k] = 0ull;
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -290,18 +299,20 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     const unsigned lt_mask = (1u << lane) - 1u;
     const double depth_min = a.depth_min;
     const int qstop = a.qcap - kW * 32 * kSub;
-    double eb_scale = 0.0;  // filter pass: scale of the error bound = max |w d| over the light curve
+    double eb_scale = 0.0, ea_scale = 0.0;  // filter pass: scales of the error bounds = max |w d| (and max w) over the light curve
     Gate32 g32;
     g32.mu = 0.0; g32.err = 0.0; g32.depth_min = depth_min;
-    if (kUniformW) {
-        eb_scale = a.filter ? a.w0 * block_max_abs<kT>(a.dval, N, red_d) : INFINITY;
+    if (kFilt) {
+        if (kUniformW) eb_scale = a.w0 * block_max_abs<kT>(a.dval, N, red_d);
+        else block_max_abs2<kT>(a.dval, a.wval, N, red_d, eb_scale, ea_scale);
+        if (!a.filter) eb_scale = ea_scale = INFINITY;
         g32.mu = block_mean<kT>(a.dval, N, red_d);
     }
 
     for (;;) {
         if (tid == 0) {
             s_next[0] = atomicAdd(a.counter, 1);
-            if (kUniformW) {
+            if (kFilt) {
                 fs->U = (unsigned long long)__double_as_longlong((double)N);  // core.py:46: a model must beat N to count
                 fs->fq_fill = 0;
             }
@@ -329,19 +340,19 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         float cmax = 0.f;
         if (tid == 0) {
             cs[0] = 0.0;
-            if (kUniformW) cs32[0] = 0.f;
+            if (kFilt) cs32[0] = 0.f;
         }
         bool on_chip = false;
         if (a.seg_cap > 0)
-            on_chip = sort_on_chip<kT, kUniformW>(a, r, reinterpret_cast<unsigned char *>(cs_s), seg_cnt, gkey, gid,
-                                                  cs + 1, w, wd, wd32, (int)nmp_even, red_d, tpart, cs32 + 1, g32.mu, cmax);
+            on_chip = sort_on_chip<kT, kUniformW, kFilt>(a, r, reinterpret_cast<unsigned char *>(cs_s), seg_cnt, gkey, gid,
+                                                         cs + 1, w, wd, wd32, (int)nmp_even, red_d, tpart, cs32 + 1, g32.mu, cmax, w32);
         if (!on_chip) {  // clustered phases (or no room for segments): sort in the global scratch
             if (tid == 0 && a.seg_cap > 0) atomicAdd(a.counter + 4, 1);
             fold_sort_gather<kT, unsigned, !kUniformW, false, 8>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval,
                                                                  cs + 1, w, reinterpret_cast<int *>(red_d));
             __syncthreads();
-            tpart = wrap_weight_scan<kT, kUniformW, kScanItems, true, kUniformW, kUniformW>(cs + 1, w, wd, a.w0, N, NM, (int)nmp_even,
-                                                                                            red_d, 0, 0.0, wd32, cs32 + 1, g32.mu, &cmax);
+            tpart = wrap_weight_scan<kT, kUniformW, kScanItems, true, kFilt, kFilt, false, unsigned short, (kFilt && !kUniformW)>(
+                cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d, 0, 0.0, wd32, cs32 + 1, g32.mu, &cmax, nullptr, nullptr, w32);
         }
 #pragma unroll
         for (int off = 16; off; off >>= 1) {
@@ -355,7 +366,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         __syncthreads();
         double T = 0.0;
         for (int k = 0; k < kW; ++k) T += red_d[kW + 1 + k];
-        if (kUniformW) {
+        if (kFilt) {
             float cm = 0.f;
             for (int k = 0; k < kW; ++k) cm = fmaxf(cm, __int_as_float(red_i[k]));
             g32.set_err(cm, NM);
@@ -403,11 +414,14 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         // gate + taps over the tables' tiles, widths ub-1 downwards; csb / wb / wdb are indexable by global offsets
         ExactView<false> view;
         view.cs = cs; view.wd = wd; view.dval = nullptr; view.sid = nullptr; view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
-        auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *cs32b, const float *wd32b, int ub) {
+        view.wval = nullptr; view.w = w;
+        auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *cs32b, const float *wd32b,
+                         const float *w32b, int ub) {
             const int tile_end = s_next[4];
-            if constexpr (kUniformW) {  // barrier-free gate + filter sweep (tlsb_device.cuh)
-                sweep_filter<kT, kBlock, false>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, cs32b, wd32b, a.tq32,
-                                                a.w0, T, g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats);
+            if constexpr (kFilt) {  // barrier-free gate + filter sweep (tlsb_device.cuh)
+                sweep_filter<kT, kBlock, false, kUniformW>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, cs32b, wd32b,
+                                                           a.tq32, a.w0, T, g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats,
+                                                           w32b, ea_scale);
                 return;
             }
             int g_next = wid;
@@ -502,11 +516,12 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 __syncthreads();  // phase A / the previous chunk are done with the staging area and the tables
                 if (tid == 0) {
                     const int len_cs = min(C, (int)cs_elems - a0);
-                    if (kUniformW) {
+                    if (kFilt) {
                         const int len_c32 = min(C, (int)cs4 - a0), len_32 = min(C, (int)nmp4 - a0);
-                        mbar_expect_tx(bar, 4u * (unsigned)(len_c32 + len_32));
+                        mbar_expect_tx(bar, 4u * (unsigned)(len_c32 + (kUniformW ? 1 : 2) * len_32));
                         bulk_copy_g2s(cs32_s, cs32 + a0, 4u * (unsigned)len_c32, bar);
                         bulk_copy_g2s(wd32_s, wd32 + a0, 4u * (unsigned)len_32, bar);
+                        if (!kUniformW) bulk_copy_g2s(w32_s, w32 + a0, 4u * (unsigned)len_32, bar);
                         fs->fq_fill = 0;
                         *ss = SweepShared{};
                     } else {
@@ -524,18 +539,18 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
                 __syncthreads();
                 mbar_wait(bar, parity);
                 parity ^= 1u;
-                sweep(cs_s - a0, w_s - a0, wd_s - a0, cs32_s - a0, wd32_s - a0, uT);
+                sweep(cs_s - a0, w_s - a0, wd_s - a0, cs32_s - a0, wd32_s - a0, w32_s - a0, uT);
             }
         }
         if (uT < uhi) {  // the widest widths: gate and taps read the scratch through L1/L2
             __syncthreads();  // the last chunk's sweep is done with the queue and the tables
             if (tid == 0) {
                 s_next[1] = 0; s_next[2] = 0; s_next[3] = 0;
-                if (kUniformW) { fs->fq_fill = 0; *ss = SweepShared{}; }
+                if (kFilt) { fs->fq_fill = 0; *ss = SweepShared{}; }
             }
             build_tables(0, 1 << 30, max(ulo, uT), uhi);
             __syncthreads();
-            sweep(cs, w, wd, cs32, wd32, uhi);
+            sweep(cs, w, wd, cs32, wd32, w32, uhi);
         }
 
         // ---- C. block arg-min with the reference's tie order ---------------------------
@@ -620,10 +635,12 @@ cudaError_t launch_search_tiled(const SearchArgs &a, int threads, bool uniform_w
     if (threads == 256) {
         if (uni && kb == 7) TLSB_GO((tlsb_search_tiled_kernel<256, true, 7>));
         else if (uni) TLSB_GO((tlsb_search_tiled_kernel<256, true, 5>));
+        else if (a.fq_cap > 0) TLSB_GO((tlsb_search_tiled_kernel<256, false, 5, true>));
         else TLSB_GO((tlsb_search_tiled_kernel<256, false, 5>));
     } else {
         if (uni && kb == 7) TLSB_GO((tlsb_search_tiled_kernel<512, true, 7>));
         else if (uni) TLSB_GO((tlsb_search_tiled_kernel<512, true, 5>));
+        else if (a.fq_cap > 0) TLSB_GO((tlsb_search_tiled_kernel<512, false, 5, true>));
         else TLSB_GO((tlsb_search_tiled_kernel<512, false, 5>));
     }
 }
