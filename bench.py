@@ -605,6 +605,7 @@ def secondary_records(args, peak_gbs, device, dist, rank, world, stream):
     * ``cfg5_multi_planet``  mask + rerun x3 on the 4-yr curve with three planets through ``search_planets(dist=)``
       (tests/test_multi_planet.py:33-40), periods AND T0-fit trial epochs dealt to the ranks;
     * ``power``        wall clock of the drop-in ``.power()`` on the headline workload, cold and warm (N = 1 only).
+    * ``per_point_dy`` the headline workload with per-point uncertainties (two correlations per tap), device-timed (N = 1 only).
 
     Each record carries its wall time and the shares of search / T0 fit / host work."""
     import warnings
@@ -765,6 +766,37 @@ def secondary_records(args, peak_gbs, device, dist, rank, world, stream):
                             "SDE": float(res.SDE), "period": float(res.period)}
         except Exception as exc:
             out["power"] = {"error": repr(exc)[:300]}
+        # ---- the headline workload with PER-POINT uncertainties (what light-curve files usually carry): two correlations
+        # per tap, fp32 gate + filter pass with exact fp64 finalists; one GPU, device-timed, oracle-checked
+        try:
+            from tls_b200 import native
+
+            t, y, dy, kw = workloads.lightcurve(args.workload, hetero=True)
+            inp = transitleastsquares(t, y, dy, verbose=False).prepare(verbose=False, **kw)
+            s = native.Searcher(device=device)
+            s.set_inputs(inp.t, inp.y, inp.dy, inp.templates, inp.params)
+            s.set_periods(inp.periods)
+            ms = []
+            for _ in range(1 + max(3, args.steps // 4)):
+                s.search_async()
+                got = s.results()
+                ms.append(s.kernel_ms)
+            lay = s.layout
+            s.close()
+            rec = {"workload": args.workload + " with per-point dy (workloads.lightcurve(hetero=True))", "periods": int(len(inp.periods)),
+                   "kernel_ms": float(np.mean(ms[1:])), "value": float(len(inp.periods) / (np.mean(ms[1:]) * 1e-3)), "unit": UNIT,
+                   "layout": lay}
+            if not args.no_cpu_baseline:
+                from oracle import oracle
+
+                sel = np.linspace(0, len(inp.periods) - 1, 48).astype(int)
+                w = oracle.search_periods_c(inp.t, inp.y, inp.dy, inp.periods[sel], inp.templates, inp.params)
+                fin = np.isfinite(w[0])
+                rec["parity"] = {"periods_checked": int(len(sel)), "rows_equal": bool(np.array_equal(got[1][sel], w[1])),
+                                 "chi2_max_rel_err": float(np.max(np.abs(got[0][sel][fin] - w[0][fin]) / np.abs(w[0][fin]))) if fin.any() else 0.0}
+            out["per_point_dy"] = rec
+        except Exception as exc:
+            out["per_point_dy"] = {"error": repr(exc)[:300]}
     return out if rank == 0 else None
 
 

@@ -146,7 +146,8 @@ def test_bad_arguments_raise():
         native.search_periods(g["t"][:2], g["y"][:2], g["dy"][:2], g["periods"], g["templates"], g["params"])
 
 
-@pytest.mark.parametrize("workload,hetero,count", [("cfg1", False, 400), ("cfg1_500ppm", True, 300), ("cfg3", False, 40)])
+@pytest.mark.parametrize("workload,hetero,count", [("cfg1", False, 400), ("cfg1_500ppm", True, 300), ("cfg3", False, 40),
+                                                    ("cfg1", True, 300), ("cfg3", True, 24)])
 def test_cuda_matches_c_oracle_on_seeded_inputs(workload, hetero, count):
     """Same seeded inputs into the CUDA path and the CPU oracle (oracle/ is the checker only)."""
     native = _native()
