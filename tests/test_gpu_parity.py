@@ -359,3 +359,31 @@ def test_one_call_async_upload_equals_the_three_setters_and_get_results_guards_i
         np.testing.assert_array_equal(a, b)
     s.close()
     s2.close()
+
+
+@pytest.mark.parametrize("hetero", [False, True])
+def test_resident_layout_with_one_big_cta_per_sm(hetero):
+    """A curve whose folded arrays fit shared memory once but not twice per SM (146 d @ 30 min, N = 7000) takes the
+    resident kernel as ONE 512-thread CTA per SM with the barrier-free ring schedule (tlsb_device.cuh: sweep_filter) -
+    with equal weights and with per-point dy.  Results against the C oracle (core.py:96-188)."""
+    native = _native()
+    from oracle import oracle
+    from tls_b200 import transitleastsquares, workloads
+
+    n = 7000
+    t = np.linspace(3.14, 3.14 + n / 48.0, n)
+    np.random.seed(11)
+    y = workloads.inject(t, 7.77, 3.14) + np.random.normal(0, 300e-6, n)
+    dy = 300e-6 * np.random.uniform(0.5, 2.0, n) if hetero else None
+    inp = transitleastsquares(t, y, dy, verbose=False).prepare(verbose=False)
+    periods = inp.periods[np.linspace(0, len(inp.periods) - 1, 60).astype(int)]
+    s = native.Searcher()
+    s.set_inputs(inp.t, inp.y, inp.dy, inp.templates, inp.params)
+    s.set_periods(periods)
+    s.search_async()
+    got = s.results()
+    lay = s.layout
+    s.close()
+    assert lay["path"] == "resident" and lay["threads"] == 512 and lay["ctas_per_sm"] == 1, lay
+    want = oracle.search_periods_c(inp.t, inp.y, inp.dy, periods, inp.templates, inp.params)
+    assert_search_parity(got[:3], dict(y=inp.y, chi2=want[0], row=want[1], depth=want[2]), rtol=RTOL, label="N=7000 resident 512x1")
