@@ -847,16 +847,22 @@ struct ExactView {
     int N;
     const double *wval;    // kGather, unequal weights: 1 / dy^2 per sample
     const double *w;       // !kGather, unequal weights: w per folded position
+    const unsigned *sid32; // kGather with 32-bit ids (tiled kernel: the sorted ids live in the CTA's global scratch), else NULL
+    __device__ __forceinline__ int id_at(int k) const
+    {
+        const int kk = k < N ? k : k - N;
+        return sid32 ? (int)__ldcg(sid32 + kk) : (int)sid[kk];
+    }
     __device__ __forceinline__ double wdv(int k) const
     {
-        if (kGather) return __dmul_rn(w0, __ldg(dval + sid[k < N ? k : k - N]));
+        if (kGather) return __dmul_rn(w0, __ldg(dval + id_at(k)));
         return wd[k];
     }
     // unequal weights: the weight and the product w*d of folded position k (the same product the fp64 arrays would hold)
     __device__ __forceinline__ void wpair(int k, double &wk, double &wdk) const
     {
         if (kGather) {
-            const int id = sid[k < N ? k : k - N];
+            const int id = id_at(k);
             wk = __ldg(wval + id);
             wdk = __dmul_rn(wk, __ldg(dval + id));
         } else {

@@ -488,6 +488,7 @@ Layout choose_layout(const tlsb_handle *h)
                         (size_t)(kMaxSegments + 2) * 4;
             best.scratch_per_cta = cs + (size_t)(narr - 1) * nmp_even * 8 +
                                    (h->uniform_w ? (cs4 + nmp4) * 4 : wfilter ? (cs4 + 2 * nmp4) * 4 : 0) + align16((size_t)N * 4);
+            const size_t list_base = best.scratch_per_cta;
             // on-chip sort: segments of S keys sorted in the chunk area; 1.5x head room over N / n_seg
             const char *oc = std::getenv("TLSB_ONCHIP_SORT");  // "0" disables (experiments)
             const size_t area = elem * (size_t)C;
@@ -497,8 +498,9 @@ Layout choose_layout(const tlsb_handle *h)
             if (!(oc && std::atoi(oc) == 0) && S >= 64 && S <= 65534 && ns >= 1 && ns <= kMaxSegments) {
                 best.seg_cap = (int)S;
                 best.n_seg = (int)ns;
-                best.scratch_per_cta += (size_t)ns * (size_t)S * 12 + 16;
+                best.scratch_per_cta += (size_t)ns * (size_t)S * 4 + 16;  // lists of sample ids
             }
+            best.scratch_per_cta = std::max(best.scratch_per_cta, list_base + align16((size_t)N * 4) + 16);  // sorted ids of a fallback sort
             best.scratch_per_cta = (best.scratch_per_cta + 255) & ~(size_t)255;
             return best;
         }

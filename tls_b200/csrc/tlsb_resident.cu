@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         ExactView<true> view;
         if (kFilter) {
             view.cs = cs64g; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
-            view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N; view.wval = a.wval; view.w = nullptr;
+            view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N; view.wval = a.wval; view.w = nullptr; view.sid32 = nullptr;
         }
         if constexpr (kDynamic) {
             // B1 + B2 as one barrier-free sweep: warps switch between gating tiles and taking batches of survivors

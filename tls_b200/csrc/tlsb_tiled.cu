@@ -23,11 +23,14 @@ namespace {
 // continued from the previous segment, and the first M samples stashed behind position N for the
 // wrap (core.py:126-132).  Returns false (nothing consumed) if a segment overflows its capacity -
 // strongly clustered phases - and the caller then sorts in global scratch instead.
+#ifndef TLSB_STCS
+#define TLSB_STCS 1  // streaming stores for the fp64 arrays of the filter layouts
+#endif
 template <int kT, bool kUniformW, bool kFilt>
 __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsigned char *area, int *cnt,
-                                             double *gkey, unsigned *gid, double *cs1, double *w, double *wd, float *wd32,
+                                             unsigned *gid, double *cs1, double *w, double *wd, float *wd32,
                                              int nmp_even, double *red_d, double &tpart_out, float *cs32_1, double mu,
-                                             float &cmax_out, float *w32)
+                                             float &cmax_out, float *w32, unsigned *gsid)
 {
 #ifndef TLSB_SEG_RANK_U
 #define TLSB_SEG_RANK_U 4
@@ -81,8 +84,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
             if (sg >= 0) {
                 const int slot = base + __popc(peers & lt_mask);
                 if (slot < S) {
-                    gkey[(size_t)sg * S + slot] = ph;
-                    gid[(size_t)sg * S + slot] = (unsigned)k;
+                    gid[(size_t)sg * S + slot] = (unsigned)k;  // the list holds ids only: the phase is folded again from t[id]
                 }
             }
         }
@@ -104,13 +106,11 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     for (int j = 0; j < ns; ++j) {
         const int nj = cnt[j];
         if (nj == 0) continue;
-        const double *lk = gkey + (size_t)j * S;
         const unsigned *li = gid + (size_t)j * S;
         for (int b = tid; b <= S; b += kT) Hw[b] = 0u;  // entries 0 .. 2 S + 1
         if (j + 1 < ns) {  // the next segment's lists were written a while ago and may have left L2: fetch them back now
             const int nn = cnt[j + 1];
-            const char *pk = reinterpret_cast<const char *>(lk + S), *pi = reinterpret_cast<const char *>(li + S);
-            for (int b = tid * 128; b < nn * 8; b += kT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + b));
+            const char *pi = reinterpret_cast<const char *>(li + S);
             for (int b = tid * 128; b < nn * 4; b += kT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + b));
         }
         __syncthreads();
@@ -121,9 +121,14 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
 #pragma unroll
         for (int i = 0; i < kSegPerThread; ++i) {
             const int q = tid + i * kT;
-            ph[i] = q < nj ? lk[q] : 0.0;
             id[i] = q < nj ? li[q] : 0u;
         }
+        // the same fold as the partition pass, bit for bit (time stamps from L2: 4 instead of 12 bytes per key went through
+        // the lists - cfg-2: 4.91 -> 3.58 MB of DRAM traffic per period and 2 % less time)
+#pragma unroll
+        for (int i = 0; i < kSegPerThread; ++i) ph[i] = __ldg(a.t + id[i]);
+#pragma unroll
+        for (int i = 0; i < kSegPerThread; ++i) ph[i] = fold_phase(ph[i], r);
 #pragma unroll
         for (int i = 0; i < kSegPerThread; ++i) {
             if (tid + i * kT < nj) {
@@ -181,6 +186,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
                 if (q0 + u * kT < nj) {
                     val_s[rank[u]] = v1[u];
                     if (!kUniformW) wv_s[rank[u]] = v2[u];
+                    if (kFilt) __stcs(gsid + off + rank[u], sidq[u]);  // the exact evaluations gather w, d through these
                 }
             }
         }
@@ -190,10 +196,10 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
             const double d = val_s[q];
             const double wv = kUniformW ? a.w0 : wv_s[q];
             const double x = wv * d;
-            wd[pos] = x;
+            if (!kFilt) wd[pos] = x;          // (filter layouts: finalists rebuild w*d from the sorted ids)
             if (kFilt) wd32[pos] = (float)x;  // the filter pass's samples
             tpart = fma(x, d, tpart);
-            if (!kUniformW) w[pos] = wv;
+            if (!kUniformW && !kFilt) w[pos] = wv;
             if (kFilt && !kUniformW) w32[pos] = (float)wv;
             if (pos < M) {
                 cs1[N + pos] = d;
@@ -204,7 +210,9 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
         block_inclusive_scan<kT, double, kSegScanItems>(val_s, nj, red_d);
         for (int q = tid; q < nj; q += kT) {
             const double c = carry + val_s[q];
-            cs1[off + q] = c;
+            // filter layouts: the fp64 sums are read again only by the rare exact evaluations - streaming stores keep them
+            // from pushing the fp32 arrays and the segment lists (re-read within the period) out of L2
+            if (kFilt && TLSB_STCS) __stcs(cs1 + off + q, c); else cs1[off + q] = c;
             if (kFilt) {  // the detrended fp32 copy the gate and the screen read (tlsb_device.cuh: fp32 gate)
                 const float c32 = (float)fma(-(double)(off + q + 1), mu, c);
                 cs32_1[off + q] = c32;
@@ -217,7 +225,7 @@ __device__ __forceinline__ bool sort_on_chip(const SearchArgs &a, double r, unsi
     }
     // positions N .. NM-1 hold the wrapped d: continue the cumulative sum, weight them, zero the slack
     float cmax2 = 0.f;
-    wrap_weight_scan<kT, kUniformW, kSegScanItems, true, kFilt, kFilt, false, unsigned short, (kFilt && !kUniformW)>(
+    wrap_weight_scan<kT, kUniformW, kSegScanItems, !kFilt, kFilt, kFilt, false, unsigned short, (kFilt && !kUniformW)>(
         cs1, w, wd, a.w0, N, NM, nmp_even, red_d, N, carry, wd32, cs32_1, mu, &cmax2, nullptr, nullptr, w32);
     tpart_out = tpart;
     cmax_out = fmaxf(cmax, cmax2);
@@ -283,8 +291,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
     int *ch_tiles = ch_hi + nU;    // [nU]
     int *seg_cnt = ch_tiles + nU;  // [kMaxSegments + 1] on-chip sort: keys per phase segment
     // segment lists of the on-chip sort, behind the arrays above
-    double *gkey = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(sid) + (((size_t)N * 4 + 15) & ~(size_t)15));
-    unsigned *gid = reinterpret_cast<unsigned *>(gkey + (size_t)a.n_seg * a.seg_cap);
+    // (at least N entries: a period whose sort falls back to the global scratch keeps its sorted ids here)
+    unsigned *gid = reinterpret_cast<unsigned *>(reinterpret_cast<unsigned char *>(sid) + (((size_t)N * 4 + 15) & ~(size_t)15));
 
     for (int k = tid; k < nU * (int)(sizeof(WidthRec) / 4); k += kT)
         reinterpret_cast<int *>(rec)[k] = reinterpret_cast<const int *>(a.rec)[k];
@@ -344,14 +352,15 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         }
         bool on_chip = false;
         if (a.seg_cap > 0)
-            on_chip = sort_on_chip<kT, kUniformW, kFilt>(a, r, reinterpret_cast<unsigned char *>(cs_s), seg_cnt, gkey, gid,
-                                                         cs + 1, w, wd, wd32, (int)nmp_even, red_d, tpart, cs32 + 1, g32.mu, cmax, w32);
+            on_chip = sort_on_chip<kT, kUniformW, kFilt>(a, r, reinterpret_cast<unsigned char *>(cs_s), seg_cnt, gid,
+                                                         cs + 1, w, wd, wd32, (int)nmp_even, red_d, tpart, cs32 + 1, g32.mu, cmax, w32, sid);
         if (!on_chip) {  // clustered phases (or no room for segments): sort in the global scratch
             if (tid == 0 && a.seg_cap > 0) atomicAdd(a.counter + 4, 1);
-            fold_sort_gather<kT, unsigned, !kUniformW, false, 8>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval,
-                                                                 cs + 1, w, reinterpret_cast<int *>(red_d));
+            // (filter layouts: the sorted ids go to the segment lists' memory, which this period does not use)
+            fold_sort_gather<kT, unsigned, !kUniformW, false, 8, kScanItems, kFilt>(a.t, 0.0, r, N, NB, H, skey, sid, a.dval, a.wval,
+                                                                                    cs + 1, w, reinterpret_cast<int *>(red_d), gid);
             __syncthreads();
-            tpart = wrap_weight_scan<kT, kUniformW, kScanItems, true, kFilt, kFilt, false, unsigned short, (kFilt && !kUniformW)>(
+            tpart = wrap_weight_scan<kT, kUniformW, kScanItems, !kFilt, kFilt, kFilt, false, unsigned short, (kFilt && !kUniformW)>(
                 cs + 1, w, wd, a.w0, N, NM, (int)nmp_even, red_d, 0, 0.0, wd32, cs32 + 1, g32.mu, &cmax, nullptr, nullptr, w32);
         }
 #pragma unroll
@@ -412,14 +421,15 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
         };
 
         // gate + taps over the tables' tiles, widths ub-1 downwards; csb / wb / wdb are indexable by global offsets
-        ExactView<false> view;
-        view.cs = cs; view.wd = wd; view.dval = nullptr; view.sid = nullptr; view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
-        view.wval = nullptr; view.w = w;
+        // finalists: fp64 cumulative sums from the scratch, w and w*d rebuilt from the light curve through the sorted ids
+        ExactView<true> view;
+        view.cs = cs; view.wd = nullptr; view.dval = a.dval; view.sid = nullptr; view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
+        view.wval = a.wval; view.w = nullptr; view.sid32 = on_chip ? sid : gid;
         auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *cs32b, const float *wd32b,
                          const float *w32b, int ub) {
             const int tile_end = s_next[4];
             if constexpr (kFilt) {  // barrier-free gate + filter sweep (tlsb_device.cuh)
-                sweep_filter<kT, kBlock, false, kUniformW>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, cs32b, wd32b,
+                sweep_filter<kT, kBlock, true, kUniformW>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, cs32b, wd32b,
                                                            a.tq32, a.w0, T, g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats,
                                                            w32b, ea_scale);
                 return;
