@@ -13,7 +13,11 @@ trial period of the grid) over one synthetic light curve:
   ``tlsb_search_periods`` with HOST buffers (pinned), host<->device copies inside the
   timed region, wall clock bracketed by device synchronisation.  With N > 1 the host buffers
   go up through the handle setters of the same C ABI every step, the records are
-  all-gathered on the device and every rank copies the whole result back once.
+  all-gathered on the device and every rank copies the whole result back once.  Measured with
+  ``TLSB_MEMO=0`` (the library re-derives the template arrays and re-runs the plan kernel in every
+  step); the figure with the memo on rides along as ``e2e.memo_on``.
+* ``secondary`` — strong scaling of the whole cfg-2 grid, the cfg-5 multi-planet search and the cfg-4 batch at the
+  same N; at N = 1 also ``.power()`` cold / warm and the headline workload with per-point uncertainties.
 * multi-GPU  — weak scaling: every rank searches ``P`` periods of the same light curve; the
   job's grid is the reference's period grid oversampled N x (``oversampling_factor = 3 N``),
   dealt to the ranks round-robin (period k -> rank k mod N), one all-gather at the end of

@@ -29,6 +29,11 @@
 //        cumulative-sum reads (mean_i > transit_depth_min) and appends the surviving blocks of
 //        kBlock neighbouring candidates to a CTA-wide queue; B2 runs the register-blocked,
 //        software-pipelined tap loop on full warps of survivors.
+//        Filter layouts (everything but the streaming path): the gate reads detrended fp32
+//        cumulative sums (a superset passes: Gate32), B2 accumulates the correlation(s) in fp32
+//        with rigorous error bounds (tap_block32 / tap_block32w), a screen and exact bounds
+//        discard what cannot be the minimum, and the few candidates left are evaluated in fp64
+//        by whole warps (eval_exact_warp): results are bit-identical to an all-fp64 evaluation.
 //     C. lexicographic (chi2, width order, offset) block arg-min = the reference's strict-<
 //        tie rules (core.py:71, :183), sentinel N / +inf handling (core.py:46, :139-140).
 //

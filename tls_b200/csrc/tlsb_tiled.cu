@@ -1,13 +1,15 @@
 // tlsb_tiled.cu — tlsb_search_tiled_kernel: light curves too long for shared memory.
 // ------------------------------------------------------------------------------------------
-// Tiled path (light curves too long for the resident path): phase A runs in a per-CTA global
-// scratch; phase B walks the folded curve in POSITION CHUNKS.  One elected thread stages
-// cs[a0, a0+C), wd[a0, a0+C) (and w) of the chunk into shared memory with 1-D bulk async
-// copies (TMA, cp.async.bulk -> mbarrier complete_tx), then the same gate / survivor queue /
-// register-blocked tap loop as the resident kernel runs from shared memory for every
-// candidate block that STARTS inside [a0, a0+TP), TP = C - (widest admissible window + the
-// tap loop's overshoot).  Each folded sample is read from L2 once per chunk instead of twice
-// per admissible width.
+// Tiled path (light curves too long for the resident path): phase A sorts the fold on chip one
+// phase segment at a time and writes the folded arrays to a per-CTA global scratch; phase B walks
+// the folded curve in POSITION CHUNKS.  One elected thread stages cs32[a0, a0+C) and
+// wd32[a0, a0+C) (and w32 with per-point dy; cs, w, w*d in fp64 for the all-fp64 kernels) of the
+// chunk into shared memory with 1-D bulk async copies (TMA, cp.async.bulk -> mbarrier
+// complete_tx), then the same fp32 gate / survivor ring / fp32 filter pass as the resident kernel
+// runs from shared memory for every candidate block that STARTS inside [a0, a0+TP),
+// TP = C - (widest admissible window + the tap loop's overshoot); finalists are evaluated in fp64
+// from the scratch (cumulative sums) and the light curve (w, d through the sorted sample ids).
+// Each folded sample is read from L2 once per chunk instead of twice per admissible width.
 // ------------------------------------------------------------------------------------------
 #include "tlsb_device.cuh"
 
