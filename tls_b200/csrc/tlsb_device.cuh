@@ -839,9 +839,10 @@ __device__ __forceinline__ double chi2_value(double T, double D, double Aq, doub
     return __fma_rn(D, __fma_rn(D, Aq, -2.0 * B), T);  // T + D (D Aq - 2 B), core.py:67-70 after the algebra of DESIGN.md §3
 }
 
-// What the exact evaluation of a finalist reads: cumulative sums, the fp64 products w*d (resident kernel: rebuilt
-// from the sorted sample ids, w0 * d[id], the same product the folded array held; tiled kernel: the CTA's scratch).
-template <bool kGather>
+// What the exact evaluation of a finalist reads: cumulative sums, the fp64 products w*d.  kGather = 1 (resident kernel):
+// rebuilt from the sorted sample ids in shared memory (u16), w0 * d[id], the same product a folded fp64 array would
+// hold; kGather = 2 (tiled kernel): the same through 32-bit ids in the CTA's global scratch; kGather = 0: fp64 arrays.
+template <int kGather>
 struct ExactView {
     const double *cs;      // cumulative sums, indexable by the global offset
     const double *wd;      // !kGather: w*d per folded position
@@ -852,11 +853,11 @@ struct ExactView {
     int N;
     const double *wval;    // kGather, unequal weights: 1 / dy^2 per sample
     const double *w;       // !kGather, unequal weights: w per folded position
-    const unsigned *sid32; // kGather with 32-bit ids (tiled kernel: the sorted ids live in the CTA's global scratch), else NULL
+    const unsigned *sid32; // kGather == 2: 32-bit ids (tiled kernel: the sorted ids live in the CTA's global scratch)
     __device__ __forceinline__ int id_at(int k) const
     {
         const int kk = k < N ? k : k - N;
-        return sid32 ? (int)__ldcg(sid32 + kk) : (int)sid[kk];
+        return kGather == 2 ? (int)__ldcg(sid32 + kk) : (int)sid[kk];
     }
     __device__ __forceinline__ double wdv(int k) const
     {
@@ -883,7 +884,7 @@ struct ExactView {
 // This is the ONLY place the equal-weights paths evaluate chi2 in fp64, so results do not depend on what the
 // filter let through.
 // kUW = false (unequal weights): the quadratic term A = sum_j q_j^2 w_{i+j} is accumulated the same way.
-template <bool kGather, bool kUW = true>
+template <int kGather, bool kUW = true>
 __device__ __noinline__ void eval_exact_warp(const ExactView<kGather> &v, const WidthRec *rec, int c0, int rr, int u,
                                              Best &best)
 {
@@ -1079,7 +1080,7 @@ __device__ __noinline__ float bound_one_w(const double *cs64, int i, int W, doub
 }
 
 // What the cold paths of a sweep need, gathered once per sweep (lives in local memory)
-template <bool kGather>
+template <int kGather>
 struct FilterCtx {
     ExactView<kGather> view;
     const WidthRec *rec;
@@ -1095,7 +1096,7 @@ struct FilterCtx {
 // Finalists of one batch (bit rr of `fin`, lower bounds rounded down to fp32) go to the finalist queue once more
 // checked against the threshold as it is NOW; the bound travels with them and is checked a last time before the
 // exact evaluation.  All 32 lanes must call.  Queue full (rare): the warp evaluates the leftovers on the spot.
-template <int kBlock, bool kGather, bool kUW = true>
+template <int kBlock, int kGather, bool kUW = true>
 __device__ __noinline__ void warp_push(const FilterCtx<kGather> &cx, int fin, int c0, int u, float l0, float l1, float l2,
                                        float l3, float l4, float l5, float l6, Best &best)
 {
@@ -1131,7 +1132,7 @@ __device__ __noinline__ void warp_push(const FilterCtx<kGather> &cx, int fin, in
 // The queued finalists, one per warp at a time (call after a barrier, all threads of the CTA): each is checked
 // against the current threshold once more (most were queued while it was still settling), evaluated in fp64, and
 // its exact chi2 tightens the threshold for the rest.
-template <int kT, bool kGather, bool kUW = true>
+template <int kT, int kGather, bool kUW = true>
 __device__ __forceinline__ void drain_finalists(const FilterCtx<kGather> &cx, Best &best)
 {
     constexpr int kW = kT / 32;
@@ -1162,7 +1163,7 @@ struct Pending {
         for (int rr = 0; rr < kBlock; ++rr) lo[rr] = 0.f;
     }
     __device__ __forceinline__ float at(int k) const { return k < kBlock ? lo[k < kBlock ? k : 0] : 0.f; }
-    template <bool kGather, bool kUW = true>
+    template <int kGather, bool kUW = true>
     __device__ __forceinline__ void push(const FilterCtx<kGather> &cx, Best &best)  // all 32 lanes must call
     {
         if (__any_sync(kFull, fin != 0))
@@ -1173,7 +1174,7 @@ struct Pending {
 
 // One batch of survivor blocks (one per lane, `have`): fp32 correlation, fp32 screen, exact gate + exact bounds for
 // what the screen lets through; then the PREVIOUS batch's finalists are pushed and this batch's become pending.
-template <int kBlock, bool kGather, bool kUW = true>
+template <int kBlock, int kGather, bool kUW = true>
 __device__ __forceinline__ void tap_batch(bool have, int2 e, const FilterCtx<kGather> &cx, const float *cs32, const float *wd32,
                                           const float *__restrict__ tq32, double w0, double T, double eb_scale, float slopTf,
                                           Threshold &th, Pending<kBlock> &pend, Best &best, const float *w32 = nullptr)
@@ -1261,7 +1262,7 @@ struct SweepShared {
 // ub-1 and cover its candidates [t_lo, t_hi), and so on downwards.  Finalists are pushed one batch late, so that
 // their bounds meet a threshold every active warp has contributed to.  Ends with the finalist queue drained
 // (contains barriers: all threads of the CTA must call).  cs / wd32 must be indexable by global offsets.
-template <int kT, int kBlock, bool kGather, bool kUW = true>
+template <int kT, int kBlock, int kGather, bool kUW = true>
 __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int qmask, int tile_end, int ub, const int *t_lo,
                                              const int *t_hi, const int *t_tiles, const WidthRec *rec, const float *cs32,
                                              const float *wd32, const float *__restrict__ tq32, double w0, double T,
@@ -1390,7 +1391,7 @@ __device__ __forceinline__ void sweep_filter(SweepShared *ss, int2 *queue, int q
 // The same work with the classic schedule, for layouts with two CTAs per SM (the other CTA fills this one's barrier
 // waits, and short batches make the ring's bookkeeping the larger cost): one ROUND of the survivor queue, filled by
 // the gate before a barrier; warps take batches of 32 entries until the queue is empty, then drain the finalists.
-template <int kT, int kBlock, bool kGather, bool kUW = true>
+template <int kT, int kBlock, int kGather, bool kUW = true>
 __device__ __forceinline__ void filter_round(const int2 *queue, int qfill, int *q_head, const WidthRec *rec, const float *cs32,
                                              const float *wd32, const float *__restrict__ tq32, double w0, double T,
                                              const Gate32 &g32, double eb_scale, FilterShared *fs, int2 *fq, float *fq_lo,

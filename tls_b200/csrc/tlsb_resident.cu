@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
         best.i = -1;
 
         constexpr bool kDynamic = kFilter && kT > 256;  // one big CTA per SM: nothing else would fill a barrier wait
-        ExactView<true> view;
+        ExactView<1> view;
         if (kFilter) {
             view.cs = cs64g; view.wd = nullptr; view.dval = a.dval; view.sid = reinterpret_cast<const unsigned short *>(sid_sorted);
             view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N; view.wval = a.wval; view.w = nullptr; view.sid32 = nullptr;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
             // B1 + B2 as one barrier-free sweep: warps switch between gating tiles and taking batches of survivors
             // (fp32 correlation, screen, bounds); finalists are evaluated in fp64 by whole warps at the end
             const int tile_total = rec[ulo].cum + rec[ulo].tiles - rec[uhi - 1].cum;
-            sweep_filter<kT, kBlock, true, kUniformW>(ss, queue, a.qcap - 1, tile_total, uhi, t_lo, t_hi, t_tiles, rec, cs32, wd32, a.tq32,
+            sweep_filter<kT, kBlock, 1, kUniformW>(ss, queue, a.qcap - 1, tile_total, uhi, t_lo, t_hi, t_tiles, rec, cs32, wd32, a.tq32,
                                                       a.w0, T, g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats, w32, ea_scale);
         } else {
             const int tile_end = rec[ulo].cum + rec[ulo].tiles;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kT, (kT <= 384 ? 2 : 1)) tlsb_search_kernel(co
                 const bool more = s_next[1] != 0;
                 // B2
                 if constexpr (kFilter) {
-                    filter_round<kT, kBlock, true, kUniformW>(queue, qfill, &s_next[3], rec, cs32, wd32, a.tq32, a.w0, T, g32, eb_scale, fs,
+                    filter_round<kT, kBlock, 1, kUniformW>(queue, qfill, &s_next[3], rec, cs32, wd32, a.tq32, a.w0, T, g32, eb_scale, fs,
                                                               fq, fq_lo, a.fq_cap, view, best, a.stats, w32, ea_scale);
                 } else
                 for (;;) {

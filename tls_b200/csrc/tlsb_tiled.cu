@@ -424,14 +424,14 @@ __global__ void __launch_bounds__(kT, (kT <= 256 ? 2 : 1)) tlsb_search_tiled_ker
 
         // gate + taps over the tables' tiles, widths ub-1 downwards; csb / wb / wdb are indexable by global offsets
         // finalists: fp64 cumulative sums from the scratch, w and w*d rebuilt from the light curve through the sorted ids
-        ExactView<true> view;
+        ExactView<2> view;
         view.cs = cs; view.wd = nullptr; view.dval = a.dval; view.sid = nullptr; view.tq = a.tq; view.w0 = a.w0; view.T = T; view.N = N;
         view.wval = a.wval; view.w = nullptr; view.sid32 = on_chip ? sid : gid;
         auto sweep = [&](const double *csb, const double *wb, const double *wdb, const float *cs32b, const float *wd32b,
                          const float *w32b, int ub) {
             const int tile_end = s_next[4];
             if constexpr (kFilt) {  // barrier-free gate + filter sweep (tlsb_device.cuh)
-                sweep_filter<kT, kBlock, true, kUniformW>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, cs32b, wd32b,
+                sweep_filter<kT, kBlock, 2, kUniformW>(ss, queue, a.qcap - 1, tile_end, ub, ch_lo, ch_hi, ch_tiles, rec, cs32b, wd32b,
                                                            a.tq32, a.w0, T, g32, eb_scale, fs, fq, fq_lo, a.fq_cap, view, best, a.stats,
                                                            w32b, ea_scale);
                 return;
