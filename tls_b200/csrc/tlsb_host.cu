@@ -316,9 +316,14 @@ Layout choose_layout(const tlsb_handle *h)
 {
     Layout best;
     const int N = h->N;
-    // block size R: 7 candidates per lane when all weights are equal, 5 with two correlations (registers)
-    const char *kbe = std::getenv("TLSB_BLOCK");  // experiments: force 5
-    const int kb_pref = (h->uniform_w && !(kbe && std::atoi(kbe) == 5)) ? 7 : 5;
+    // block size R: 7 candidates per lane in the filter layouts (one or two fp32 correlations), 5 in the all-fp64 kernels
+    // of unequal weights (two fp64 correlations: registers)
+    const char *kbe = std::getenv("TLSB_BLOCK");   // experiments: 5 forces R = 5 with equal weights
+    const char *wke = std::getenv("TLSB_WBLOCK");  // experiments: 5 forces R = 5 in the filter layouts of unequal weights
+    const int kb_w = (wke && std::atoi(wke) == 5) ? 5 : 7;
+    const char *wf = std::getenv("TLSB_WFILTER");  // "0": unequal weights keep the all-fp64 kernels (experiments / A-B runs)
+    const bool wfilter = !h->uniform_w && !(wf && std::atoi(wf) == 0);  // unequal weights with the fp32 gate + filter pass
+    const int kb_pref = h->uniform_w ? ((kbe && std::atoi(kbe) == 5) ? 5 : 7) : 5;
     best.kb = kb_pref;
     if (N < 65536 && h->path_mode <= 1 && h->uniform_w && kb_pref == 7) {
         // equal weights: fp32 filter pass; the folded curve costs 8 (cs) + 4 (w*d in fp32) + 2 (ids) bytes per sample
@@ -346,9 +351,8 @@ Layout choose_layout(const tlsb_handle *h)
             return best;
         }
     }
-    const char *wf = std::getenv("TLSB_WFILTER");  // "0": unequal weights keep the all-fp64 kernels (experiments / A-B runs)
-    if (N < 65536 && h->path_mode <= 1 && !h->uniform_w && !(wf && std::atoi(wf) == 0)) {
-        // unequal weights: fp32 gate + two fp32 correlations (R = 5); cs32, wd32, w32 and the sorted ids stay on chip
+    if (N < 65536 && h->path_mode <= 1 && wfilter) {
+        // unequal weights: fp32 gate + two fp32 correlations; cs32, wd32, w32 and the sorted ids stay on chip
         const int tries[5][5] = {{256, 2, 3584, 832, 1}, {256, 2, 3072, 512, 1}, {256, 2, 3072, 512, 2}, {512, 1, 8192, 2048, 1},
                                  {512, 1, 4096, 1024, 1}};
         const int cs_elems = (N + h->M + 2) & ~1;
@@ -357,7 +361,7 @@ Layout choose_layout(const tlsb_handle *h)
             const size_t bytes = resident_filter_smem_bytes(N, h->M, h->pad, h->nU, t[2], t[3], t[0], NB, false);
             if (bytes > h->max_smem) continue;
             if ((bytes + 1024) * (size_t)t[1] > h->smem_per_sm) continue;
-            best.kb = 5;
+            best.kb = kb_w;  // R = 5 -> 7: cfg-1 at 500 ppm with dy 12.3 -> 11.0 ms (no spills at 128 registers)
             best.resident = true;
             best.threads = t[0];
             best.ctas_per_sm = t[1];
@@ -400,15 +404,15 @@ Layout choose_layout(const tlsb_handle *h)
     const int narr = h->uniform_w ? 2 : 3;
     // bytes a folded sample takes in a staged chunk: detrended cs in fp32 (4) + w*d in fp32 (4) with equal weights
     // (fp32 gate + filter pass), cs + w + w*d in fp64 otherwise
-    const bool wfilter = !h->uniform_w && !(wf && std::atoi(wf) == 0);  // unequal weights with the fp32 gate + filter pass
     const bool filt = h->uniform_w || wfilter;
+    const int kb_t = wfilter ? kb_w : kb_pref;  // tiled layouts (R = 5 -> 7 with unequal weights: cfg-3 with dy 54.6 -> 45.5 ms)
     const size_t elem = h->uniform_w ? 8 : wfilter ? 12 : 24;
     const size_t nmp4 = (NMP + 3) & ~(size_t)3;
     const size_t cs4 = (NM + 2 + 3) & ~(size_t)3;
     const int fq_cap = filt ? 1024 : 0;
     int need_max = 0, need5 = 0;
     for (const WidthRec &wr : h->recs) {
-        need_max = std::max(need_max, window_need(wr.W, wr.X, kb_pref));
+        need_max = std::max(need_max, window_need(wr.W, wr.X, kb_t));
         need5 = std::max(need5, window_need(wr.W, wr.X, 5));
     }
     const char *force = std::getenv("TLSB_TILED");  // "0": never, "256"/"512": force that CTA size (experiments)
@@ -428,7 +432,7 @@ Layout choose_layout(const tlsb_handle *h)
             const bool exact_cap = h->chunk_cap < 0;  // tests: cap the chunk exactly; widths that do not fit take the L2 pass
             if (h->chunk_cap > 0) C = std::min<long long>(C, std::max<long long>(h->chunk_cap, need_max + 64) & ~3LL);
             if (exact_cap) C = std::min<long long>(C, (long long)(-h->chunk_cap) & ~3LL);
-            int kb = kb_pref, n_tiled = h->nU;
+            int kb = kb_t, n_tiled = h->nU;
             long long TP = 0;
             bool fits = C > need5;
             if (fits) {

@@ -398,11 +398,13 @@ cudaError_t launch_search_resident(const SearchArgs &a, int threads, bool reside
         if (threads == 256) {
             if (uni && kb == 7) TLSB_GO((tlsb_search_kernel<256, true, true, 7>));
             else if (uni) TLSB_GO((tlsb_search_kernel<256, true, true, 5>));
+            else if (a.fq_cap > 0 && kb == 7) TLSB_GO((tlsb_search_kernel<256, true, false, 7, true>));
             else if (a.fq_cap > 0) TLSB_GO((tlsb_search_kernel<256, true, false, 5, true>));
             else TLSB_GO((tlsb_search_kernel<256, true, false, 5>));
         } else {
             if (uni && kb == 7) TLSB_GO((tlsb_search_kernel<512, true, true, 7>));
             else if (uni) TLSB_GO((tlsb_search_kernel<512, true, true, 5>));
+            else if (a.fq_cap > 0 && kb == 7) TLSB_GO((tlsb_search_kernel<512, true, false, 7, true>));
             else if (a.fq_cap > 0) TLSB_GO((tlsb_search_kernel<512, true, false, 5, true>));
             else TLSB_GO((tlsb_search_kernel<512, true, false, 5>));
         }

@@ -647,11 +647,13 @@ cudaError_t launch_search_tiled(const SearchArgs &a, int threads, bool uniform_w
     if (threads == 256) {
         if (uni && kb == 7) TLSB_GO((tlsb_search_tiled_kernel<256, true, 7>));
         else if (uni) TLSB_GO((tlsb_search_tiled_kernel<256, true, 5>));
+        else if (a.fq_cap > 0 && kb == 7) TLSB_GO((tlsb_search_tiled_kernel<256, false, 7, true>));
         else if (a.fq_cap > 0) TLSB_GO((tlsb_search_tiled_kernel<256, false, 5, true>));
         else TLSB_GO((tlsb_search_tiled_kernel<256, false, 5>));
     } else {
         if (uni && kb == 7) TLSB_GO((tlsb_search_tiled_kernel<512, true, 7>));
         else if (uni) TLSB_GO((tlsb_search_tiled_kernel<512, true, 5>));
+        else if (a.fq_cap > 0 && kb == 7) TLSB_GO((tlsb_search_tiled_kernel<512, false, 7, true>));
         else if (a.fq_cap > 0) TLSB_GO((tlsb_search_tiled_kernel<512, false, 5, true>));
         else TLSB_GO((tlsb_search_tiled_kernel<512, false, 5>));
     }
