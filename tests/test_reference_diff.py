@@ -274,3 +274,34 @@ def test_oracle_spectra_and_t0_fit_against_the_reference_on_random_inputs(ref):
                                    T0_fit_margin=margin, show_progress_bar=False, verbose=False)
             got = oracle.final_T0_fit_numpy(signal.copy(), depth, t, y, dy.copy(), period, margin)[0]
         assert got == want, (case, got, want)
+
+
+def test_oracle_against_the_numba_search_on_the_gpu_fuzz_cases(ref):
+    """The randomised GPU test (tests/test_gpu_fuzz.py) compares the CUDA search with the C oracle on the GPU box, where
+    the reference does not exist.  Here, where it does, the SAME light curves and periods go through the reference's own
+    numba ``core.search_period`` (core.py:96-188) and the oracle: rows exact (ties in value excepted, as in the GPU test),
+    chi2 / depth to 1e-9.  Together the two tests tie the CUDA results on those inputs to the unmodified reference."""
+    from transitleastsquares.core import search_period
+
+    import test_gpu_fuzz
+    from oracle import oracle
+
+    checked = 0
+    for seed in range(28):  # the generator is deterministic per seed
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            inp, periods = test_gpu_fuzz._case(seed)
+        periods = periods[:: max(1, len(periods) // 12)]
+        chi2, row, depth = oracle.search_periods_c(inp.t, inp.y, inp.dy, periods, inp.templates, inp.params)
+        for k, p in enumerate(periods):
+            out = search_period(p, inp.t, inp.y, inp.dy, lc_arr=inp.lc_arr, lc_cache_overview=inp.overview, **inp.params)
+            if np.isfinite(out[1]):
+                np.testing.assert_allclose(chi2[k], out[1], rtol=1e-9, err_msg="seed %d period %r" % (seed, p))
+                tie = abs(chi2[k] - out[1]) <= 1e-13 * abs(out[1])
+                assert int(out[2]) == int(row[k]) or tie, (seed, p, out, chi2[k], row[k])
+                if int(out[2]) == int(row[k]):
+                    np.testing.assert_allclose(depth[k], out[3], rtol=1e-9, atol=1e-15)
+            else:
+                assert chi2[k] == out[1] and int(out[2]) == int(row[k])
+            checked += 1
+    assert checked >= 300
